@@ -1,0 +1,988 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked into, imported by or called from the product
+// path (scann-rust_b200/, libscann_b200.so).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library.
+//
+// CPU restatement (C++17) of the batched-search hot path of sunbains/scann-rust, following the
+// reference's arithmetic order exactly.  Every function cites the reference
+// file:line it restates (paths relative to /root/reference).
+//
+// Parity pinning: the reference is pure Rust and cannot be compiled in this image (no cargo/rustc),
+// and it ships no golden-vector files.  This oracle is pinned against every known-answer test the
+// reference's own test modules hold for the path (tests/test_oracle_kat.py lists them one by one).
+// End-to-end outputs of the reference itself could not be generated here: beyond those KATs the
+// parity is "pinned by KATs only".  Tie order inside exact-distance ties (BinaryHeap drain order,
+// FastTopNeighbors eviction slot) is restated from Rust std semantics but is not pinned by any
+// reference test.
+//
+// Build: g++ -O2 -std=c++17 -mavx2 -mfma -ffp-contract=off -fPIC -shared (see oracle/Makefile).
+// -ffp-contract=off is REQUIRED: scalar Rust never fuses a*b+c; FMA appears only where the
+// reference calls _mm256_fmadd_ps explicitly.
+//
+// Rust semantics restated: f32::round = half away from zero (roundf); float->int `as` saturates
+// (NaN->0); i32 `as i8` wraps; slice::sort_by / sort_by_key are stable; partial_cmp().unwrap_or(Equal);
+// OrderedFloat total order; Iterator::sum::<f32>() is a left fold; rayon par_iter().collect()
+// preserves order.
+
+#include <immintrin.h>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+enum Measure { SQL2 = 0, L2 = 1, DOT = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// L0/L1 SIMD kernels
+// ---------------------------------------------------------------------------------------------
+
+// src/simd/x86.rs:31-44  horizontal_sum_f32_avx2: ((a0+a4)+(a1+a5)) + ((a2+a6)+(a3+a7))
+inline float hsum_movehdup(__m256 v) {
+  __m128 hi = _mm256_extractf128_ps(v, 1);
+  __m128 lo = _mm256_castps256_ps128(v);
+  __m128 s = _mm_add_ps(lo, hi);
+  __m128 sh = _mm_movehdup_ps(s);
+  __m128 t = _mm_add_ps(s, sh);
+  sh = _mm_movehl_ps(t, t);
+  t = _mm_add_ss(t, sh);
+  return _mm_cvtss_f32(t);
+}
+
+// src/distance_measures/one_to_many_asymmetric.rs:383-399  horizontal_sum_avx (hadd variant)
+inline float hsum_hadd(__m256 v) {
+  __m128 hi = _mm256_extractf128_ps(v, 1);
+  __m128 lo = _mm256_castps256_ps128(v);
+  __m128 s = _mm_add_ps(lo, hi);
+  __m128 s64 = _mm_hadd_ps(s, s);
+  __m128 s32 = _mm_hadd_ps(s64, s64);
+  return _mm_cvtss_f32(s32);
+}
+
+// src/simd/x86.rs:72-96  dot_product_avx2
+float dot_avx2(const float* a, const float* b, size_t len) {
+  size_t chunks = len / 8, rem = len % 8;
+  __m256 sum = _mm256_setzero_ps();
+  for (size_t i = 0; i < chunks; ++i)
+    sum = _mm256_fmadd_ps(_mm256_loadu_ps(a + i * 8), _mm256_loadu_ps(b + i * 8), sum);
+  float r = hsum_movehdup(sum);
+  for (size_t i = len - rem; i < len; ++i) r += a[i] * b[i];
+  return r;
+}
+
+// src/simd/x86.rs:139-165  squared_l2_avx2
+float sql2_avx2(const float* a, const float* b, size_t len) {
+  size_t chunks = len / 8, rem = len % 8;
+  __m256 sum = _mm256_setzero_ps();
+  for (size_t i = 0; i < chunks; ++i) {
+    __m256 d = _mm256_sub_ps(_mm256_loadu_ps(a + i * 8), _mm256_loadu_ps(b + i * 8));
+    sum = _mm256_fmadd_ps(d, d, sum);
+  }
+  float r = hsum_movehdup(sum);
+  for (size_t i = len - rem; i < len; ++i) {
+    float d = a[i] - b[i];
+    r += d * d;
+  }
+  return r;
+}
+
+// src/simd/x86.rs:195-258  one_to_many_dot_product_avx2 (3 rows in flight; results negated)
+void one_to_many_dot(const float* q, size_t dim, const float* db, size_t stride, size_t n, float* out) {
+  size_t chunks = dim / 8, rem = dim % 8;
+  size_t triples = n / 3;
+  for (size_t b = 0; b < triples; ++b) {
+    size_t base = b * 3;
+    __m256 s0 = _mm256_setzero_ps(), s1 = s0, s2 = s0;
+    for (size_t i = 0; i < chunks; ++i) {
+      __m256 qv = _mm256_loadu_ps(q + i * 8);
+      s0 = _mm256_fmadd_ps(qv, _mm256_loadu_ps(db + base * stride + i * 8), s0);
+      s1 = _mm256_fmadd_ps(qv, _mm256_loadu_ps(db + (base + 1) * stride + i * 8), s1);
+      s2 = _mm256_fmadd_ps(qv, _mm256_loadu_ps(db + (base + 2) * stride + i * 8), s2);
+    }
+    float r0 = hsum_movehdup(s0), r1 = hsum_movehdup(s1), r2 = hsum_movehdup(s2);
+    for (size_t j = dim - rem; j < dim; ++j) {
+      float qq = q[j];
+      r0 += qq * db[base * stride + j];
+      r1 += qq * db[(base + 1) * stride + j];
+      r2 += qq * db[(base + 2) * stride + j];
+    }
+    out[base] = -r0;
+    out[base + 1] = -r1;
+    out[base + 2] = -r2;
+  }
+  for (size_t i = triples * 3; i < n; ++i) out[i] = -dot_avx2(q, db + i * stride, dim);
+}
+
+// src/simd/x86.rs:267-346  one_to_many_squared_l2_avx2 (4 rows in flight). Per row the arithmetic
+// is identical to sql2_avx2(q, row): lane-wise fma over chunks, hsum, scalar tail.
+void one_to_many_sql2(const float* q, size_t dim, const float* db, size_t stride, size_t n, float* out) {
+  size_t chunks = dim / 8, rem = dim % 8;
+  size_t quads = n / 4;
+  for (size_t b = 0; b < quads; ++b) {
+    size_t base = b * 4;
+    __m256 s[4] = {_mm256_setzero_ps(), _mm256_setzero_ps(), _mm256_setzero_ps(), _mm256_setzero_ps()};
+    for (size_t i = 0; i < chunks; ++i) {
+      __m256 qv = _mm256_loadu_ps(q + i * 8);
+      for (int r = 0; r < 4; ++r) {
+        __m256 d = _mm256_sub_ps(qv, _mm256_loadu_ps(db + (base + r) * stride + i * 8));
+        s[r] = _mm256_fmadd_ps(d, d, s[r]);
+      }
+    }
+    float r4[4];
+    for (int r = 0; r < 4; ++r) r4[r] = hsum_movehdup(s[r]);
+    for (size_t j = dim - rem; j < dim; ++j) {
+      float qq = q[j];
+      for (int r = 0; r < 4; ++r) {
+        float d = qq - db[(base + r) * stride + j];
+        r4[r] += d * d;
+      }
+    }
+    for (int r = 0; r < 4; ++r) out[base + r] = r4[r];
+  }
+  for (size_t i = quads * 4; i < n; ++i) out[i] = sql2_avx2(q, db + i * stride, dim);
+}
+
+inline __m256 load_i8x8_as_f32(const int8_t* p) {
+  // one_to_many_asymmetric.rs:109-124: loadl_epi64, cvtepi8_epi16, cvtepi16_epi32 lo/hi, cvtepi32_ps
+  __m128i bytes = _mm_loadl_epi64(reinterpret_cast<const __m128i*>(p));
+  __m128i i16 = _mm_cvtepi8_epi16(bytes);
+  __m128i lo = _mm_cvtepi16_epi32(i16);
+  __m128i hi = _mm_cvtepi16_epi32(_mm_shuffle_epi32(i16, 0xEE));
+  __m256i i32 = _mm256_setr_m128i(lo, hi);
+  return _mm256_cvtepi32_ps(i32);
+}
+
+// src/distance_measures/one_to_many_asymmetric.rs:77-144 (sign-extends the byte; no offset)
+void one_to_many_i8_dot(const float* q, size_t dim, const int8_t* db, float inv_mul, size_t stride, size_t n,
+                        float* out) {
+  size_t chunks = dim / 8, rem = dim % 8;
+  __m256 mul = _mm256_set1_ps(inv_mul);
+  for (size_t i = 0; i < n; ++i) {
+    size_t base = i * stride;
+    __m256 acc = _mm256_setzero_ps();
+    for (size_t c = 0; c < chunks; ++c) {
+      __m256 qv = _mm256_loadu_ps(q + c * 8);
+      __m256 x = _mm256_mul_ps(load_i8x8_as_f32(db + base + c * 8), mul);
+      acc = _mm256_fmadd_ps(qv, x, acc);
+    }
+    float r = hsum_hadd(acc);
+    for (size_t j = dim - rem; j < dim; ++j) {
+      float x = static_cast<float>(db[base + j]) * inv_mul;
+      r += q[j] * x;
+    }
+    out[i] = -r;
+  }
+}
+
+// src/distance_measures/one_to_many_asymmetric.rs:207-261
+void one_to_many_i8_sql2(const float* q, size_t dim, const int8_t* db, float inv_mul, size_t stride, size_t n,
+                         float* out) {
+  size_t chunks = dim / 8, rem = dim % 8;
+  __m256 mul = _mm256_set1_ps(inv_mul);
+  for (size_t i = 0; i < n; ++i) {
+    size_t base = i * stride;
+    __m256 acc = _mm256_setzero_ps();
+    for (size_t c = 0; c < chunks; ++c) {
+      __m256 qv = _mm256_loadu_ps(q + c * 8);
+      __m256 x = _mm256_mul_ps(load_i8x8_as_f32(db + base + c * 8), mul);
+      __m256 d = _mm256_sub_ps(qv, x);
+      acc = _mm256_fmadd_ps(d, d, acc);
+    }
+    float r = hsum_hadd(acc);
+    for (size_t j = dim - rem; j < dim; ++j) {
+      float x = static_cast<float>(db[base + j]) * inv_mul;
+      float d = q[j] - x;
+      r += d * d;
+    }
+    out[i] = r;
+  }
+}
+
+// src/distance_measures/mod.rs:70-81 + one_to_one.rs:162-214,463-469 — single-pair distance as the
+// reorder paths see it (f32 dense → AVX2+FMA kernels via simd::dispatch).
+float pair_distance(int measure, const float* a, const float* b, size_t dim) {
+  switch (measure) {
+    case SQL2: return sql2_avx2(a, b, dim);
+    case L2: return std::sqrt(sql2_avx2(a, b, dim));
+    default: return -dot_avx2(a, b, dim);
+  }
+}
+
+// scalar, sequential, non-fused Σ d·d: tree_partitioner.rs:183-192, codebook.rs:106-115,
+// lut16.rs:246-255 (all three are the same fold)
+inline float scalar_sqdist(const float* a, const float* b, size_t len) {
+  float s = 0.0f;
+  for (size_t i = 0; i < len; ++i) {
+    float d = a[i] - b[i];
+    s += d * d;
+  }
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Top-k trackers
+// ---------------------------------------------------------------------------------------------
+
+struct Pair {
+  float d;
+  uint32_t idx;
+};
+// (OrderedFloat<f32>, u32) lexicographic order (top_k.rs:23)
+inline int cmp_of32(float a, float b) {
+  bool an = std::isnan(a), bn = std::isnan(b);
+  if (an || bn) return an == bn ? 0 : (an ? 1 : -1);  // NaN greatest, equal to itself
+  return a < b ? -1 : (a > b ? 1 : 0);
+}
+inline bool pair_le(const Pair& a, const Pair& b) {
+  int c = cmp_of32(a.d, b.d);
+  if (c != 0) return c < 0;
+  return a.idx <= b.idx;
+}
+
+// top_k.rs:20-113 TopK over std::collections::BinaryHeap (max-heap). The sift routines restate
+// Rust std's binary_heap (sift_up with a hole; pop = swap-with-last + sift_down_to_bottom + sift_up).
+struct TopK {
+  std::vector<Pair> data;
+  size_t k;
+  explicit TopK(size_t k_) : k(k_) { data.reserve(k_ + 1); }
+  void sift_up(size_t start, size_t pos) {
+    Pair elt = data[pos];
+    while (pos > start) {
+      size_t parent = (pos - 1) / 2;
+      if (pair_le(elt, data[parent])) break;
+      data[pos] = data[parent];
+      pos = parent;
+    }
+    data[pos] = elt;
+  }
+  void sift_down_to_bottom(size_t pos) {
+    size_t end = data.size(), start = pos;
+    Pair elt = data[pos];
+    size_t child = 2 * pos + 1;
+    while (child <= (end >= 2 ? end - 2 : 0) && end >= 2) {
+      if (pair_le(data[child], data[child + 1])) child += 1;
+      data[pos] = data[child];
+      pos = child;
+      child = 2 * pos + 1;
+    }
+    if (child == end - 1) {
+      data[pos] = data[child];
+      pos = child;
+    }
+    data[pos] = elt;
+    sift_up(start, pos);
+  }
+  void heap_push(Pair p) {
+    data.push_back(p);
+    sift_up(0, data.size() - 1);
+  }
+  void heap_pop() {
+    Pair last = data.back();
+    data.pop_back();
+    if (!data.empty()) {
+      data[0] = last;  // (swap; the popped max is discarded by the caller)
+      sift_down_to_bottom(0);
+    }
+  }
+  bool push(uint32_t idx, float d) {  // top_k.rs:66-81
+    if (data.size() < k) {
+      heap_push({d, idx});
+      return true;
+    }
+    if (!data.empty()) {
+      if (d < data[0].d) {  // strict
+        heap_pop();
+        heap_push({d, idx});
+        return true;
+      }
+    }
+    return false;
+  }
+  // top_k.rs:105-112: drain() yields the heap array in order, then a STABLE sort by distance only.
+  std::vector<Pair> drain_sorted() {
+    std::vector<Pair> r = data;
+    data.clear();
+    std::stable_sort(r.begin(), r.end(), [](const Pair& a, const Pair& b) { return a.d < b.d; });
+    return r;
+  }
+};
+
+// top_k.rs:264-393 FastTopNeighbors: O(k) scan for the first slot holding the max; strict replace.
+struct FastTopNeighbors {
+  std::vector<uint32_t> idx;
+  std::vector<float> dist;
+  size_t size = 0, cap;
+  explicit FastTopNeighbors(size_t c) : idx(c, 0), dist(c, std::numeric_limits<float>::infinity()), cap(c) {}
+  void push(uint32_t i, float d) {
+    if (size < cap) {
+      idx[size] = i;
+      dist[size] = d;
+      ++size;
+    } else {
+      if (size == 0) return;  // capacity 0: Rust would index distances[0] of an empty vec and panic
+      size_t mi = 0;
+      float md = dist[0];
+      for (size_t j = 1; j < size; ++j)
+        if (dist[j] > md) {
+          md = dist[j];
+          mi = j;
+        }
+      if (d < md) {
+        idx[mi] = i;
+        dist[mi] = d;
+      }
+    }
+  }
+  std::vector<Pair> results() const {  // top_k.rs:374-382
+    std::vector<Pair> r(size);
+    for (size_t j = 0; j < size; ++j) r[j] = {dist[j], idx[j]};
+    std::stable_sort(r.begin(), r.end(), [](const Pair& a, const Pair& b) { return a.d < b.d; });
+    return r;
+  }
+};
+
+inline void stable_sort_by_dist(std::vector<Pair>& v) {
+  std::stable_sort(v.begin(), v.end(), [](const Pair& a, const Pair& b) { return a.d < b.d; });
+}
+
+// one task per query over a thread pool == rayon par_iter().map().collect() (order preserved)
+template <class F>
+void parallel_for(size_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n <= 1) {
+    for (size_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  int nt = static_cast<int>(std::min<size_t>(nthreads, n));
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (;;) {
+        size_t i = next.fetch_add(1);
+        if (i >= n) break;
+        f(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+void write_results(const std::vector<Pair>& r, size_t k, uint32_t* ids, float* dists, uint32_t* count) {
+  size_t m = std::min(k, r.size());
+  for (size_t j = 0; j < m; ++j) {
+    ids[j] = r[j].idx;
+    dists[j] = r[j].d;
+  }
+  for (size_t j = m; j < k; ++j) {
+    ids[j] = 0xFFFFFFFFu;
+    dists[j] = std::numeric_limits<float>::infinity();
+  }
+  *count = static_cast<uint32_t>(m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// PQ / LUT pieces
+// ---------------------------------------------------------------------------------------------
+
+// hashes/lut.rs:47-70 + codebook.rs:98-103: f32 table [S][C] of scalar squared-L2
+void lut_f32(const float* cb, size_t S, size_t C, size_t ds, const float* q, float* lut) {
+  for (size_t s = 0; s < S; ++s)
+    for (size_t c = 0; c < C; ++c) lut[s * C + c] = scalar_sqdist(q + s * ds, cb + (s * C + c) * ds, ds);
+}
+
+// hashes/lut16_simd.rs:39-90 from_float_tables
+void lut16_quantize(const float* lutf, size_t S, uint8_t* lut8, float* bias, float* mult) {
+  if (S == 0) {
+    *bias = 0.0f;
+    *mult = 1.0f;
+    return;
+  }
+  float gmin = std::numeric_limits<float>::max();
+  float gmax = std::numeric_limits<float>::lowest();
+  for (size_t i = 0; i < S * 16; ++i) {
+    gmin = std::fmin(gmin, lutf[i]);  // f32::min
+    gmax = std::fmax(gmax, lutf[i]);
+  }
+  float range = gmax - gmin;
+  float scale;
+  if (range < 1e-10f) {
+    *mult = 1.0f;
+    scale = 1.0f;
+  } else {
+    scale = 255.0f / range;
+    *mult = 1.0f / scale;
+  }
+  *bias = gmin;
+  for (size_t i = 0; i < S * 16; ++i) {
+    float v = roundf((lutf[i] - gmin) * scale);
+    // Rust `as u8`: saturating, NaN -> 0
+    uint8_t qv;
+    if (!(v == v)) qv = 0;
+    else if (v <= 0.0f) qv = 0;
+    else if (v >= 255.0f) qv = 255;
+    else qv = static_cast<uint8_t>(v);
+    lut8[i] = qv;
+  }
+}
+
+// simd/dispatch.rs:259-295 lut16_distances_batch_portable: u32 Σ over nibbles, low nibble first
+inline uint32_t lut16_sum(const uint8_t* packed_row, const uint8_t* lut8, size_t S) {
+  size_t bpp = (S + 1) / 2;
+  uint32_t sum = 0;
+  size_t sub = 0;
+  for (size_t b = 0; b < bpp; ++b) {
+    uint8_t byte = packed_row[b];
+    if (sub < S) {
+      sum += lut8[sub * 16 + (byte & 0x0F)];
+      ++sub;
+    }
+    if (sub < S) {
+      sum += lut8[sub * 16 + ((byte >> 4) & 0x0F)];
+      ++sub;
+    }
+  }
+  return sum;
+}
+
+// lut16_simd.rs:119-141 compute_distances_batch epilogue: sum as f32 * multiplier + bias * S
+inline float lut16_dequant(uint32_t sum, float mult, float bias, size_t S) {
+  float bias_total = bias * static_cast<float>(S);
+  return static_cast<float>(sum) * mult + bias_total;
+}
+
+// codebook.rs:82-95 SubspaceCodebook::encode (strict <, lowest code wins ties); :205-215 Codebook::encode
+void pq_encode_row(const float* cb, size_t S, size_t C, size_t ds, const float* x, uint8_t* codes) {
+  for (size_t s = 0; s < S; ++s) {
+    float best = std::numeric_limits<float>::infinity();
+    uint8_t bi = 0;
+    for (size_t c = 0; c < C; ++c) {
+      float d = scalar_sqdist(x + s * ds, cb + (s * C + c) * ds, ds);
+      if (d < best) {
+        best = d;
+        bi = static_cast<uint8_t>(c);
+      }
+    }
+    codes[s] = bi;
+  }
+}
+
+// partitioning/tree_partitioner.rs:175-229: SqL2 to all centres (scalar), stable sort by OrderedFloat
+void partition_one(const float* centers, size_t K, size_t dim, const float* q, size_t L, uint32_t* tokens,
+                   float* dists) {
+  std::vector<Pair> v(K);
+  for (size_t c = 0; c < K; ++c) v[c] = {scalar_sqdist(q, centers + c * dim, dim), static_cast<uint32_t>(c)};
+  std::stable_sort(v.begin(), v.end(), [](const Pair& a, const Pair& b) { return cmp_of32(a.d, b.d) < 0; });
+  size_t m = std::min(L, K);
+  for (size_t j = 0; j < m; ++j) {
+    tokens[j] = v[j].idx;
+    if (dists) dists[j] = v[j].d;
+  }
+  for (size_t j = m; j < L; ++j) {
+    tokens[j] = 0xFFFFFFFFu;
+    if (dists) dists[j] = std::numeric_limits<float>::infinity();
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI (ctypes)
+// =============================================================================================
+extern "C" {
+
+void orc_one_to_many_sql2(const float* q, size_t dim, const float* db, size_t stride, size_t n, float* out) {
+  one_to_many_sql2(q, dim, db, stride, n, out);
+}
+void orc_one_to_many_dot(const float* q, size_t dim, const float* db, size_t stride, size_t n, float* out) {
+  one_to_many_dot(q, dim, db, stride, n, out);
+}
+void orc_one_to_many_i8_dot(const float* q, size_t dim, const int8_t* db, float inv_mul, size_t stride, size_t n,
+                            float* out) {
+  one_to_many_i8_dot(q, dim, db, inv_mul, stride, n, out);
+}
+void orc_one_to_many_i8_sql2(const float* q, size_t dim, const int8_t* db, float inv_mul, size_t stride, size_t n,
+                             float* out) {
+  one_to_many_i8_sql2(q, dim, db, inv_mul, stride, n, out);
+}
+float orc_pair_distance(int measure, const float* a, const float* b, size_t dim) {
+  return pair_distance(measure, a, b, dim);
+}
+float orc_scalar_sqdist(const float* a, const float* b, size_t dim) { return scalar_sqdist(a, b, dim); }
+
+// DenseDataset stride rule, data_format/dataset.rs:90-96 (64-byte rows)
+size_t orc_dense_stride(size_t dim, size_t elem_size) {
+  size_t per_line = 64 / elem_size;
+  return (dim + per_line - 1) / per_line * per_line;
+}
+
+// ---- top-k trackers exposed for the reference's KAT sequences (top_k.rs:399-465)
+uint32_t orc_topk_run(size_t k, const uint32_t* ids, const float* dists, size_t n, uint32_t* out_ids,
+                      float* out_dists, uint8_t* accepted) {
+  TopK t(k);
+  for (size_t i = 0; i < n; ++i) {
+    bool a = t.push(ids[i], dists[i]);
+    if (accepted) accepted[i] = a ? 1 : 0;
+  }
+  auto r = t.drain_sorted();
+  for (size_t j = 0; j < r.size(); ++j) {
+    out_ids[j] = r[j].idx;
+    out_dists[j] = r[j].d;
+  }
+  return static_cast<uint32_t>(r.size());
+}
+uint32_t orc_ftn_run(size_t cap, const uint32_t* ids, const float* dists, size_t n, int batch_mode,
+                     uint32_t* out_ids, float* out_dists) {
+  FastTopNeighbors f(cap);
+  for (size_t i = 0; i < n; ++i) {
+    if (batch_mode) {  // push_batch, top_k.rs:358-365: only pushes when dist < threshold()
+      float thr = std::numeric_limits<float>::infinity();
+      if (f.size >= f.cap) {
+        float m = -std::numeric_limits<float>::infinity();
+        for (size_t j = 0; j < f.size; ++j) m = std::fmax(m, f.dist[j]);
+        thr = m * (1.0f + 0.0f);
+      }
+      if (dists[i] < thr) f.push(ids[i], dists[i]);
+    } else {
+      f.push(ids[i], dists[i]);
+    }
+  }
+  auto r = f.results();
+  for (size_t j = 0; j < r.size(); ++j) {
+    out_ids[j] = r[j].idx;
+    out_dists[j] = r[j].d;
+  }
+  return static_cast<uint32_t>(r.size());
+}
+
+// ---- a1: BruteForceSearcher::search_batched (brute_force/searcher.rs:77-208)
+// returns 0 Ok / 3 InvalidArgument.  Empty dataset -> Ok with counts 0.
+int orc_bf_search(const float* db, size_t n, size_t dim, size_t stride, int measure, const float* q, size_t nq,
+                  size_t qdim, size_t k, uint32_t* ids, float* dists, uint32_t* counts, int nthreads) {
+  if (n == 0) {
+    for (size_t i = 0; i < nq; ++i) counts[i] = 0;
+    return 0;
+  }
+  if (qdim != dim) return 3;
+  size_t kk = std::min(k, n);
+  parallel_for(nq, nthreads, [&](size_t qi) {
+    std::vector<float> d(n);
+    if (measure == DOT) one_to_many_dot(q + qi * dim, dim, db, stride, n, d.data());
+    else {
+      one_to_many_sql2(q + qi * dim, dim, db, stride, n, d.data());
+      if (measure == L2)
+        for (auto& x : d) x = std::sqrt(x);
+    }
+    TopK t(kk);
+    for (size_t i = 0; i < n; ++i) t.push(static_cast<uint32_t>(i), d[i]);
+    auto r = t.drain_sorted();
+    write_results(r, k, ids + qi * k, dists + qi * k, counts + qi);
+  });
+  return 0;
+}
+
+// searcher.rs:142-167 search_radius: all points with d <= radius, stable-sorted. Returns count.
+size_t orc_bf_search_radius(const float* db, size_t n, size_t dim, size_t stride, int measure, const float* q,
+                            float radius, uint32_t* ids, float* dists, size_t cap) {
+  std::vector<float> d(n);
+  if (measure == DOT) one_to_many_dot(q, dim, db, stride, n, d.data());
+  else {
+    one_to_many_sql2(q, dim, db, stride, n, d.data());
+    if (measure == L2)
+      for (auto& x : d) x = std::sqrt(x);
+  }
+  std::vector<Pair> r;
+  for (size_t i = 0; i < n; ++i)
+    if (d[i] <= radius) r.push_back({d[i], static_cast<uint32_t>(i)});
+  stable_sort_by_dist(r);
+  for (size_t j = 0; j < r.size() && j < cap; ++j) {
+    ids[j] = r[j].idx;
+    dists[j] = r[j].d;
+  }
+  return r.size();
+}
+
+// ---- a4: QuantizationStats::from_dataset (quantization/mod.rs:77-110) → out {min,max,mean,std}
+void orc_sq8_stats(const float* db, size_t n, size_t dim, size_t stride, float* out4) {
+  float mn = std::numeric_limits<float>::max(), mx = std::numeric_limits<float>::lowest();
+  double sum = 0.0, sum_sq = 0.0;
+  uint64_t count = 0;
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = 0; j < dim; ++j) {
+      float v = db[i * stride + j];
+      mn = std::fmin(mn, v);
+      mx = std::fmax(mx, v);
+      sum += static_cast<double>(v);
+      sum_sq += static_cast<double>(v) * static_cast<double>(v);
+      ++count;
+    }
+  float mean = count > 0 ? static_cast<float>(sum / static_cast<double>(count)) : 0.0f;
+  float var = count > 1 ? static_cast<float>((sum_sq - sum * sum / static_cast<double>(count)) /
+                                             static_cast<double>(count - 1))
+                        : 0.0f;
+  out4[0] = mn;
+  out4[1] = mx;
+  out4[2] = mean;
+  out4[3] = std::sqrt(var);
+}
+
+// ScalarQuantizer::calibrate default (non-symmetric, no explicit range) quantization/scalar.rs:103-130
+// in: stats{min,max,mean,std}, num_std_devs(3.0), bits(8) → out {min_value,max_value,scale,inv_scale}
+void orc_sq8_calibrate(const float* stats4, float num_std_devs, int bits, float* out4) {
+  int num_levels = (1 << bits) - 1;
+  float range0 = num_std_devs * stats4[3];
+  float mn = std::fmax(stats4[2] - range0, stats4[0]);
+  float mx = std::fmin(stats4[2] + range0, stats4[1]);
+  float range = mx - mn;
+  float scale = 1.0f, inv_scale = 1.0f;
+  if (range > 1e-10f) {
+    scale = range / static_cast<float>(num_levels);
+    inv_scale = static_cast<float>(num_levels) / range;
+  }
+  out4[0] = mn;
+  out4[1] = mx;
+  out4[2] = scale;
+  out4[3] = inv_scale;
+}
+
+// quantize_value scalar.rs:162-166: clamp → round((v-min)*inv_scale) as i32 → clamp 0..levels → as i8 (wraps)
+int8_t orc_sq8_quantize_value(float v, const float* cal4, int bits) {
+  int num_levels = (1 << bits) - 1;
+  float c = v;
+  if (c < cal4[0]) c = cal4[0];  // f32::clamp
+  if (c > cal4[1]) c = cal4[1];
+  float r = roundf((c - cal4[0]) * cal4[3]);
+  int32_t qi;
+  if (!(r == r)) qi = 0;
+  else if (r >= 2147483648.0f) qi = INT32_MAX;
+  else if (r <= -2147483648.0f) qi = INT32_MIN;
+  else qi = static_cast<int32_t>(r);
+  qi = std::min(std::max(qi, 0), num_levels);
+  return static_cast<int8_t>(static_cast<uint8_t>(qi & 0xFF));
+}
+
+// dequantize_value scalar.rs:168-172 (treats the byte as u8, adds min) — NOT what search uses
+float orc_sq8_dequantize_value(int8_t qv, const float* cal4) {
+  return static_cast<float>(static_cast<uint8_t>(qv)) * cal4[2] + cal4[0];
+}
+
+// QuantizedDataset::from_dataset scalar.rs:195-226: stride = dim; cal4 out
+void orc_sq8_quantize(const float* db, size_t n, size_t dim, size_t stride, int8_t* out, float* cal4) {
+  float st[4];
+  orc_sq8_stats(db, n, dim, stride, st);
+  orc_sq8_calibrate(st, 3.0f, 8, cal4);
+  for (size_t i = 0; i < n; ++i)
+    for (size_t j = 0; j < dim; ++j) out[i * dim + j] = orc_sq8_quantize_value(db[i * stride + j], cal4, 8);
+}
+
+// ---- a5: ScalarQuantizedBruteForceSearcher::search_batched (scalar_quantized.rs:168-326)
+int orc_sq8_search(const int8_t* db, size_t n, size_t dim, float scale, int measure, const float* q, size_t nq,
+                   size_t qdim, size_t k, uint32_t* ids, float* dists, uint32_t* counts, int nthreads) {
+  if (n == 0) {
+    for (size_t i = 0; i < nq; ++i) counts[i] = 0;
+    return 0;
+  }
+  if (qdim != dim) return 3;
+  size_t kk = std::min(k, n);
+  parallel_for(nq, nthreads, [&](size_t qi) {
+    std::vector<float> d(n);
+    if (measure == DOT) one_to_many_i8_dot(q + qi * dim, dim, db, scale, dim, n, d.data());
+    else {
+      one_to_many_i8_sql2(q + qi * dim, dim, db, scale, dim, n, d.data());
+      if (measure == L2)
+        for (auto& x : d) x = std::sqrt(x);
+    }
+    TopK t(kk);
+    for (size_t i = 0; i < n; ++i) t.push(static_cast<uint32_t>(i), d[i]);
+    auto r = t.drain_sorted();
+    write_results(r, k, ids + qi * k, dists + qi * k, counts + qi);
+  });
+  return 0;
+}
+
+// ---- a6: TreePartitioner::partition
+int orc_partition(const float* centers, size_t K, size_t dim, const float* q, size_t nq, size_t L,
+                  uint32_t* tokens, float* dists, int nthreads) {
+  parallel_for(nq, nthreads, [&](size_t qi) {
+    partition_one(centers, K, dim, q + qi * dim, L, tokens + qi * L, dists ? dists + qi * L : nullptr);
+  });
+  return 0;
+}
+
+// ---- a8/a9/a10 pieces
+void orc_pq_encode(const float* cb, size_t S, size_t C, size_t ds, const float* x, size_t n, size_t stride,
+                   uint8_t* codes) {
+  for (size_t i = 0; i < n; ++i) pq_encode_row(cb, S, C, ds, x + i * stride, codes + i * S);
+}
+// residual encode as TreeX build does (tree_x_hybrid/mod.rs:177-189): x - centroid then encode
+void orc_pq_encode_residual(const float* cb, size_t S, size_t C, size_t ds, const float* x, size_t n,
+                            size_t stride, const float* centers, const uint32_t* assign, uint8_t* codes) {
+  size_t dim = S * ds;
+  std::vector<float> r(dim);
+  for (size_t i = 0; i < n; ++i) {
+    const float* c = centers + static_cast<size_t>(assign[i]) * dim;
+    for (size_t j = 0; j < dim; ++j) r[j] = x[i * stride + j] - c[j];
+    pq_encode_row(cb, S, C, ds, r.data(), codes + i * S);
+  }
+}
+// PackedCodes4Bit::from_codes hashes/lut16.rs:43-61 (low nibble = even subspace)
+void orc_pack4(const uint8_t* codes, size_t n, size_t S, uint8_t* packed) {
+  size_t bpp = (S + 1) / 2;
+  for (size_t i = 0; i < n; ++i)
+    for (size_t b = 0; b < bpp; ++b) {
+      uint8_t lo = codes[i * S + 2 * b] & 0x0F;
+      uint8_t hi = (2 * b + 1 < S) ? static_cast<uint8_t>((codes[i * S + 2 * b + 1] & 0x0F) << 4) : 0;
+      packed[i * bpp + b] = lo | hi;
+    }
+}
+// PackedCodes4Bit::get_codes lut16.rs:64-77
+void orc_unpack4(const uint8_t* packed, size_t n, size_t S, uint8_t* codes) {
+  size_t bpp = (S + 1) / 2;
+  for (size_t i = 0; i < n; ++i)
+    for (size_t b = 0; b < bpp; ++b) {
+      codes[i * S + 2 * b] = packed[i * bpp + b] & 0x0F;
+      if (2 * b + 1 < S) codes[i * S + 2 * b + 1] = (packed[i * bpp + b] >> 4) & 0x0F;
+    }
+}
+void orc_lut_f32(const float* cb, size_t S, size_t C, size_t ds, const float* q, float* lut) {
+  lut_f32(cb, S, C, ds, q, lut);
+}
+// LookupTable::compute_distance lut.rs:74-82 (sequential f32 Σ)
+void orc_lut_f32_scan(const float* lut, size_t S, size_t C, const uint8_t* codes, size_t n, float* out) {
+  for (size_t i = 0; i < n; ++i) {
+    float s = 0.0f;
+    for (size_t j = 0; j < S; ++j) s += lut[j * C + codes[i * S + j]];
+    out[i] = s;
+  }
+}
+void orc_lut16_quantize(const float* lutf, size_t S, uint8_t* lut8, float* bias, float* mult) {
+  lut16_quantize(lutf, S, lut8, bias, mult);
+}
+// Lut16LookupTables::from_query → to_simd_tables (lut16.rs:151-173,214-222); optional residual centroid
+void orc_lut16_build(const float* cb, size_t S, size_t ds, const float* q, const float* centroid, uint8_t* lut8,
+                     float* bias, float* mult, float* lutf_out) {
+  size_t dim = S * ds;
+  std::vector<float> qq(dim);
+  for (size_t j = 0; j < dim; ++j) qq[j] = centroid ? q[j] - centroid[j] : q[j];
+  std::vector<float> lf(S * 16);
+  lut_f32(cb, S, 16, ds, qq.data(), lf.data());
+  if (lutf_out) std::memcpy(lutf_out, lf.data(), lf.size() * sizeof(float));
+  lut16_quantize(lf.data(), S, lut8, bias, mult);
+}
+void orc_lut16_scan_u32(const uint8_t* packed, const uint8_t* lut8, size_t S, size_t n, uint32_t* out) {
+  size_t bpp = (S + 1) / 2;
+  for (size_t i = 0; i < n; ++i) out[i] = lut16_sum(packed + i * bpp, lut8, S);
+}
+// lut16_distances_batch: f32 of the u32 sums (dispatch.rs:293)
+void orc_lut16_scan_f32(const uint8_t* packed, const uint8_t* lut8, size_t S, size_t n, float* out) {
+  size_t bpp = (S + 1) / 2;
+  for (size_t i = 0; i < n; ++i) out[i] = static_cast<float>(lut16_sum(packed + i * bpp, lut8, S));
+}
+// Lut16SimdTables::compute_distances_batch (lut16_simd.rs:119-141)
+void orc_lut16_distances(const uint8_t* packed, const uint8_t* lut8, size_t S, size_t n, float bias, float mult,
+                         float* out) {
+  size_t bpp = (S + 1) / 2;
+  for (size_t i = 0; i < n; ++i) out[i] = lut16_dequant(lut16_sum(packed + i * bpp, lut8, S), mult, bias, S);
+}
+// compute_distance_single lut16_simd.rs:144-154 (one byte per code)
+float orc_lut16_distance_single(const uint8_t* codes, const uint8_t* lut8, size_t S, float bias, float mult) {
+  uint32_t sum = 0;
+  for (size_t s = 0; s < S; ++s) sum += lut8[s * 16 + (codes[s] & 0x0F)];
+  return static_cast<float>(sum) * mult + bias * static_cast<float>(S);
+}
+
+// ---- a11: AsymmetricHasher::search / search_with_reordering (hashes/hasher.rs:162-229)
+// lut16 = 0: f32 LookupTable over byte codes [n*S] (the reference's wiring);
+// lut16 = 1: LUT16 composition over packed nibbles [n*ceil(S/2)], C must be 16.
+// pre_k = 0: plain search(k); pre_k > 0: search(pre_k) then exact SqL2 re-rank (hard-coded SqL2, :208)
+int orc_ah_search(const float* cb, size_t S, size_t C, size_t ds, const uint8_t* codes, size_t n, int lut16,
+                  const float* raw, size_t stride, const float* q, size_t nq, size_t qdim, size_t k, size_t pre_k,
+                  uint32_t* ids, float* dists, uint32_t* counts, int nthreads) {
+  if (n == 0) {
+    for (size_t i = 0; i < nq; ++i) counts[i] = 0;
+    return 0;
+  }
+  size_t dim = S * ds;
+  if (qdim != dim) return 3;
+  if (pre_k > 0 && !raw) return 9;  // FailedPrecondition "Dataset not stored"
+  size_t bpp = (S + 1) / 2;
+  parallel_for(nq, nthreads, [&](size_t qi) {
+    const float* qq = q + qi * dim;
+    size_t cap = pre_k > 0 ? pre_k : k;
+    FastTopNeighbors top(cap);
+    if (!lut16) {
+      std::vector<float> lut(S * C);
+      lut_f32(cb, S, C, ds, qq, lut.data());
+      for (size_t i = 0; i < n; ++i) {
+        float s = 0.0f;
+        for (size_t j = 0; j < S; ++j) s += lut[j * C + codes[i * S + j]];
+        top.push(static_cast<uint32_t>(i), s);
+      }
+    } else {
+      std::vector<uint8_t> l8(S * 16);
+      float bias, mult;
+      orc_lut16_build(cb, S, ds, qq, nullptr, l8.data(), &bias, &mult, nullptr);
+      for (size_t i = 0; i < n; ++i)
+        top.push(static_cast<uint32_t>(i), lut16_dequant(lut16_sum(codes + i * bpp, l8.data(), S), mult, bias, S));
+    }
+    auto r = top.results();
+    if (pre_k > 0) {
+      for (auto& p : r) p.d = pair_distance(SQL2, qq, raw + static_cast<size_t>(p.idx) * stride, dim);
+      stable_sort_by_dist(r);
+      if (r.size() > k) r.resize(k);
+    }
+    write_results(r, k, ids + qi * k, dists + qi * k, counts + qi);
+  });
+  return 0;
+}
+
+// ---- a12: TreeXHybridSearcher::search (tree_x_hybrid/mod.rs:245-364)
+// Index arrays: centers[K*dim]; cb[S*C*ds]; part_off[K+1]; part_ids[n] grouped by partition;
+// codes grouped by partition: lut16=0 → bytes [n*S]; lut16=1 → packed nibbles [n*ceil(S/2)].
+// R = pre_reorder_k (caller computes (k as f32 * multiplier) as usize). reorder_measure: the
+// reference hard-wires SqL2 (:124); Dot is the setter SURVEY §5 adds for config C3.
+// cand_out (optional) [nq*R]: the truncated approximate candidate list (ids) and cand_dists (f32).
+int orc_treex_search(const float* centers, size_t K, size_t dim, const float* cb, size_t S, size_t C, size_t ds,
+                     const uint64_t* part_off, const uint32_t* part_ids, const uint8_t* codes, int lut16,
+                     const float* raw, size_t stride, int use_residuals, int reorder_measure, const float* q,
+                     size_t nq, size_t qdim, size_t L, size_t R, size_t k, uint32_t* ids, float* dists,
+                     uint32_t* counts, uint32_t* cand_out, float* cand_dists, uint32_t* cand_counts,
+                     int nthreads) {
+  if (qdim != dim) return 3;
+  if (S * ds != dim) return 3;
+  size_t bpp = (S + 1) / 2;
+  parallel_for(nq, nthreads, [&](size_t qi) {
+    const float* qq = q + qi * dim;
+    size_t m = std::min(L, K);
+    std::vector<uint32_t> tokens(L);
+    partition_one(centers, K, dim, qq, L, tokens.data(), nullptr);
+    std::vector<Pair> all;
+    std::vector<float> qr(dim), lutf(S * C);
+    std::vector<uint8_t> l8(S * 16);
+    for (size_t t = 0; t < m; ++t) {  // par_iter over tokens; collect keeps token order (:266-280)
+      uint32_t pid = tokens[t];
+      const float* cen = centers + static_cast<size_t>(pid) * dim;
+      for (size_t j = 0; j < dim; ++j) qr[j] = use_residuals ? qq[j] - cen[j] : qq[j];  // :309-316
+      size_t b = part_off[pid], e = part_off[pid + 1];
+      FastTopNeighbors top(R);
+      if (!lut16) {
+        lut_f32(cb, S, C, ds, qr.data(), lutf.data());
+        for (size_t i = b; i < e; ++i) {
+          float s = 0.0f;
+          for (size_t j = 0; j < S; ++j) s += lutf[j * C + codes[i * S + j]];
+          top.push(part_ids[i], s);
+        }
+      } else {
+        lut_f32(cb, S, 16, ds, qr.data(), lutf.data());
+        float bias, mult;
+        lut16_quantize(lutf.data(), S, l8.data(), &bias, &mult);
+        for (size_t i = b; i < e; ++i)
+          top.push(part_ids[i], lut16_dequant(lut16_sum(codes + i * bpp, l8.data(), S), mult, bias, S));
+      }
+      auto r = top.results();
+      all.insert(all.end(), r.begin(), r.end());
+    }
+    stable_sort_by_dist(all);  // :289
+    if (all.size() > R) all.resize(R);
+    if (cand_out) {
+      for (size_t j = 0; j < all.size(); ++j) {
+        cand_out[qi * R + j] = all[j].idx;
+        if (cand_dists) cand_dists[qi * R + j] = all[j].d;
+      }
+      for (size_t j = all.size(); j < R; ++j) {
+        cand_out[qi * R + j] = 0xFFFFFFFFu;
+        if (cand_dists) cand_dists[qi * R + j] = std::numeric_limits<float>::infinity();
+      }
+      if (cand_counts) cand_counts[qi] = static_cast<uint32_t>(all.size());
+    }
+    if (raw) {  // reorder_results :342-364
+      for (auto& p : all) p.d = pair_distance(reorder_measure, qq, raw + static_cast<size_t>(p.idx) * stride, dim);
+      stable_sort_by_dist(all);
+    }
+    if (all.size() > k) all.resize(k);
+    write_results(all, k, ids + qi * k, dists + qi * k, counts + qi);
+  });
+  return 0;
+}
+
+// ---- a13: Scann::search_partitioned (scann.rs:215-253): exact distance inside the L leaves, full sort
+int orc_scann_partitioned(const float* centers, size_t K, size_t dim, const uint64_t* part_off,
+                          const uint32_t* part_ids, const float* raw, size_t stride, int measure, const float* q,
+                          size_t nq, size_t L, size_t k, uint32_t* ids, float* dists, uint32_t* counts,
+                          int nthreads) {
+  parallel_for(nq, nthreads, [&](size_t qi) {
+    const float* qq = q + qi * dim;
+    size_t m = std::min(L, K);
+    std::vector<uint32_t> tokens(L);
+    partition_one(centers, K, dim, qq, L, tokens.data(), nullptr);
+    std::vector<Pair> res;
+    for (size_t t = 0; t < m; ++t)
+      for (size_t i = part_off[tokens[t]]; i < part_off[tokens[t] + 1]; ++i) {
+        uint32_t id = part_ids[i];
+        res.push_back({pair_distance(measure, qq, raw + static_cast<size_t>(id) * stride, dim), id});
+      }
+    stable_sort_by_dist(res);
+    if (res.size() > k) res.resize(k);
+    write_results(res, k, ids + qi * k, dists + qi * k, counts + qi);
+  });
+  return 0;
+}
+
+// ---- a13: Scann::search_tree_ah, "variant B" (scann.rs:256-294): global non-residual codebook,
+// codes indexed by datapoint id [N*S] bytes, f32 LUT, collect everything, stable sort, truncate k.
+// reorder_measure >= 0 applies Scann::search_impl's post-hoc reorder of the k results (:198-209).
+int orc_scann_tree_ah(const float* centers, size_t K, size_t dim, const uint64_t* part_off,
+                      const uint32_t* part_ids, const float* cb, size_t S, size_t C, size_t ds,
+                      const uint8_t* codes_by_id, const float* raw, size_t stride, int reorder_measure,
+                      const float* q, size_t nq, size_t L, size_t k, uint32_t* ids, float* dists,
+                      uint32_t* counts, int nthreads) {
+  parallel_for(nq, nthreads, [&](size_t qi) {
+    const float* qq = q + qi * dim;
+    size_t m = std::min(L, K);
+    std::vector<uint32_t> tokens(L);
+    partition_one(centers, K, dim, qq, L, tokens.data(), nullptr);
+    std::vector<float> lut(S * C);
+    lut_f32(cb, S, C, ds, qq, lut.data());
+    std::vector<Pair> res;
+    for (size_t t = 0; t < m; ++t)
+      for (size_t i = part_off[tokens[t]]; i < part_off[tokens[t] + 1]; ++i) {
+        uint32_t id = part_ids[i];
+        const uint8_t* c = codes_by_id + static_cast<size_t>(id) * S;
+        float s = 0.0f;
+        for (size_t j = 0; j < S; ++j) s += lut[j * C + c[j]];
+        res.push_back({s, id});
+      }
+    stable_sort_by_dist(res);
+    if (res.size() > k) res.resize(k);
+    if (reorder_measure >= 0 && raw) {  // utils/reordering.rs:23-54
+      for (auto& p : res) p.d = pair_distance(reorder_measure, qq, raw + static_cast<size_t>(p.idx) * stride, dim);
+      stable_sort_by_dist(res);
+    }
+    write_results(res, k, ids + qi * k, dists + qi * k, counts + qi);
+  });
+  return 0;
+}
+
+// utils/reordering.rs:23-54 ReorderingHelper::reorder
+uint32_t orc_reorder(const float* raw, size_t stride, size_t dim, int measure, const float* q,
+                     const uint32_t* cand, size_t ncand, size_t k, uint32_t* ids, float* dists) {
+  std::vector<Pair> r(ncand);
+  for (size_t j = 0; j < ncand; ++j)
+    r[j] = {pair_distance(measure, q, raw + static_cast<size_t>(cand[j]) * stride, dim), cand[j]};
+  stable_sort_by_dist(r);
+  if (r.size() > k) r.resize(k);
+  for (size_t j = 0; j < r.size(); ++j) {
+    ids[j] = r[j].idx;
+    dists[j] = r[j].d;
+  }
+  return static_cast<uint32_t>(r.size());
+}
+
+int orc_num_threads(void) {
+  unsigned n = std::thread::hardware_concurrency();
+  return n ? static_cast<int>(n) : 1;
+}
+
+}  // extern "C"
