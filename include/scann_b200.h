@@ -1,0 +1,183 @@
+/*
+ * scann_b200.h — C ABI of libscann_b200.so: the B200-native (sm_100a) batched-search hot path of
+ * sunbains/scann-rust.  This header is the drop-in boundary: every entry point is
+ * what a thin `extern "C"` FFI layer in the reference crate would bind for the cited Rust method.
+ * Plain pointers and sizes only — no torch, no C++ types.
+ *
+ * Conventions
+ *  - Status codes are the ordinals of the reference's `ErrorCode` (src/error.rs:10-45).
+ *  - `scann_last_error()` returns a thread-local message for the last non-OK status.
+ *  - Every `*_create` copies the caller's index arrays to the GPU; the caller keeps ownership of
+ *    what it passed.  Every `*_search` writes caller-allocated outputs.
+ *  - `memspace` says where the caller's query/result buffers live: SCANN_HOST (plain or pinned host
+ *    memory; the library does the H2D/D2H copies on its stream and synchronises before returning)
+ *    or SCANN_DEVICE (device pointers on the handle's device; work is enqueued on `stream` and NOT
+ *    synchronised — the caller orders it, e.g. with torch's current stream).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the library's own per-handle stream for
+ *    SCANN_HOST calls, the legacy default stream for SCANN_DEVICE calls).
+ *  - Result layout for all searchers: ids[nq*k] (u32, 0xFFFFFFFF padding), dists[nq*k] (f32, +inf
+ *    padding), counts[nq] = number of valid results of each query (min(k, available)).
+ *  - Handles are safe for concurrent `search` calls from several threads (calls on one handle
+ *    serialise on an internal mutex around the shared workspace; tests/stress_tests.rs:256-297).
+ *  - There is no CPU fallback: every entry point that computes needs a CUDA device and returns
+ *    SCANN_UNAVAILABLE when none is usable.
+ */
+#ifndef SCANN_B200_H_
+#define SCANN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t scann_status;
+
+/* src/error.rs:10-45 ErrorCode ordinals */
+enum {
+  SCANN_OK = 0,
+  SCANN_CANCELLED = 1,
+  SCANN_UNKNOWN = 2,
+  SCANN_INVALID_ARGUMENT = 3,
+  SCANN_DEADLINE_EXCEEDED = 4,
+  SCANN_NOT_FOUND = 5,
+  SCANN_ALREADY_EXISTS = 6,
+  SCANN_PERMISSION_DENIED = 7,
+  SCANN_RESOURCE_EXHAUSTED = 8,
+  SCANN_FAILED_PRECONDITION = 9,
+  SCANN_ABORTED = 10,
+  SCANN_OUT_OF_RANGE = 11,
+  SCANN_UNIMPLEMENTED = 12,
+  SCANN_INTERNAL = 13,
+  SCANN_UNAVAILABLE = 14,
+  SCANN_DATA_LOSS = 15,
+  SCANN_UNAUTHENTICATED = 16
+};
+
+/* src/distance_measures/mod.rs:32-66 — the three measures the hot path dispatches to SIMD kernels */
+enum { SCANN_SQL2 = 0, SCANN_L2 = 1, SCANN_DOT = 2 };
+
+enum { SCANN_HOST = 0, SCANN_DEVICE = 1 };
+
+typedef struct scann_bf scann_bf;         /* BruteForceSearcher<f32>                     */
+typedef struct scann_sq8 scann_sq8;       /* ScalarQuantizedBruteForceSearcher           */
+typedef struct scann_part scann_part;     /* TreePartitioner (query side)                */
+typedef struct scann_treeah scann_treeah; /* TreeXHybridSearcher / AsymmetricHasher LUT16 */
+
+const char* scann_last_error(void);
+int scann_version(void);
+scann_status scann_device_count(int* count);
+
+/* ---------------------------------------------------------------------------------------------
+ * BruteForceSearcher<f32>  (src/brute_force/searcher.rs:34-208)
+ *   scann_bf_create  ← BruteForceSearcher::new / with_shared_dataset (:34-55); `db` is
+ *                      DenseDataset::raw_data() with its row stride (data_format/dataset.rs:90-96).
+ *                      n == 0 is legal (search then returns counts = 0, searcher.rs:78-80).
+ *   scann_bf_search  ← search_batched (:170-208) / search (:77-93): k clamped to n; qdim != dim →
+ *                      SCANN_INVALID_ARGUMENT (:83-89); nq == 0 → OK.  Dot distances are negated,
+ *                      L2 is sqrt(SqL2) (:119-130).
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_bf_create(const float* db, size_t n, size_t dim, size_t stride, int measure, int device,
+                             int memspace, scann_bf** out);
+scann_status scann_bf_search(scann_bf* h, const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids,
+                             float* dists, uint32_t* counts, int memspace, void* stream);
+void scann_bf_destroy(scann_bf* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * ScalarQuantizedBruteForceSearcher  (src/brute_force/scalar_quantized.rs:99-326)
+ *   scann_sq8_quantize ← QuantizedDataset::from_dataset (src/quantization/scalar.rs:195-226) with
+ *                        QuantizationStats::from_dataset (quantization/mod.rs:77-110) and
+ *                        ScalarQuantizer::calibrate (scalar.rs:103-130): writes codes[n*dim] (i8,
+ *                        levels 0..255 stored wrapped) and cal4 = {min, max, scale, inv_scale}.
+ *   scann_sq8_create   ← ScalarQuantizedBruteForceSearcher::from_quantized (:116-129)
+ *   scann_sq8_search   ← search_batched (:288-326): distances are q·((i8)x·scale), sign-extended,
+ *                        no offset — the reference's behaviour, reproduced as is.
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_sq8_quantize(const float* db, size_t n, size_t dim, size_t stride, int8_t* codes, float* cal4,
+                                int device, int memspace);
+scann_status scann_sq8_create(const int8_t* codes, size_t n, size_t dim, float scale, int measure, int device,
+                              int memspace, scann_sq8** out);
+scann_status scann_sq8_search(scann_sq8* h, const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids,
+                              float* dists, uint32_t* counts, int memspace, void* stream);
+void scann_sq8_destroy(scann_sq8* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * TreePartitioner, query side  (src/partitioning/tree_partitioner.rs:175-229)
+ *   scann_part_create ← the `centers` a built TreePartitioner holds (:148-150), row-major [K*dim]
+ *   scann_part_select ← Partitioner::partition (:196-229): squared-L2 to all K centres in the
+ *                       reference's sequential non-fused f32 order, stable order (dist, centre id),
+ *                       first L tokens + distances.  L > K pads with 0xFFFFFFFF / +inf.
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_part_create(const float* centers, size_t K, size_t dim, int device, int memspace,
+                               scann_part** out);
+scann_status scann_part_select(scann_part* h, const float* queries, size_t nq, size_t qdim, size_t L,
+                               uint32_t* tokens, float* dists, int memspace, void* stream);
+void scann_part_destroy(scann_part* h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tree-AH / Tree-X-Hybrid with the LUT16 path  (src/tree_x_hybrid/mod.rs:131-364 composed with
+ * src/hashes/lut16.rs:43-61,151-173 and src/hashes/lut16_simd.rs:39-141)
+ *   scann_treeah_create ← the arrays TreeXHybridSearcher::build leaves behind (:131-209):
+ *       centers[K*dim]; codebook[S*16*ds] (ds = dim/S); packed[n*ceil(S/2)] = PackedCodes4Bit rows
+ *       (low nibble = even subspace) GROUPED BY PARTITION; ids[n] = datapoint index of each row;
+ *       part_offsets[K+1] row offsets; raw[N*stride] = DenseDataset::raw_data() or NULL (no
+ *       reorder; results then carry the approximate LUT16 distances); num_raw = N.
+ *       K == 1 with use_residuals = 0 is the flat AsymmetricHasher (src/hashes/hasher.rs:162-229).
+ *   scann_treeah_search ← TreeXHybridSearcher::search (:240-294) / trait search_batched (:399-409):
+ *       partition → per-leaf residual LUT16 → integer scan → top-R by approximate distance
+ *       (R = pre_reorder_k) → exact `reorder_measure` distance of the R rows → top-k.
+ *       cand_ids/cand_dists (optional, [nq*R]) receive the R approximate candidates in order
+ *       (parity tap; pass NULL otherwise), cand_counts[nq] their number.
+ *   Limits: 1 <= S <= 256, dim % S == 0, L <= 1024, R <= 2048, leaf size < 2^(32-bits(255*S)).
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, const float* codebook, size_t S,
+                                 const uint8_t* packed, const uint32_t* ids, const uint64_t* part_offsets,
+                                 size_t n, const float* raw, size_t num_raw, size_t stride, int use_residuals,
+                                 int reorder_measure, int device, int memspace, scann_treeah** out);
+scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L, size_t R,
+                                 size_t k, uint32_t* ids, float* dists, uint32_t* counts, uint32_t* cand_ids,
+                                 float* cand_dists, uint32_t* cand_counts, int memspace, void* stream);
+void scann_treeah_destroy(scann_treeah* h);
+/* introspection used by bench.py for the roofline arithmetic: algorithmic code bytes scanned by the
+ * last scann_treeah_search call (Σ over (query, leaf) pairs of leaf_size * ceil(S/2)); host sync. */
+scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint64_t* pairs);
+
+/* ---------------------------------------------------------------------------------------------
+ * Parity taps for the LUT16 pieces (bit-exact targets of BASELINE.json)
+ *   scann_lut16_build ← Lut16LookupTables::from_query (hashes/lut16.rs:151-173) →
+ *       Lut16SimdTables::from_float_tables (hashes/lut16_simd.rs:39-90): for each query (optionally
+ *       minus centroids[leaf_of_query[i]]) the u8 table lut8[nq*S*16] and {bias, multiplier}.
+ *   scann_lut16_scan  ← lut16_distances_batch (src/simd/dispatch.rs:246-295): u32 sums[n] of one
+ *       u8 table over PackedCodes4Bit rows.
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_lut16_build(const float* codebook, size_t S, size_t ds, const float* queries, size_t nq,
+                               const float* centroids /* [nq*dim] or NULL */, uint8_t* lut8, float* bias,
+                               float* mult, int device, int memspace);
+scann_status scann_lut16_scan(const uint8_t* packed, size_t n, size_t S, const uint8_t* lut8, uint32_t* sums,
+                              int device, int memspace);
+
+/* ---------------------------------------------------------------------------------------------
+ * Index-build helpers with the reference's exact semantics (needed to build the
+ * 10M-row bench index on the GPU)
+ *   scann_pq_encode ← Codebook::encode (hashes/codebook.rs:82-95,205-215) of x - centers[assign]
+ *       (tree_x_hybrid/mod.rs:177-189; assign NULL → no residual) followed by
+ *       PackedCodes4Bit::from_codes (hashes/lut16.rs:43-61): packed[n*ceil(S/2)].
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_pq_encode(const float* codebook, size_t S, size_t ds, const float* x, size_t n, size_t stride,
+                             const float* centers, const uint32_t* assign, uint8_t* packed, int device,
+                             int memspace);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU merge: k-way merge of `parts` per-shard result lists laid out
+ * [parts][nq][k] (as produced by an all-gather of each rank's ids/dists) into [nq][k], ordered by
+ * (distance, id); padding entries (id 0xFFFFFFFF) are ignored.
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
+                              uint32_t* ids_out, float* dists_out, uint32_t* counts_out, int device, int memspace,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANN_B200_H_ */

@@ -1,0 +1,571 @@
+// BruteForceSearcher<f32> (src/brute_force/searcher.rs:77-208) and ScalarQuantizedBruteForceSearcher
+// (src/brute_force/scalar_quantized.rs:168-326) on the GPU.
+//
+// The reference streams the whole database once per query (one_to_many_* kernels) and pushes N
+// distances through a binary heap.  Here a batch is a dense contraction Q x X^T:
+//   1. bf_gemm_kernel      128x128x16 register-tiled f32 kernel (8x8 micro-tiles, double-buffered shared
+//                          memory; int8 rows are widened while staging).  Fused distance epilogue:
+//                          SqL2/L2 -> |q|^2 + |x|^2 - 2 q.x, Dot -> -q.x (negated as the reference does).
+//                          Scores go to an L2-resident tile [<=1024 queries][16384 rows].
+//   2. bf_select_kernel    per query: exact running top-kc over the tile (threshold filter + radix
+//                          select, common.cuh), kc = k + 32 candidates carried between row tiles.
+//   3. rescore_topk_kernel exact distance of the kc candidates in the reference's AVX2+FMA order
+//                          (bit-identical floats), final order (distance, id), top-k   (select.cu)
+// The GEMM scores only rank candidates; every distance that is returned comes from step 3.
+// Round-1 note: step 1 runs on the CUDA cores; the tcgen05/TMA version of the contraction replaces this
+// kernel only (same tile buffer, same epilogue).
+#include <string.h>
+
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace scann {
+
+constexpr int kBM = 128, kBN = 128, kBK = 16;
+constexpr int kQTile = 1024;    // queries per score tile
+constexpr int kNTile = 16384;   // rows per score tile
+constexpr int kBfMargin = 32;   // extra candidates kept beyond k
+
+__global__ void pad_queries_kernel(const float* __restrict__ q, size_t nq, size_t dim, size_t dim_pad, size_t rows_pad,
+                                   float* __restrict__ out, float* __restrict__ qn) {
+  size_t r = static_cast<size_t>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x & 31;
+  if (r >= rows_pad) return;
+  float s = 0.0f;
+  for (size_t d = lane; d < dim_pad; d += 32) {
+    float v = (r < nq && d < dim) ? q[r * dim + d] : 0.0f;
+    out[r * dim_pad + d] = v;
+    s = fmaf(v, v, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) qn[r] = s;
+}
+
+// db rows -> compact zero-padded rows [n_pad][dim_pad] (+ squared norms of the values the GEMM sees)
+template <bool I8>
+__global__ void pad_rows_kernel(const void* __restrict__ src, size_t n, size_t dim, size_t stride, size_t dim_pad,
+                                size_t n_pad, void* __restrict__ dst, float* __restrict__ xn, float scale) {
+  size_t r = static_cast<size_t>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x & 31;
+  if (r >= n_pad) return;
+  float s = 0.0f;
+  for (size_t d = lane; d < dim_pad; d += 32) {
+    bool in = r < n && d < dim;
+    if (I8) {
+      int8_t v = in ? static_cast<const int8_t*>(src)[r * stride + d] : 0;
+      static_cast<int8_t*>(dst)[r * dim_pad + d] = v;
+      float f = static_cast<float>(v) * scale;
+      s = fmaf(f, f, s);
+    } else {
+      float v = in ? static_cast<const float*>(src)[r * stride + d] : 0.0f;
+      static_cast<float*>(dst)[r * dim_pad + d] = v;
+      s = fmaf(v, v, s);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) xn[r] = s;
+}
+
+template <bool I8>
+__global__ void __launch_bounds__(256) bf_gemm_kernel(const float* __restrict__ A, const void* __restrict__ Bv, int Kd,
+                                                      const float* __restrict__ qn, const float* __restrict__ xn,
+                                                      float scale, int measure, float* __restrict__ C, int ldc) {
+  __shared__ __align__(16) float As[2][kBK][kBM];
+  __shared__ __align__(16) float Bs[2][kBK][kBN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const size_t m0 = static_cast<size_t>(blockIdx.y) * kBM, n0 = static_cast<size_t>(blockIdx.x) * kBN;
+  const float* Bf = static_cast<const float*>(Bv);
+  const int8_t* Bi = static_cast<const int8_t*>(Bv);
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+
+  // staging registers
+  float4 ra[2], rb[2];
+  uint4 rbi = make_uint4(0, 0, 0, 0);
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int idx = tid + i * 256, row = idx >> 2, kq = idx & 3;
+      ra[i] = *reinterpret_cast<const float4*>(A + (m0 + row) * Kd + k0 + kq * 4);
+      if (!I8) rb[i] = *reinterpret_cast<const float4*>(Bf + (n0 + row) * Kd + k0 + kq * 4);
+    }
+    if (I8 && tid < kBN) rbi = *reinterpret_cast<const uint4*>(Bi + (n0 + tid) * Kd + k0);
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int idx = tid + i * 256, row = idx >> 2, kq = idx & 3;
+      As[buf][kq * 4 + 0][row] = ra[i].x;
+      As[buf][kq * 4 + 1][row] = ra[i].y;
+      As[buf][kq * 4 + 2][row] = ra[i].z;
+      As[buf][kq * 4 + 3][row] = ra[i].w;
+      if (!I8) {
+        Bs[buf][kq * 4 + 0][row] = rb[i].x;
+        Bs[buf][kq * 4 + 1][row] = rb[i].y;
+        Bs[buf][kq * 4 + 2][row] = rb[i].z;
+        Bs[buf][kq * 4 + 3][row] = rb[i].w;
+      }
+    }
+    if (I8 && tid < kBN) {
+      const uint32_t w[4] = {rbi.x, rbi.y, rbi.z, rbi.w};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        int8_t v = static_cast<int8_t>((w[j >> 2] >> (8 * (j & 3))) & 0xFF);
+        Bs[buf][j][tid] = static_cast<float>(v);
+      }
+    }
+  };
+
+  const int nk = Kd / kBK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * kBK);
+#pragma unroll
+    for (int kk = 0; kk < kBK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[cur][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(cur ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // fused distance epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const size_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    const float qq = qn[m];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const size_t nb = n0 + (h == 0 ? tx * 4 : 64 + tx * 4);
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float dot = acc[i][h * 4 + j];
+        if (I8) dot *= scale;
+        o[j] = (measure == SCANN_DOT) ? -dot : (qq + xn[nb + j] - 2.0f * dot);
+      }
+      *reinterpret_cast<float4*>(C + m * ldc + nb) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+constexpr int kBfChunk = 2048;
+
+// per query: merge the carried top-kc state with the `ncols` scores of this row tile
+__global__ void __launch_bounds__(256) bf_select_kernel(const float* __restrict__ scores, int ldc, int ncols,
+                                                        uint32_t row0, uint64_t* __restrict__ state, int have, int kc) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int p2 = next_pow2(kc < 1 ? 1 : kc);
+  uint64_t* buf = reinterpret_cast<uint64_t*>(sm);
+  uint64_t* out = buf + (kc + kBfChunk);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(out + p2);
+  const size_t q = blockIdx.x;
+  const float* row = scores + q * ldc;
+  uint64_t* st = state + q * kc;
+  // once kc candidates are carried, nothing >= the current worst can enter
+  uint64_t thr0 = (have >= kc) ? st[kc - 1] + 1 : ~0ull;
+  auto gen = [&](int i) -> uint64_t {
+    if (i < have) return st[i];
+    int c = i - have;
+    return (static_cast<uint64_t>(f32_key(row[c])) << 32) | (row0 + static_cast<uint32_t>(c));
+  };
+  int m = block_topr_sorted<256, kBfChunk>(gen, have + ncols, kc, buf, out, hist, thr0);
+  __syncthreads();
+  for (int j = threadIdx.x; j < kc; j += 256) st[j] = j < m ? out[j] : ~0ull;
+}
+
+__global__ void state_to_cand_kernel(const uint64_t* __restrict__ state, size_t total, uint32_t* __restrict__ cand) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  uint64_t k = state[i];
+  cand[i] = k == ~0ull ? 0xFFFFFFFFu : static_cast<uint32_t>(k & 0xFFFFFFFFu);
+}
+
+struct BfCore {
+  int device = 0;
+  size_t n = 0, dim = 0, dim_pad = 0, n_pad = 0;
+  int measure = SCANN_SQL2;
+  bool i8 = false;
+  float scale = 1.0f;
+  DevBuf<float> rows_f;   // [n_pad][dim_pad]
+  DevBuf<int8_t> rows_i;  // [n_pad][dim_pad]
+  DevBuf<float> xn;       // [n_pad]
+  Workspace ws;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+
+  scann_status init(const void* db, size_t n_, size_t dim_, size_t stride, int measure_, bool i8_, float scale_,
+                    int device_, int memspace) {
+    device = device_;
+    n = n_;
+    dim = dim_;
+    measure = measure_;
+    i8 = i8_;
+    scale = scale_;
+    dim_pad = (dim + kBK - 1) / kBK * kBK;
+    n_pad = (n + kBN - 1) / kBN * kBN;
+    SCANN_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (n == 0) return SCANN_OK;
+    SCANN_TRY(xn.alloc(n_pad));
+    unsigned grid = static_cast<unsigned>((n_pad + 7) / 8);
+    if (i8) {
+      DevBuf<int8_t> tmp;
+      const int8_t* src = static_cast<const int8_t*>(db);
+      if (memspace == SCANN_HOST) {
+        SCANN_TRY(tmp.upload(src, n * stride, SCANN_HOST, stream));
+        src = tmp.p;
+      }
+      SCANN_TRY(rows_i.alloc(n_pad * dim_pad));
+      pad_rows_kernel<true><<<grid, 256, 0, stream>>>(src, n, dim, stride, dim_pad, n_pad, rows_i.p, xn.p, scale);
+      SCANN_CUDA(cudaGetLastError());
+      SCANN_CUDA(cudaStreamSynchronize(stream));
+    } else {
+      DevBuf<float> tmp;
+      const float* src = static_cast<const float*>(db);
+      if (memspace == SCANN_HOST) {
+        SCANN_TRY(tmp.upload(src, n * stride, SCANN_HOST, stream));
+        src = tmp.p;
+      }
+      SCANN_TRY(rows_f.alloc(n_pad * dim_pad));
+      pad_rows_kernel<false><<<grid, 256, 0, stream>>>(src, n, dim, stride, dim_pad, n_pad, rows_f.p, xn.p, 1.0f);
+      SCANN_CUDA(cudaGetLastError());
+      SCANN_CUDA(cudaStreamSynchronize(stream));
+    }
+    return SCANN_OK;
+  }
+
+  scann_status search(const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids, float* dists,
+                      uint32_t* counts, int memspace, void* user_stream) {
+    if (nq == 0) return SCANN_OK;  // searcher.rs:175-177
+    SCANN_REQUIRE(queries && counts, SCANN_INVALID_ARGUMENT, "NULL buffer");
+    std::lock_guard<std::mutex> lock(mu);
+    DeviceGuard g(device);
+    cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(user_stream)
+                                               : (user_stream ? static_cast<cudaStream_t>(user_stream) : stream);
+    const bool host = memspace == SCANN_HOST;
+    if (n == 0) {  // empty dataset -> Ok(vec![]) (searcher.rs:78-80) before any dimension check
+      if (host) memset(counts, 0, nq * sizeof(uint32_t));
+      else SCANN_CUDA(cudaMemsetAsync(counts, 0, nq * sizeof(uint32_t), s));
+      return SCANN_OK;
+    }
+    SCANN_REQUIRE(qdim == dim, SCANN_INVALID_ARGUMENT,
+                  "Query dimensionality %zu does not match dataset dimensionality %zu", qdim, dim);
+    SCANN_REQUIRE(k >= 1 && ids && dists, SCANN_INVALID_ARGUMENT, "k must be >= 1 and outputs non-NULL");
+    const size_t kk = std::min(k, n);                  // k clamped to n (searcher.rs:91)
+    const size_t kc = std::min(n, kk + kBfMargin);     // candidates carried per query
+    SCANN_REQUIRE(kc <= 2048, SCANN_INVALID_ARGUMENT, "k = %zu too large (max %d)", k, 2048 - kBfMargin);
+    const size_t qt = std::min<size_t>(kQTile, (nq + kBM - 1) / kBM * kBM);
+    const size_t nt = std::min<size_t>(kNTile, n_pad);
+
+    size_t need = Workspace::padded(qt * dim_pad * 4) + Workspace::padded(qt * 4) + Workspace::padded(qt * nt * 4) +
+                  Workspace::padded(qt * kc * 8) + Workspace::padded(qt * kc * 4) + 4096;
+    if (host)
+      need += Workspace::padded(qt * dim * 4) + 2 * Workspace::padded(qt * k * 4) + Workspace::padded(qt * 4);
+    SCANN_TRY(ws.reserve(need));
+    float* Apad = ws.take<float>(qt * dim_pad);
+    float* qn = ws.take<float>(qt);
+    float* scores = ws.take<float>(qt * nt);
+    uint64_t* state = ws.take<uint64_t>(qt * kc);
+    uint32_t* cand = ws.take<uint32_t>(qt * kc);
+    float* hq = nullptr;
+    uint32_t *hids = nullptr, *hcounts = nullptr;
+    float* hd = nullptr;
+    if (host) {
+      hq = ws.take<float>(qt * dim);
+      hids = ws.take<uint32_t>(qt * k);
+      hd = ws.take<float>(qt * k);
+      hcounts = ws.take<uint32_t>(qt);
+    }
+    const int p2 = next_pow2(static_cast<int>(kc));
+    const size_t sel_smem = (kc + kBfChunk + p2) * 8 + 264 * 4;
+    SCANN_CUDA(cudaFuncSetAttribute(bf_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sel_smem)));
+
+    for (size_t q0 = 0; q0 < nq; q0 += qt) {
+      const size_t nqc = std::min(qt, nq - q0);
+      const size_t rows_pad = (nqc + kBM - 1) / kBM * kBM;
+      const float* qsrc = queries + q0 * dim;
+      if (host) {
+        SCANN_CUDA(cudaMemcpyAsync(hq, qsrc, nqc * dim * 4, cudaMemcpyHostToDevice, s));
+        qsrc = hq;
+      }
+      pad_queries_kernel<<<static_cast<unsigned>((rows_pad + 7) / 8), 256, 0, s>>>(qsrc, nqc, dim, dim_pad, rows_pad,
+                                                                                   Apad, qn);
+      for (size_t r0 = 0; r0 < n; r0 += nt) {
+        const size_t ncols = std::min(nt, n - r0);
+        const size_t cols_pad = (ncols + kBN - 1) / kBN * kBN;
+        dim3 grid(static_cast<unsigned>(cols_pad / kBN), static_cast<unsigned>(rows_pad / kBM));
+        if (i8)
+          bf_gemm_kernel<true><<<grid, 256, 0, s>>>(Apad, rows_i.p + r0 * dim_pad, static_cast<int>(dim_pad), qn,
+                                                    xn.p + r0, scale, measure, scores, static_cast<int>(nt));
+        else
+          bf_gemm_kernel<false><<<grid, 256, 0, s>>>(Apad, rows_f.p + r0 * dim_pad, static_cast<int>(dim_pad), qn,
+                                                     xn.p + r0, 1.0f, measure, scores, static_cast<int>(nt));
+        const int have = static_cast<int>(std::min(kc, r0));
+        bf_select_kernel<<<static_cast<unsigned>(nqc), 256, sel_smem, s>>>(scores, static_cast<int>(nt),
+                                                                           static_cast<int>(ncols),
+                                                                           static_cast<uint32_t>(r0), state, have,
+                                                                           static_cast<int>(kc));
+      }
+      SCANN_CUDA(cudaGetLastError());
+      state_to_cand_kernel<<<static_cast<unsigned>((nqc * kc + 255) / 256), 256, 0, s>>>(state, nqc * kc, cand);
+      RescoreParams rp;
+      rp.queries = qsrc;
+      rp.dim = dim;
+      rp.raw = i8 ? nullptr : rows_f.p;
+      rp.raw_i8 = i8 ? rows_i.p : nullptr;
+      rp.scale = scale;
+      rp.stride = dim_pad;
+      rp.measure = measure;
+      uint32_t* oid = host ? hids : ids + q0 * k;
+      float* od = host ? hd : dists + q0 * k;
+      uint32_t* oc = host ? hcounts : counts + q0;
+      SCANN_TRY(launch_rescore_topk(rp, cand, nqc, kc, k, oid, od, oc, s));
+      if (host) {
+        SCANN_CUDA(cudaMemcpyAsync(ids + q0 * k, hids, nqc * k * 4, cudaMemcpyDeviceToHost, s));
+        SCANN_CUDA(cudaMemcpyAsync(dists + q0 * k, hd, nqc * k * 4, cudaMemcpyDeviceToHost, s));
+        SCANN_CUDA(cudaMemcpyAsync(counts + q0, hcounts, nqc * 4, cudaMemcpyDeviceToHost, s));
+        SCANN_CUDA(cudaStreamSynchronize(s));
+      }
+    }
+    return SCANN_OK;
+  }
+
+  void destroy() {
+    DeviceGuard g(device);
+    cudaDeviceSynchronize();
+    ws.release();
+    rows_f.free_();
+    rows_i.free_();
+    xn.free_();
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+// ---- scalar quantiser (build helper) -----------------------------------------------------------
+// QuantizationStats::from_dataset (src/quantization/mod.rs:77-110): f32 min/max, f64 Σ and Σ²
+__global__ void __launch_bounds__(256) sq8_stats_kernel(const float* __restrict__ db, size_t n, size_t dim,
+                                                        size_t stride, double* __restrict__ acc /* sum, sumsq */,
+                                                        float* __restrict__ mm /* min,max as ordered u32 */) {
+  __shared__ double s_sum[256], s_sq[256];
+  __shared__ uint32_t s_mn[256], s_mx[256];
+  double sum = 0.0, sq = 0.0;
+  uint32_t mn = 0xFFFFFFFFu, mx = 0;
+  const size_t total = n * dim;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t r = i / dim, d = i - r * dim;
+    float v = db[r * stride + d];
+    sum += static_cast<double>(v);
+    sq += static_cast<double>(v) * static_cast<double>(v);
+    uint32_t kf = f32_key(v);
+    mn = min(mn, kf);
+    mx = max(mx, kf);
+  }
+  s_sum[threadIdx.x] = sum;
+  s_sq[threadIdx.x] = sq;
+  s_mn[threadIdx.x] = mn;
+  s_mx[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+      s_sq[threadIdx.x] += s_sq[threadIdx.x + o];
+      s_mn[threadIdx.x] = min(s_mn[threadIdx.x], s_mn[threadIdx.x + o]);
+      s_mx[threadIdx.x] = max(s_mx[threadIdx.x], s_mx[threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(&acc[0], s_sum[0]);
+    atomicAdd(&acc[1], s_sq[0]);
+    atomicMin(reinterpret_cast<uint32_t*>(mm), s_mn[0]);
+    atomicMax(reinterpret_cast<uint32_t*>(mm) + 1, s_mx[0]);
+  }
+}
+
+// ScalarQuantizer::quantize_value (src/quantization/scalar.rs:162-166)
+__global__ void sq8_quantize_kernel(const float* __restrict__ db, size_t n, size_t dim, size_t stride, float mn,
+                                    float mx, float inv_scale, int8_t* __restrict__ out) {
+  size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  size_t r = i / dim, d = i - r * dim;
+  float v = db[r * stride + d];
+  float c = v;
+  if (c < mn) c = mn;
+  if (c > mx) c = mx;
+  float rr = roundf(__fmul_rn(__fsub_rn(c, mn), inv_scale));
+  int qi;
+  if (!(rr == rr)) qi = 0;
+  else if (rr >= 2147483648.0f) qi = 2147483647;
+  else if (rr <= -2147483648.0f) qi = -2147483647 - 1;
+  else qi = static_cast<int>(rr);
+  qi = min(max(qi, 0), 255);
+  out[i] = static_cast<int8_t>(static_cast<uint8_t>(qi));
+}
+
+}  // namespace scann
+
+struct scann_bf {
+  scann::BfCore core;
+};
+struct scann_sq8 {
+  scann::BfCore core;
+};
+
+extern "C" {
+
+scann_status scann_bf_create(const float* db, size_t n, size_t dim, size_t stride, int measure, int device,
+                             int memspace, scann_bf** out) {
+  using namespace scann;
+  SCANN_REQUIRE(out != nullptr, SCANN_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  SCANN_REQUIRE(measure == SCANN_SQL2 || measure == SCANN_L2 || measure == SCANN_DOT, SCANN_UNIMPLEMENTED,
+                "distance measure %d is outside the GPU hot path (SqL2, L2, Dot)", measure);
+  SCANN_REQUIRE(n == 0 || (db != nullptr && dim > 0 && stride >= dim), SCANN_INVALID_ARGUMENT, "bad dataset arguments");
+  SCANN_REQUIRE(n < 0xFFFFFFFFull, SCANN_INVALID_ARGUMENT, "dataset too large for u32 ids");
+  SCANN_TRY(check_device(device));
+  DeviceGuard g(device);
+  scann_bf* h = new scann_bf();
+  scann_status st = h->core.init(db, n, dim, stride, measure, false, 1.0f, device, memspace);
+  if (st != SCANN_OK) {
+    h->core.destroy();
+    delete h;
+    return st;
+  }
+  *out = h;
+  return SCANN_OK;
+}
+
+scann_status scann_bf_search(scann_bf* h, const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids,
+                             float* dists, uint32_t* counts, int memspace, void* stream) {
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  return h->core.search(queries, nq, qdim, k, ids, dists, counts, memspace, stream);
+}
+
+void scann_bf_destroy(scann_bf* h) {
+  if (!h) return;
+  h->core.destroy();
+  delete h;
+}
+
+scann_status scann_sq8_create(const int8_t* codes, size_t n, size_t dim, float scale, int measure, int device,
+                              int memspace, scann_sq8** out) {
+  using namespace scann;
+  SCANN_REQUIRE(out != nullptr, SCANN_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  SCANN_REQUIRE(measure == SCANN_SQL2 || measure == SCANN_L2 || measure == SCANN_DOT, SCANN_UNIMPLEMENTED,
+                "distance measure %d is outside the GPU hot path (SqL2, L2, Dot)", measure);
+  SCANN_REQUIRE(n == 0 || (codes != nullptr && dim > 0), SCANN_INVALID_ARGUMENT, "bad dataset arguments");
+  SCANN_REQUIRE(n < 0xFFFFFFFFull, SCANN_INVALID_ARGUMENT, "dataset too large for u32 ids");
+  SCANN_TRY(check_device(device));
+  DeviceGuard g(device);
+  scann_sq8* h = new scann_sq8();
+  scann_status st = h->core.init(codes, n, dim, dim, measure, true, scale, device, memspace);
+  if (st != SCANN_OK) {
+    h->core.destroy();
+    delete h;
+    return st;
+  }
+  *out = h;
+  return SCANN_OK;
+}
+
+scann_status scann_sq8_search(scann_sq8* h, const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids,
+                              float* dists, uint32_t* counts, int memspace, void* stream) {
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  return h->core.search(queries, nq, qdim, k, ids, dists, counts, memspace, stream);
+}
+
+void scann_sq8_destroy(scann_sq8* h) {
+  if (!h) return;
+  h->core.destroy();
+  delete h;
+}
+
+scann_status scann_sq8_quantize(const float* db, size_t n, size_t dim, size_t stride, int8_t* codes, float* cal4,
+                                int device, int memspace) {
+  using namespace scann;
+  SCANN_REQUIRE(n > 0 && dim > 0, SCANN_INVALID_ARGUMENT, "Cannot quantize empty dataset");  // scalar.rs:199-201
+  SCANN_REQUIRE(db && codes && cal4 && stride >= dim, SCANN_INVALID_ARGUMENT, "bad arguments");
+  SCANN_TRY(check_device(device));
+  DeviceGuard g(device);
+  const bool host = memspace == SCANN_HOST;
+  DevBuf<float> d_db;
+  DevBuf<int8_t> d_codes;
+  DevBuf<double> d_acc;
+  DevBuf<float> d_mm;
+  const float* src = db;
+  if (host) {
+    SCANN_TRY(d_db.upload(db, n * stride, SCANN_HOST, 0));
+    src = d_db.p;
+    SCANN_TRY(d_codes.alloc(n * dim));
+  }
+  SCANN_TRY(d_acc.alloc(2));
+  SCANN_TRY(d_mm.alloc(2));
+  SCANN_CUDA(cudaMemset(d_acc.p, 0, 2 * sizeof(double)));
+  uint32_t init_mm[2] = {0xFFFFFFFFu, 0u};
+  SCANN_CUDA(cudaMemcpy(d_mm.p, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice));
+  sq8_stats_kernel<<<148 * 4, 256>>>(src, n, dim, stride, d_acc.p, d_mm.p);
+  SCANN_CUDA(cudaGetLastError());
+  double acc[2];
+  uint32_t mmk[2];
+  SCANN_CUDA(cudaMemcpy(acc, d_acc.p, sizeof(acc), cudaMemcpyDeviceToHost));
+  SCANN_CUDA(cudaMemcpy(mmk, d_mm.p, sizeof(mmk), cudaMemcpyDeviceToHost));
+  auto unkey = [](uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  // Host-side scalar epilogue of QuantizationStats::from_dataset + ScalarQuantizer::calibrate
+  // (quantization/mod.rs:96-102, scalar.rs:112-129).  NOTE: the f64 sums are reduced in a different
+  // order than the reference's sequential loop; mean/std can differ in the last f64 bits before the
+  // cast to f32 (documented in DESIGN.md).
+  const double count = static_cast<double>(n) * static_cast<double>(dim);
+  const float data_min = unkey(mmk[0]), data_max = unkey(mmk[1]);
+  const float mean = static_cast<float>(acc[0] / count);
+  const float var = (n * dim > 1) ? static_cast<float>((acc[1] - acc[0] * acc[0] / count) / (count - 1.0)) : 0.0f;
+  const float sd = sqrtf(var);
+  const float range0 = 3.0f * sd;
+  float mn = fmaxf(mean - range0, data_min);
+  float mx = fminf(mean + range0, data_max);
+  float range = mx - mn;
+  float scale = 1.0f, inv_scale = 1.0f;
+  if (range > 1e-10f) {
+    scale = range / 255.0f;
+    inv_scale = 255.0f / range;
+  }
+  int8_t* dst = host ? d_codes.p : codes;
+  size_t total = n * dim;
+  sq8_quantize_kernel<<<static_cast<unsigned>((total + 255) / 256), 256>>>(src, n, dim, stride, mn, mx, inv_scale, dst);
+  SCANN_CUDA(cudaGetLastError());
+  if (host) SCANN_CUDA(cudaMemcpy(codes, dst, total, cudaMemcpyDeviceToHost));
+  SCANN_CUDA(cudaDeviceSynchronize());
+  float cal[4] = {mn, mx, scale, inv_scale};
+  if (host) memcpy(cal4, cal, sizeof(cal));
+  else SCANN_CUDA(cudaMemcpy(cal4, cal, sizeof(cal), cudaMemcpyHostToDevice));
+  return SCANN_OK;
+}
+
+}  // extern "C"

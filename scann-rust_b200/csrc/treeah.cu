@@ -1,0 +1,800 @@
+// Tree-AH / Tree-X-Hybrid search with the LUT16 path (src/tree_x_hybrid/mod.rs:245-364 composed with
+// src/hashes/lut16.rs and src/hashes/lut16_simd.rs).
+//
+// Per batch (all on one stream, no host synchronisation inside):
+//   1. partition        exact centroid scoring + top-L tokens                      (partition.cu)
+//   2. worklist         (query, rank) pairs are grouped BY LEAF: count -> scan -> scatter -> items.
+//                       A work item = one leaf + up to G pairs that probe it.
+//   3. lut16_scan       persistent kernel, one CTA per work item: builds the G residual LUT16 tables
+//                       in shared memory (bit-exact quantiser), streams the leaf's blocked 4-bit codes
+//                       ONCE for all G queries (register-LUT PRMT lookups, integer accumulation),
+//                       keeps an exact running top-R per query (threshold filter + radix select in
+//                       shared memory) and writes <= R (approx distance, position) candidates per pair.
+//   4. merge_reorder    one CTA per query: exact top-R of the <= L*R candidates by
+//                       (approx distance, leaf rank, position), exact distance of the R raw rows in the
+//                       reference's AVX2 order, final order by (exact distance, approx rank), top-k.
+//
+// What the reference does per leaf is FastTopNeighbors(R) + concat + stable sort + truncate(R)
+// (:283-290, :322-338); the global top-R by approximate distance is a subset of the union of the
+// per-leaf top-R lists, so steps 3+4 return the same candidate set except for the order inside exact
+// ties of the approximate distance (BASELINE.json exempts those).
+#include <algorithm>
+
+#include "kernels.h"
+#include "lut16_device.cuh"
+
+namespace scann {
+
+// ------------------------------------------------------------------------------------ index build
+// Converts PackedCodes4Bit rows (src/hashes/lut16.rs:43-61; row-major, low nibble = even subspace)
+// to the blocked layout documented in lut16_device.cuh.  One thread per output u32.
+__global__ void repack_blocked_kernel(const uint8_t* __restrict__ packed, const uint32_t* __restrict__ blk_leaf,
+                                      const uint32_t* __restrict__ blk_off, const uint64_t* __restrict__ pt_off,
+                                      int S, int SG, size_t total_words, uint32_t* __restrict__ out) {
+  size_t w = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w >= total_words) return;
+  int j = static_cast<int>(w & 3);
+  int lane = static_cast<int>((w >> 2) & 31);
+  size_t rest = w >> 7;
+  int sg = static_cast<int>(rest % SG);
+  size_t gb = rest / SG;
+  int s = sg * 4 + j;
+  uint32_t word = 0;
+  if (s < S) {
+    uint32_t leaf = blk_leaf[gb];
+    uint64_t p0 = pt_off[leaf] + static_cast<uint64_t>(gb - blk_off[leaf]) * kBlockPts + lane * 8;
+    uint64_t pend = pt_off[leaf + 1];
+    int bpp = (S + 1) / 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint64_t p = p0 + i;
+      if (p < pend) {
+        uint8_t b = packed[p * bpp + (s >> 1)];
+        uint32_t nib = (s & 1) ? (b >> 4) : (b & 0x0F);
+        word |= nib << (4 * i);
+      }
+    }
+  }
+  out[w] = word;
+}
+
+// --------------------------------------------------------------------------------------- worklist
+__global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K,
+                                uint32_t* __restrict__ leaf_cnt) {
+  size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  uint32_t leaf = tokens[p];
+  if (leaf < K) atomicAdd(&leaf_cnt[leaf], 1u);
+}
+
+// single block: exclusive scans of pair counts and item counts per leaf; also accumulates the
+// algorithmic scan bytes of this batch (Σ pairs * leaf_size * bytes_per_point) for the roofline.
+__global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
+                                                       const uint64_t* __restrict__ pt_off, uint32_t bpp,
+                                                       uint32_t* __restrict__ pair_start,
+                                                       uint32_t* __restrict__ item_start,
+                                                       uint32_t* __restrict__ counters /* [0]=total items,[1]=next */,
+                                                       unsigned long long* __restrict__ stats) {
+  __shared__ uint32_t s_pair[1024], s_item[1024];
+  __shared__ unsigned long long s_bytes[1024];
+  const uint32_t per = (K + 1023) / 1024;
+  const uint32_t b = threadIdx.x * per, e = min(K, b + per);
+  uint32_t pc = 0, ic = 0;
+  unsigned long long bytes = 0;
+  for (uint32_t l = b; l < e; ++l) {
+    uint32_t c = leaf_cnt[l];
+    pc += c;
+    ic += (c + G - 1) / G;
+    bytes += static_cast<unsigned long long>(c) * (pt_off[l + 1] - pt_off[l]) * bpp;
+  }
+  s_pair[threadIdx.x] = pc;
+  s_item[threadIdx.x] = ic;
+  s_bytes[threadIdx.x] = bytes;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+    uint32_t vp = 0, vi = 0;
+    unsigned long long vb = 0;
+    if (threadIdx.x >= o) {
+      vp = s_pair[threadIdx.x - o];
+      vi = s_item[threadIdx.x - o];
+      vb = s_bytes[threadIdx.x - o];
+    }
+    __syncthreads();
+    s_pair[threadIdx.x] += vp;
+    s_item[threadIdx.x] += vi;
+    s_bytes[threadIdx.x] += vb;
+    __syncthreads();
+  }
+  uint32_t pbase = s_pair[threadIdx.x] - pc, ibase = s_item[threadIdx.x] - ic;
+  for (uint32_t l = b; l < e; ++l) {
+    uint32_t c = leaf_cnt[l];
+    pair_start[l] = pbase;
+    item_start[l] = ibase;
+    pbase += c;
+    ibase += (c + G - 1) / G;
+  }
+  if (threadIdx.x == 1023) {
+    pair_start[K] = s_pair[1023];
+    item_start[K] = s_item[1023];
+    counters[0] = s_item[1023];
+    counters[1] = 0;
+    atomicAdd(&stats[0], s_bytes[1023]);
+    atomicAdd(&stats[1], static_cast<unsigned long long>(s_pair[1023]));
+  }
+}
+
+__global__ void wl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K,
+                                  const uint32_t* __restrict__ pair_start, uint32_t* __restrict__ cursor,
+                                  uint32_t* __restrict__ sorted_pairs) {
+  size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  uint32_t leaf = tokens[p];
+  if (leaf < K) {
+    uint32_t slot = atomicAdd(&cursor[leaf], 1u);
+    sorted_pairs[pair_start[leaf] + slot] = static_cast<uint32_t>(p);
+  }
+}
+
+__global__ void wl_items_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
+                                const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ item_start,
+                                uint4* __restrict__ items) {
+  uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= K) return;
+  uint32_t c = leaf_cnt[l], pb = pair_start[l], ib = item_start[l];
+  for (uint32_t g = 0; g * G < c; ++g) items[ib + g] = make_uint4(l, pb + g * G, min(static_cast<uint32_t>(G), c - g * G), 0u);
+}
+
+// ------------------------------------------------------------------------------- the scan kernel
+struct ScanArgs {
+  const uint4* codes;
+  const uint32_t* blk_off;
+  const uint64_t* pt_off;
+  const float* centers;
+  const float* codebook;
+  const float* queries;
+  const uint4* items;
+  const uint32_t* sorted_pairs;
+  uint32_t* counters;  // [0] total items, [1] next item
+  uint2* cand;         // [P][R] {approx distance bits, position in leaf}
+  uint32_t* cand_cnt;  // [P]
+  int dim, S, ds, SG, L, R, cap, pos_bits, use_residuals;
+};
+
+template <int G>
+__global__ void __launch_bounds__(kScanWarps * 32, 2) lut16_scan_kernel(const ScanArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int S4 = a.SG * 4;
+  uint4* lut = reinterpret_cast<uint4*>(smem);                      // [G][S4]
+  float* qres = reinterpret_cast<float*>(lut + G * S4);             // [G][dim]
+  uint32_t* buf = reinterpret_cast<uint32_t*>(qres + ((G * a.dim + 3) & ~3));  // [G][cap], 16-B aligned
+  uint32_t* hist = buf + static_cast<size_t>(G) * a.cap;            // [kScanWarps][256]
+  float* s_mult = reinterpret_cast<float*>(hist + kScanWarps * 256);
+  float* s_bias = s_mult + G;
+  uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_bias + G);
+  uint32_t* s_cnt = s_thr + G;
+  uint32_t* s_pair = s_cnt + G;
+  uint32_t* s_item = s_pair + G;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t total_items = a.counters[0];
+  const uint32_t pos_mask = (1u << a.pos_bits) - 1u;
+
+  for (;;) {
+    __syncthreads();  // previous item's shared memory is dead
+    if (tid == 0) *s_item = atomicAdd(&a.counters[1], 1u);
+    __syncthreads();
+    const uint32_t item = *s_item;
+    if (item >= total_items) break;
+    const uint4 it = a.items[item];
+    const uint32_t leaf = it.x, pbeg = it.y;
+    const int ng = static_cast<int>(it.z);
+    const uint32_t blk0 = a.blk_off[leaf];
+    const int nblk = static_cast<int>(a.blk_off[leaf + 1] - blk0);
+    const uint32_t leaf_n = static_cast<uint32_t>(a.pt_off[leaf + 1] - a.pt_off[leaf]);
+
+    // (1) query residuals: q - centroid (src/tree_x_hybrid/mod.rs:309-316)
+    for (int idx = tid; idx < G * a.dim; idx += kScanWarps * 32) {
+      int g = idx / a.dim, d = idx - g * a.dim;
+      float v = 0.0f;
+      if (g < ng) {
+        uint32_t pair = a.sorted_pairs[pbeg + g];
+        uint32_t q = pair / static_cast<uint32_t>(a.L);
+        v = a.queries[static_cast<size_t>(q) * a.dim + d];
+        if (a.use_residuals) v = __fsub_rn(v, __ldg(a.centers + static_cast<size_t>(leaf) * a.dim + d));
+      }
+      qres[idx] = v;
+    }
+    const int nfull0 = min(kScanWarps, static_cast<int>(leaf_n / kBlockPts));  // full blocks of tile 0
+    if (tid < G) {
+      s_pair[tid] = tid < ng ? a.sorted_pairs[pbeg + tid] : 0xFFFFFFFFu;
+      s_cnt[tid] = static_cast<uint32_t>(nfull0) * kBlockPts;
+      s_thr[tid] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+
+    // (2) LUT16 build, warp g builds query g's table
+    for (int g = warp; g < G; g += kScanWarps) {
+      uint8_t* l8 = reinterpret_cast<uint8_t*>(lut + g * S4);
+      if (g < ng) {
+        float mult, bias;
+        warp_build_lut16(qres + g * a.dim, a.codebook, a.S, S4, a.ds, l8, &mult, &bias, lane);
+        if (lane == 0) {
+          s_mult[g] = mult;
+          s_bias[g] = __fmul_rn(bias, static_cast<float>(a.S));  // bias * S, rounded once (lut16_simd.rs:137)
+        }
+      } else {
+        for (int e = lane; e < S4 * 16; e += 32) l8[e] = 0;
+      }
+    }
+    __syncthreads();
+
+    // (3) stream the leaf, one 256-point block per warp per tile
+    const int ntiles = (nblk + kScanWarps - 1) / kScanWarps;
+    for (int t = 0; t < ntiles; ++t) {
+      const int b = t * kScanWarps + warp;
+      if (b < nblk) {
+        uint32_t sums[G][8];
+        scan_block<G>(a.codes + (static_cast<size_t>(blk0) + b) * a.SG * 32, a.SG, lut, S4, lane, sums);
+        const uint32_t pos0 = static_cast<uint32_t>(b) * kBlockPts + lane * 8;
+        if (t == 0 && b < nfull0) {
+          // no threshold yet: every point of a full block goes to its fixed slot
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (g < ng) {
+              uint4* dst = reinterpret_cast<uint4*>(buf + static_cast<size_t>(g) * a.cap + pos0);
+              dst[0] = make_uint4((sums[g][0] << a.pos_bits) | (pos0 + 0), (sums[g][1] << a.pos_bits) | (pos0 + 1),
+                                  (sums[g][2] << a.pos_bits) | (pos0 + 2), (sums[g][3] << a.pos_bits) | (pos0 + 3));
+              dst[1] = make_uint4((sums[g][4] << a.pos_bits) | (pos0 + 4), (sums[g][5] << a.pos_bits) | (pos0 + 5),
+                                  (sums[g][6] << a.pos_bits) | (pos0 + 6), (sums[g][7] << a.pos_bits) | (pos0 + 7));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (g < ng) {
+              const uint32_t thr = s_thr[g];
+              uint32_t* bg = buf + static_cast<size_t>(g) * a.cap;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t pos = pos0 + i;
+                const uint32_t key = (sums[g][i] << a.pos_bits) | pos;
+                if (pos < leaf_n && key < thr) {
+                  uint32_t slot = atomicAdd(&s_cnt[g], 1u);
+                  if (slot < static_cast<uint32_t>(a.cap)) bg[slot] = key;
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // exact compaction to the R best when the buffer could overflow in the next tile
+      for (int g = warp; g < ng; g += kScanWarps) {
+        int c = static_cast<int>(min(s_cnt[g], static_cast<uint32_t>(a.cap)));
+        if (c > a.R && (t == ntiles - 1 || c > 2 * a.R)) {
+          uint32_t T = warp_select_u32(buf + static_cast<size_t>(g) * a.cap, c, a.R, hist + warp * 256, lane);
+          if (lane == 0) {
+            s_cnt[g] = static_cast<uint32_t>(a.R);
+            s_thr[g] = T;
+          }
+        }
+      }
+      __syncthreads();
+    }
+
+    // (4) write this item's candidates: approx distance = sum*multiplier + bias*S (lut16_simd.rs:136-140)
+    for (int g = warp; g < ng; g += kScanWarps) {
+      const int c = static_cast<int>(min(s_cnt[g], static_cast<uint32_t>(a.R)));
+      const uint32_t pair = s_pair[g];
+      const float mult = s_mult[g], biasS = s_bias[g];
+      const uint32_t* bg = buf + static_cast<size_t>(g) * a.cap;
+      uint2* out = a.cand + static_cast<size_t>(pair) * a.R;
+      for (int i = lane; i < c; i += 32) {
+        uint32_t key = bg[i];
+        float dist = lut16_dequant(key >> a.pos_bits, mult, biasS);
+        out[i] = make_uint2(__float_as_uint(dist), key & pos_mask);
+      }
+      if (lane == 0) a.cand_cnt[pair] = static_cast<uint32_t>(c);
+    }
+  }
+}
+
+static size_t scan_smem_bytes(int G, int S4, int dim, int cap) {
+  return static_cast<size_t>(G) * S4 * 16 + static_cast<size_t>((G * dim + 3) & ~3) * 4 +
+         static_cast<size_t>(G) * cap * 4 +
+         kScanWarps * 256 * 4 + static_cast<size_t>(G) * 5 * 4 + 16;
+}
+
+// --------------------------------------------------------------------------- merge + exact reorder
+struct MergeArgs {
+  const uint2* cand;
+  const uint32_t* cand_cnt;
+  const uint32_t* tokens;
+  const uint64_t* pt_off;
+  const uint32_t* ids;
+  const float* raw;
+  size_t stride;
+  const float* queries;
+  int dim, L, R, k, measure;
+  uint32_t K;
+  uint32_t* out_ids;
+  float* out_dists;
+  uint32_t* out_counts;
+  uint32_t* cand_ids;
+  float* cand_dists;
+  uint32_t* cand_counts;
+};
+
+constexpr int kMergeChunk = 2048;
+
+__global__ void __launch_bounds__(256) merge_reorder_kernel(const MergeArgs a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int p2 = next_pow2(a.R < 1 ? 1 : a.R);
+  uint64_t* buf = reinterpret_cast<uint64_t*>(sm);              // [R + chunk]
+  uint64_t* out = buf + (a.R + kMergeChunk);                    // [p2]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(out + p2);       // [264]
+  uint32_t* prefix = hist + 264;                                // [L + 1]
+  uint32_t* cid = prefix + (a.L + 1);                           // [p2]
+  float* qs = reinterpret_cast<float*>(cid + p2);               // [dim]
+  const int tid = threadIdx.x;
+  const size_t q = blockIdx.x;
+
+  for (int r = tid; r < a.L; r += 256) {
+    uint32_t leaf = a.tokens[q * a.L + r];
+    prefix[r + 1] = leaf < a.K ? a.cand_cnt[q * a.L + r] : 0u;
+  }
+  for (int d = tid; d < a.dim; d += 256) qs[d] = a.queries[q * a.dim + d];
+  __syncthreads();
+  if (tid == 0) {
+    prefix[0] = 0;
+    for (int r = 0; r < a.L; ++r) prefix[r + 1] += prefix[r];
+  }
+  __syncthreads();
+  const int total = static_cast<int>(prefix[a.L]);
+  const uint2* cq = a.cand + q * static_cast<size_t>(a.L) * a.R;
+  auto gen = [&](int i) -> uint64_t {
+    int lo = 0, hi = a.L;  // largest r with prefix[r] <= i
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (prefix[mid] <= static_cast<uint32_t>(i)) lo = mid;
+      else hi = mid;
+    }
+    uint2 c = cq[static_cast<size_t>(lo) * a.R + (i - prefix[lo])];
+    return (static_cast<uint64_t>(f32_key(__uint_as_float(c.x))) << 32) | (static_cast<uint64_t>(lo) << 22) | c.y;
+  };
+  const int m = block_topr_sorted<256, kMergeChunk>(gen, total, a.R, buf, out, hist);
+
+  // the R approximate candidates, in (approx distance, leaf rank, position) order
+  for (int j = tid; j < p2; j += 256) {
+    uint32_t id = 0xFFFFFFFFu;
+    float ad = __int_as_float(0x7F800000);
+    if (j < m) {
+      uint64_t key = out[j];
+      uint32_t r = static_cast<uint32_t>((key >> 22) & 1023u), pos = static_cast<uint32_t>(key & 0x3FFFFFu);
+      uint32_t leaf = a.tokens[q * a.L + r];
+      id = a.ids[a.pt_off[leaf] + pos];
+      ad = key_f32(static_cast<uint32_t>(key >> 32));
+    }
+    cid[j] = id;
+    if (a.cand_ids && j < a.R) {
+      a.cand_ids[q * a.R + j] = id;
+      a.cand_dists[q * a.R + j] = ad;
+    }
+  }
+  if (a.cand_counts && tid == 0) a.cand_counts[q] = static_cast<uint32_t>(m);
+  __syncthreads();
+
+  uint64_t* fin = buf;  // [p2] final keys
+  if (a.raw != nullptr) {
+    // exact distance of every candidate row, 8 lanes per row (src/tree_x_hybrid/mod.rs:342-364)
+    const int grp = tid >> 3, sub = tid & 7;
+    for (int j0 = 0; j0 < m; j0 += 32) {
+      int j = j0 + grp;
+      bool valid = j < m;
+      const float* row = a.raw + static_cast<size_t>(valid ? cid[j] : cid[0]) * a.stride;
+      float d = exact_pair_distance<false>(qs, row, a.dim, a.measure, 0.0f, sub);
+      if (valid && sub == 0) fin[j] = (static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(j);
+    }
+    for (int j = m + tid; j < p2; j += 256) fin[j] = ~0ull;
+    __syncthreads();
+    block_bitonic_sort<256>(fin, p2);  // stable by construction: ties broken by approximate rank j
+  } else {
+    for (int j = tid; j < p2; j += 256)
+      fin[j] = j < m ? ((out[j] & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>(j)) : ~0ull;
+    __syncthreads();
+  }
+  const int kk = a.k < m ? a.k : m;
+  for (int j = tid; j < a.k; j += 256) {
+    if (j < kk) {
+      uint64_t key = fin[j];
+      a.out_ids[q * a.k + j] = cid[key & 0xFFFFFFFFu];
+      a.out_dists[q * a.k + j] = key_f32(static_cast<uint32_t>(key >> 32));
+    } else {
+      a.out_ids[q * a.k + j] = 0xFFFFFFFFu;
+      a.out_dists[q * a.k + j] = __int_as_float(0x7F800000);
+    }
+  }
+  if (tid == 0) a.out_counts[q] = static_cast<uint32_t>(kk);
+}
+
+static size_t merge_smem_bytes(int R, int L, int dim) {
+  int p2 = next_pow2(R < 1 ? 1 : R);
+  return (static_cast<size_t>(R) + kMergeChunk + p2) * 8 + 264 * 4 + (static_cast<size_t>(L) + 1) * 4 +
+         static_cast<size_t>(p2) * 4 + static_cast<size_t>(dim) * 4 + 16;
+}
+
+}  // namespace scann
+
+// ------------------------------------------------------------------------------------------ C ABI
+struct scann_treeah {
+  int device = 0;
+  size_t K = 0, dim = 0, S = 0, ds = 0, SG = 0, n = 0, num_raw = 0, stride = 0;
+  int use_residuals = 1, reorder_measure = SCANN_SQL2, pos_bits = 18;
+  uint32_t max_leaf = 0;
+  scann::DevBuf<float> centers, centersT, codebook, raw;
+  scann::DevBuf<uint32_t> codes, ids, blk_off;
+  scann::DevBuf<uint64_t> pt_off;
+  scann::DevBuf<unsigned long long> stats;  // [0] algorithmic scan bytes, [1] pairs of the last search
+  scann::Workspace ws;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  int sms = 148;
+};
+
+namespace scann {
+
+template <int G>
+static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
+  size_t smem = scan_smem_bytes(G, a.SG * 4, a.dim, a.cap);
+  SCANN_REQUIRE(smem <= 227 * 1024, SCANN_RESOURCE_EXHAUSTED, "scan kernel needs %zu B of shared memory (R too large)",
+                smem);
+  SCANN_CUDA(cudaFuncSetAttribute(lut16_scan_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+  int occ = 0;
+  SCANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lut16_scan_kernel<G>, kScanWarps * 32, smem));
+  if (occ < 1) occ = 1;
+  lut16_scan_kernel<G><<<sms * occ, kScanWarps * 32, smem, s>>>(a);
+  SCANN_CUDA(cudaGetLastError());
+  return SCANN_OK;
+}
+
+static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
+                                        uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cand_ids,
+                                        float* d_cand_dists, uint32_t* d_cand_counts, cudaStream_t s) {
+  const size_t K = h->K, P = nq * L;
+  // group size: how many queries share a leaf on average
+  double avg = static_cast<double>(P) / static_cast<double>(std::min<size_t>(K, P));
+  int G = avg >= 6.0 ? 8 : (avg >= 3.0 ? 4 : (avg >= 1.5 ? 2 : 1));
+  size_t max_items = P / G + std::min<size_t>(K, P) + 1;
+
+  float* scratch = h->ws.take<float>(nq * K);
+  uint32_t* tokens = h->ws.take<uint32_t>(P);
+  uint32_t* leaf_cnt = h->ws.take<uint32_t>(2 * K);  // counts + cursors
+  uint32_t* cursor = leaf_cnt + K;
+  uint32_t* pair_start = h->ws.take<uint32_t>(K + 1);
+  uint32_t* item_start = h->ws.take<uint32_t>(K + 1);
+  uint32_t* counters = h->ws.take<uint32_t>(4);
+  uint32_t* sorted_pairs = h->ws.take<uint32_t>(P);
+  uint4* items = h->ws.take<uint4>(max_items);
+  uint2* cand = h->ws.take<uint2>(P * R);
+  uint32_t* cand_cnt = h->ws.take<uint32_t>(P);
+
+  // 1. partition (K == 1 still goes through it: one centre, token 0)
+  SCANN_TRY(launch_partition(h->centersT.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, s));
+  // 2. worklist
+  SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 2 * K * sizeof(uint32_t), s));
+  SCANN_CUDA(cudaMemsetAsync(cand_cnt, 0, P * sizeof(uint32_t), s));
+  unsigned pb = static_cast<unsigned>((P + 255) / 256);
+  wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), leaf_cnt);
+  wl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->pt_off.p,
+                                    static_cast<uint32_t>((h->S + 1) / 2), pair_start, item_start, counters,
+                                    h->stats.p);
+  wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), pair_start, cursor, sorted_pairs);
+  wl_items_kernel<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
+                                                                        pair_start, item_start, items);
+  SCANN_CUDA(cudaGetLastError());
+  // 3. scan
+  ScanArgs a;
+  a.codes = reinterpret_cast<const uint4*>(h->codes.p);
+  a.blk_off = h->blk_off.p;
+  a.pt_off = h->pt_off.p;
+  a.centers = h->centers.p;
+  a.codebook = h->codebook.p;
+  a.queries = dq;
+  a.items = items;
+  a.sorted_pairs = sorted_pairs;
+  a.counters = counters;
+  a.cand = cand;
+  a.cand_cnt = cand_cnt;
+  a.dim = static_cast<int>(h->dim);
+  a.S = static_cast<int>(h->S);
+  a.ds = static_cast<int>(h->ds);
+  a.SG = static_cast<int>(h->SG);
+  a.L = static_cast<int>(L);
+  a.R = static_cast<int>(R);
+  a.cap = static_cast<int>((kTilePts + 2 * R + 31) / 32 * 32);
+  a.pos_bits = h->pos_bits;
+  a.use_residuals = h->use_residuals;
+  switch (G) {
+    case 8: SCANN_TRY(launch_scan<8>(a, h->sms, s)); break;
+    case 4: SCANN_TRY(launch_scan<4>(a, h->sms, s)); break;
+    case 2: SCANN_TRY(launch_scan<2>(a, h->sms, s)); break;
+    default: SCANN_TRY(launch_scan<1>(a, h->sms, s)); break;
+  }
+  // 4. merge + reorder
+  MergeArgs m;
+  m.cand = cand;
+  m.cand_cnt = cand_cnt;
+  m.tokens = tokens;
+  m.pt_off = h->pt_off.p;
+  m.ids = h->ids.p;
+  m.raw = h->raw.p;
+  m.stride = h->stride;
+  m.queries = dq;
+  m.dim = static_cast<int>(h->dim);
+  m.L = static_cast<int>(L);
+  m.R = static_cast<int>(R);
+  m.k = static_cast<int>(k);
+  m.measure = h->reorder_measure;
+  m.K = static_cast<uint32_t>(K);
+  m.out_ids = d_ids;
+  m.out_dists = d_dists;
+  m.out_counts = d_counts;
+  m.cand_ids = d_cand_ids;
+  m.cand_dists = d_cand_dists;
+  m.cand_counts = d_cand_counts;
+  size_t msm = merge_smem_bytes(static_cast<int>(R), static_cast<int>(L), static_cast<int>(h->dim));
+  SCANN_CUDA(cudaFuncSetAttribute(merge_reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(msm)));
+  merge_reorder_kernel<<<static_cast<unsigned>(nq), 256, msm, s>>>(m);
+  SCANN_CUDA(cudaGetLastError());
+  return SCANN_OK;
+}
+
+static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, size_t R, size_t k, bool host) {
+  size_t K = h->K, P = nq * L;
+  size_t b = 0;
+  auto add = [&](size_t bytes) { b += Workspace::padded(bytes); };
+  add(nq * K * 4);
+  add(P * 4);
+  add(2 * K * 4);
+  add((K + 1) * 4);
+  add((K + 1) * 4);
+  add(16);
+  add(P * 4);
+  add((P + K + 2) * 16);
+  add(P * R * 8);
+  add(P * 4);
+  if (host) {
+    add(nq * h->dim * 4);
+    add(nq * k * 4);
+    add(nq * k * 4);
+    add(nq * 4);
+    add(nq * R * 4);
+    add(nq * R * 4);
+    add(nq * 4);
+  }
+  return b + 4096;
+}
+
+}  // namespace scann
+
+extern "C" {
+
+scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, const float* codebook, size_t S,
+                                 const uint8_t* packed, const uint32_t* ids, const uint64_t* part_offsets,
+                                 size_t n, const float* raw, size_t num_raw, size_t stride, int use_residuals,
+                                 int reorder_measure, int device, int memspace, scann_treeah** out) {
+  using namespace scann;
+  SCANN_REQUIRE(out != nullptr, SCANN_INVALID_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  SCANN_REQUIRE(n > 0 && K > 0, SCANN_INVALID_ARGUMENT, "Cannot build from empty dataset");  // tree_x_hybrid/mod.rs:132-134
+  SCANN_REQUIRE(centers && codebook && packed && ids && part_offsets, SCANN_INVALID_ARGUMENT, "NULL index array");
+  SCANN_REQUIRE(S >= 1 && S <= 256, SCANN_INVALID_ARGUMENT, "num_subspaces %zu outside 1..256", S);
+  SCANN_REQUIRE(dim > 0 && dim % S == 0, SCANN_INVALID_ARGUMENT,
+                "Dimensionality %zu must be divisible by num_subspaces %zu", dim, S);  // codebook.rs:154-159
+  SCANN_REQUIRE(reorder_measure == SCANN_SQL2 || reorder_measure == SCANN_L2 || reorder_measure == SCANN_DOT,
+                SCANN_INVALID_ARGUMENT, "unsupported reorder measure %d", reorder_measure);
+  SCANN_REQUIRE(raw == nullptr || stride >= dim, SCANN_INVALID_ARGUMENT, "stride %zu < dim %zu", stride, dim);
+  SCANN_REQUIRE(K < 0xFFFFFFFFull && n < 0xFFFFFFFFull, SCANN_INVALID_ARGUMENT, "index too large for u32 ids");
+  SCANN_TRY(check_device(device));
+  DeviceGuard g(device);
+
+  scann_treeah* h = new scann_treeah();
+  h->device = device;
+  h->K = K;
+  h->dim = dim;
+  h->S = S;
+  h->ds = dim / S;
+  h->SG = (S + 3) / 4;
+  h->n = n;
+  h->num_raw = raw ? num_raw : 0;
+  h->stride = stride;
+  h->use_residuals = use_residuals ? 1 : 0;
+  h->reorder_measure = reorder_measure;
+  h->sms = sm_count(device);
+  int sum_bits = 1;
+  while ((1u << sum_bits) <= 255u * S) ++sum_bits;
+  h->pos_bits = 32 - sum_bits;
+  if (h->pos_bits > 22) h->pos_bits = 22;
+
+  scann_status st = SCANN_OK;
+  do {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      st = cuda_fail(cudaGetLastError(), "cudaStreamCreate", __FILE__, __LINE__);
+      break;
+    }
+    cudaStream_t s = h->stream;
+    // partition offsets on the host (block table is built there)
+    std::vector<uint64_t> off(K + 1);
+    if (cudaMemcpy(off.data(), part_offsets, (K + 1) * sizeof(uint64_t),
+                   memspace == SCANN_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost) != cudaSuccess) {
+      st = cuda_fail(cudaGetLastError(), "copy part_offsets", __FILE__, __LINE__);
+      break;
+    }
+    bool ok = off[0] == 0 && off[K] == n;
+    for (size_t l = 0; l < K && ok; ++l) ok = off[l] <= off[l + 1];
+    if (!ok) {
+      set_error("part_offsets must be non-decreasing with part_offsets[0]=0 and part_offsets[K]=n");
+      st = SCANN_INVALID_ARGUMENT;
+      break;
+    }
+    std::vector<uint32_t> blk_off(K + 1), blk_leaf;
+    uint64_t nb = 0, max_leaf = 0;
+    for (size_t l = 0; l < K; ++l) {
+      blk_off[l] = static_cast<uint32_t>(nb);
+      uint64_t sz = off[l + 1] - off[l];
+      max_leaf = std::max(max_leaf, sz);
+      nb += (sz + kBlockPts - 1) / kBlockPts;
+    }
+    blk_off[K] = static_cast<uint32_t>(nb);
+    if (max_leaf >= (1ull << h->pos_bits)) {
+      set_error("partition with %llu points exceeds the %d-bit in-leaf position limit for S=%zu",
+                static_cast<unsigned long long>(max_leaf), h->pos_bits, S);
+      st = SCANN_OUT_OF_RANGE;
+      break;
+    }
+    h->max_leaf = static_cast<uint32_t>(max_leaf);
+    blk_leaf.resize(nb);
+    for (size_t l = 0; l < K; ++l)
+      for (uint32_t b = blk_off[l]; b < blk_off[l + 1]; ++b) blk_leaf[b] = static_cast<uint32_t>(l);
+
+    DevBuf<uint8_t> d_packed;
+    DevBuf<uint32_t> d_blk_leaf;
+    size_t bpp = (S + 1) / 2;
+    if ((st = h->centers.upload(centers, K * dim, memspace, s)) != SCANN_OK) break;
+    if ((st = h->centersT.alloc(K * dim)) != SCANN_OK) break;
+    launch_transpose(h->centers.p, K, dim, h->centersT.p, s);
+    if ((st = h->codebook.upload(codebook, S * 16 * h->ds, memspace, s)) != SCANN_OK) break;
+    if ((st = h->ids.upload(ids, n, memspace, s)) != SCANN_OK) break;
+    if ((st = h->pt_off.upload(off.data(), K + 1, SCANN_HOST, s)) != SCANN_OK) break;
+    if ((st = h->blk_off.upload(blk_off.data(), K + 1, SCANN_HOST, s)) != SCANN_OK) break;
+    if ((st = d_blk_leaf.upload(blk_leaf.data(), nb, SCANN_HOST, s)) != SCANN_OK) break;
+    if ((st = d_packed.upload(packed, n * bpp, memspace, s)) != SCANN_OK) break;
+    size_t words = static_cast<size_t>(nb) * h->SG * 128;
+    if ((st = h->codes.alloc(words > 0 ? words : 4)) != SCANN_OK) break;
+    if (words > 0) {
+      repack_blocked_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, s>>>(
+          d_packed.p, d_blk_leaf.p, h->blk_off.p, h->pt_off.p, static_cast<int>(S), static_cast<int>(h->SG), words,
+          h->codes.p);
+    }
+    if (raw) {
+      if ((st = h->raw.upload(raw, num_raw * stride, memspace, s)) != SCANN_OK) break;
+    }
+    if ((st = h->stats.alloc(2)) != SCANN_OK) break;
+    cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s);
+    if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      st = cuda_fail(cudaGetLastError(), "treeah_create sync", __FILE__, __LINE__);
+      break;
+    }
+  } while (0);
+  if (st != SCANN_OK) {
+    scann_treeah_destroy(h);
+    return st;
+  }
+  *out = h;
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L, size_t R,
+                                 size_t k, uint32_t* ids, float* dists, uint32_t* counts, uint32_t* cand_ids,
+                                 float* cand_dists, uint32_t* cand_counts, int memspace, void* stream) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  if (nq == 0) return SCANN_OK;  // empty batch -> Ok(vec![])
+  SCANN_REQUIRE(queries && ids && dists && counts, SCANN_INVALID_ARGUMENT, "NULL buffer");
+  SCANN_REQUIRE(qdim == h->dim, SCANN_INVALID_ARGUMENT, "Query dimensionality mismatch");  // tree_x_hybrid/mod.rs:251-253
+  SCANN_REQUIRE(L >= 1 && L <= 1024, SCANN_INVALID_ARGUMENT, "partitions_to_search %zu outside 1..1024", L);
+  SCANN_REQUIRE(R <= 2048, SCANN_INVALID_ARGUMENT, "pre_reorder_k %zu > 2048 unsupported", R);
+  SCANN_REQUIRE(k >= 1, SCANN_INVALID_ARGUMENT, "k must be >= 1");
+  SCANN_REQUIRE((cand_ids == nullptr) == (cand_dists == nullptr), SCANN_INVALID_ARGUMENT,
+                "cand_ids and cand_dists go together");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(stream)
+                                             : (stream ? static_cast<cudaStream_t>(stream) : h->stream);
+  if (L > h->K) L = h->K;  // partition() returns min(L, K) tokens (tree_partitioner.rs:214)
+  const size_t Reff = R < 1 ? 1 : R;  // R == 0 (k*multiplier < 1) -> no candidates
+  // chunk the batch so that the candidate buffer stays <= 1 GiB and the centre-distance scratch <= 512 MiB
+  size_t chunk = nq;
+  chunk = std::min(chunk, std::max<size_t>(1, (size_t(1) << 30) / (L * Reff * 8)));
+  chunk = std::min(chunk, std::max<size_t>(1, (size_t(512) << 20) / (h->K * 4)));
+  const bool host = memspace == SCANN_HOST;
+  SCANN_TRY(h->ws.reserve(treeah_chunk_bytes(h, chunk, L, Reff, k, host)));
+  SCANN_CUDA(cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s));
+  for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+    size_t nqc = std::min(chunk, nq - q0);
+    h->ws.reset();
+    const float* dq = queries + q0 * h->dim;
+    uint32_t *d_ids = ids + q0 * k, *d_counts = counts + q0;
+    float* d_dists = dists + q0 * k;
+    uint32_t* d_cid = cand_ids ? cand_ids + q0 * R : nullptr;
+    float* d_cd = cand_dists ? cand_dists + q0 * R : nullptr;
+    uint32_t* d_cc = cand_counts ? cand_counts + q0 : nullptr;
+    if (host) {
+      float* t = h->ws.take<float>(nqc * h->dim);
+      SCANN_CUDA(cudaMemcpyAsync(t, dq, nqc * h->dim * 4, cudaMemcpyHostToDevice, s));
+      dq = t;
+      d_ids = h->ws.take<uint32_t>(nqc * k);
+      d_dists = h->ws.take<float>(nqc * k);
+      d_counts = h->ws.take<uint32_t>(nqc);
+      d_cid = h->ws.take<uint32_t>(nqc * Reff);
+      d_cd = h->ws.take<float>(nqc * Reff);
+      d_cc = h->ws.take<uint32_t>(nqc);
+    }
+    if (R == 0) {
+      // (k as f32 * multiplier) as usize == 0: FastTopNeighbors(0) keeps nothing -> empty results
+      SCANN_CUDA(cudaMemsetAsync(d_ids, 0xFF, nqc * k * 4, s));
+      SCANN_CUDA(cudaMemsetAsync(d_counts, 0, nqc * 4, s));
+      if (d_cc) SCANN_CUDA(cudaMemsetAsync(d_cc, 0, nqc * 4, s));
+    } else {
+      SCANN_TRY(treeah_search_chunk(h, dq, nqc, L, R, k, d_ids, d_dists, d_counts, d_cid, d_cd, d_cc, s));
+    }
+    if (host) {
+      SCANN_CUDA(cudaMemcpyAsync(ids + q0 * k, d_ids, nqc * k * 4, cudaMemcpyDeviceToHost, s));
+      SCANN_CUDA(cudaMemcpyAsync(dists + q0 * k, d_dists, nqc * k * 4, cudaMemcpyDeviceToHost, s));
+      SCANN_CUDA(cudaMemcpyAsync(counts + q0, d_counts, nqc * 4, cudaMemcpyDeviceToHost, s));
+      if (cand_ids && R > 0) {
+        SCANN_CUDA(cudaMemcpyAsync(cand_ids + q0 * R, d_cid, nqc * R * 4, cudaMemcpyDeviceToHost, s));
+        SCANN_CUDA(cudaMemcpyAsync(cand_dists + q0 * R, d_cd, nqc * R * 4, cudaMemcpyDeviceToHost, s));
+      }
+      if (cand_counts) SCANN_CUDA(cudaMemcpyAsync(cand_counts + q0, d_cc, nqc * 4, cudaMemcpyDeviceToHost, s));
+      SCANN_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint64_t* pairs) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  DeviceGuard g(h->device);
+  unsigned long long v[2] = {0, 0};
+  SCANN_CUDA(cudaDeviceSynchronize());
+  SCANN_CUDA(cudaMemcpy(v, h->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
+  if (bytes) *bytes = v[0];
+  if (pairs) *pairs = v[1];
+  return SCANN_OK;
+}
+
+void scann_treeah_destroy(scann_treeah* h) {
+  if (!h) return;
+  {
+    scann::DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    h->ws.release();
+    h->centers.free_();
+    h->centersT.free_();
+    h->codebook.free_();
+    h->raw.free_();
+    h->codes.free_();
+    h->ids.free_();
+    h->blk_off.free_();
+    h->pt_off.free_();
+    h->stats.free_();
+    if (h->stream) cudaStreamDestroy(h->stream);
+  }
+  delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,528 @@
+"""Host-side mirror of the reference crate's searcher API over the C ABI (include/scann_b200.h).
+
+Same names, argument meaning and error behaviour as the Rust types they mirror, so the parity tests read
+like the reference's own tests:
+
+  BruteForceSearcher                 src/brute_force/searcher.rs:34-208
+  ScalarQuantizedBruteForceSearcher  src/brute_force/scalar_quantized.rs:99-326
+  TreePartitioner (query side)       src/partitioning/tree_partitioner.rs:37-229
+  AsymmetricHasher (LUT16 path)      src/hashes/hasher.rs:97-238
+  TreeXHybridSearcher                src/tree_x_hybrid/mod.rs:114-294
+  Scann / ScannBuilder               src/scann.rs:60-137,175-303,364-432
+
+Inputs may be numpy arrays (host path: the library copies H2D/D2H and synchronises) or torch CUDA tensors
+(device path: pointers are passed through, work is enqueued on torch's current stream, results are torch
+tensors).  torch is only plumbing here (device memory + streams).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import IntEnum
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .capi import ScannError
+
+
+class DistanceMeasure(IntEnum):
+    """The measures the hot path dispatches to SIMD kernels (src/distance_measures/mod.rs:32-66)."""
+    SquaredL2 = capi.SQL2
+    L2 = capi.L2
+    DotProduct = capi.DOT
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _stream_ptr(device_index: int):
+    torch = _torch()
+    return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+class _Batch:
+    """Normalises a query batch to a contiguous f32 [nq, dim] buffer and remembers where it lives."""
+
+    def __init__(self, queries, device_index: int):
+        self.device = _is_torch(queries) and queries.is_cuda
+        if _is_torch(queries):
+            torch = _torch()
+            q = queries.to(torch.float32).contiguous()
+            if q.dim() == 1:
+                q = q[None, :]
+            self.arr = q
+            self.nq, self.dim = int(q.shape[0]), int(q.shape[1]) if q.dim() == 2 else 0
+            if self.device:
+                self.ptr = C.c_void_p(q.data_ptr())
+                self.memspace = capi.DEVICE
+                self.stream = _stream_ptr(q.device.index if q.device.index is not None else device_index)
+            else:
+                self.np = q.numpy()
+                self.ptr = capi.np_ptr(self.np)
+                self.memspace = capi.HOST
+                self.stream = None
+        else:
+            if isinstance(queries, (list, tuple)) and len(queries) > 0 and len({len(r) for r in queries}) > 1:
+                raise ScannError(capi.INVALID_ARGUMENT, "ragged query batch: dimensionalities differ")
+            q = capi.as_f32(queries)
+            if q.ndim == 1:
+                q = q[None, :] if q.size else q.reshape(0, 0)
+            self.arr = q
+            self.nq, self.dim = int(q.shape[0]), int(q.shape[1])
+            self.ptr = capi.np_ptr(q)
+            self.memspace = capi.HOST
+            self.stream = None
+
+    def outputs(self, k: int, extra_R: int = 0):
+        if self.device:
+            torch = _torch()
+            dev = self.arr.device
+            ids = torch.empty((self.nq, k), dtype=torch.int32, device=dev)
+            dists = torch.empty((self.nq, k), dtype=torch.float32, device=dev)
+            counts = torch.empty((self.nq,), dtype=torch.int32, device=dev)
+            return ids, dists, counts, C.c_void_p(ids.data_ptr()), C.c_void_p(dists.data_ptr()), \
+                C.c_void_p(counts.data_ptr())
+        ids = np.empty((self.nq, k), np.uint32)
+        dists = np.empty((self.nq, k), np.float32)
+        counts = np.zeros((self.nq,), np.uint32)
+        return ids, dists, counts, capi.np_ptr(ids), capi.np_ptr(dists), capi.np_ptr(counts)
+
+
+def _dataset_ptr(x, dtype):
+    """(pointer, memspace, keepalive, n, dim) of a 2-D dataset given as numpy or torch (CPU/CUDA)."""
+    if _is_torch(x):
+        torch = _torch()
+        tdt = {np.float32: torch.float32, np.int8: torch.int8, np.uint8: torch.uint8, np.uint32: torch.int32,
+               np.uint64: torch.int64}[dtype]
+        t = x.to(tdt).contiguous() if x.dtype != tdt else x.contiguous()
+        if t.is_cuda:
+            # the library reads index arrays on its own stream: whatever produced them must be done
+            torch.cuda.current_stream(t.device).synchronize()
+            return C.c_void_p(t.data_ptr()), capi.DEVICE, t
+        a = t.numpy()
+        return capi.np_ptr(a), capi.HOST, a
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return capi.np_ptr(a), capi.HOST, a
+
+
+def results_to_lists(ids, dists, counts):
+    """ids/dists/counts → Vec<Vec<(u32, f32)>> shape (the reference's NNResultsVector per query)."""
+    if _is_torch(ids):
+        ids, dists, counts = ids.cpu().numpy().view(np.uint32), dists.cpu().numpy(), counts.cpu().numpy()
+    return [[(int(ids[i, j]), float(dists[i, j])) for j in range(int(counts[i]))] for i in range(ids.shape[0])]
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self):
+        self._h = C.c_void_p(None)
+
+    def close(self):
+        if self._h and self._h.value:
+            getattr(capi.load(), self._destroy)(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BruteForceSearcher(_Handle):
+    """BruteForceSearcher<f32> (src/brute_force/searcher.rs:18-209)."""
+    _destroy = "scann_bf_destroy"
+
+    def __init__(self, dataset, distance_measure=DistanceMeasure.SquaredL2, device: int = 0, dim: Optional[int] = None):
+        super().__init__()
+        capi.require_gpu()
+        ptr, ms, self._keep = _dataset_ptr(dataset, np.float32)
+        shape = tuple(dataset.shape)
+        n = int(shape[0])
+        stride = int(shape[1]) if len(shape) > 1 else 0
+        self.dimensionality = int(dim) if dim is not None else stride
+        self.size = n
+        self.distance_measure = DistanceMeasure(distance_measure)
+        self.device = device
+        capi.check(capi.load().scann_bf_create(ptr, n, self.dimensionality, stride, int(self.distance_measure), device,
+                                               ms, C.byref(self._h)))
+        self._keep = None
+
+    def search_batched(self, queries, k: int):
+        """search_batched (searcher.rs:170-208): returns (ids [nq,k], dists [nq,k], counts [nq])."""
+        b = _Batch(queries, self.device)
+        ids, dists, counts, pi, pd, pc = b.outputs(k)
+        if b.nq == 0:
+            return ids, dists, counts
+        capi.check(capi.load().scann_bf_search(self._h, b.ptr, b.nq, b.dim, k, pi, pd, pc, b.memspace, b.stream))
+        return ids, dists, counts
+
+    def search(self, query, k: int):
+        """search (searcher.rs:77-93) → [(index, distance)] sorted by distance."""
+        ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
+        return results_to_lists(ids, dists, counts)[0]
+
+
+@dataclass
+class ScalarQuantizedConfig:
+    """ScalarQuantizedConfig (scalar_quantized.rs:25-76); only the distance measure reaches the GPU path."""
+    distance_measure: DistanceMeasure = DistanceMeasure.SquaredL2
+
+    @staticmethod
+    def squared_l2():
+        return ScalarQuantizedConfig(DistanceMeasure.SquaredL2)
+
+    @staticmethod
+    def dot_product():
+        return ScalarQuantizedConfig(DistanceMeasure.DotProduct)
+
+
+def scalar_quantize(dataset, device: int = 0):
+    """QuantizedDataset::from_dataset (src/quantization/scalar.rs:195-226) on the GPU.
+    Returns (codes i8 [n, dim], cal4 = [min, max, scale, inv_scale])."""
+    capi.require_gpu()
+    if _is_torch(dataset) and dataset.is_cuda:
+        torch = _torch()
+        x = dataset.to(torch.float32).contiguous()
+        n, dim = x.shape
+        if n == 0:
+            raise ScannError(capi.INVALID_ARGUMENT, "Cannot quantize empty dataset")
+        codes = torch.empty((n, dim), dtype=torch.int8, device=x.device)
+        cal = torch.empty(4, dtype=torch.float32, device=x.device)
+        capi.check(capi.load().scann_sq8_quantize(C.c_void_p(x.data_ptr()), n, dim, dim, C.c_void_p(codes.data_ptr()),
+                                                  C.c_void_p(cal.data_ptr()), device, capi.DEVICE))
+        return codes, cal.cpu().numpy()
+    x = capi.as_f32(dataset)
+    n, dim = x.shape if x.ndim == 2 else (0, 0)
+    if n == 0:
+        raise ScannError(capi.INVALID_ARGUMENT, "Cannot quantize empty dataset")
+    codes = np.empty((n, dim), np.int8)
+    cal = np.empty(4, np.float32)
+    capi.check(capi.load().scann_sq8_quantize(capi.np_ptr(x), n, dim, dim, capi.np_ptr(codes), capi.np_ptr(cal), device,
+                                              capi.HOST))
+    return codes, cal
+
+
+class ScalarQuantizedBruteForceSearcher(_Handle):
+    """ScalarQuantizedBruteForceSearcher (src/brute_force/scalar_quantized.rs:82-348)."""
+    _destroy = "scann_sq8_destroy"
+
+    def __init__(self, dataset, config: ScalarQuantizedConfig = ScalarQuantizedConfig(), device: int = 0):
+        """new(&dataset, config) (:99-113): quantises the float dataset, then builds the searcher."""
+        super().__init__()
+        codes, cal = scalar_quantize(dataset, device)
+        self._init_from(codes, float(cal[2]), config.distance_measure, device)
+        self.calibration = cal
+
+    @classmethod
+    def from_quantized(cls, codes, scale: float, distance_measure=DistanceMeasure.SquaredL2, device: int = 0):
+        """from_quantized (:116-129)."""
+        self = cls.__new__(cls)
+        _Handle.__init__(self)
+        capi.require_gpu()
+        self._init_from(codes, scale, distance_measure, device)
+        self.calibration = None
+        return self
+
+    def _init_from(self, codes, scale, distance_measure, device):
+        ptr, ms, keep = _dataset_ptr(codes, np.int8)
+        n, dim = int(codes.shape[0]), int(codes.shape[1]) if len(codes.shape) > 1 else 0
+        self.size, self.dimensionality, self.scale = n, dim, float(scale)
+        self.distance_measure = DistanceMeasure(distance_measure)
+        self.device = device
+        capi.check(capi.load().scann_sq8_create(ptr, n, dim, C.c_float(scale), int(self.distance_measure), device, ms,
+                                                C.byref(self._h)))
+
+    def search_batched(self, queries, k: int):
+        b = _Batch(queries, self.device)
+        ids, dists, counts, pi, pd, pc = b.outputs(k)
+        if b.nq == 0:
+            return ids, dists, counts
+        capi.check(capi.load().scann_sq8_search(self._h, b.ptr, b.nq, b.dim, k, pi, pd, pc, b.memspace, b.stream))
+        return ids, dists, counts
+
+    def search(self, query, k: int):
+        ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
+        return results_to_lists(ids, dists, counts)[0]
+
+
+class TreePartitioner(_Handle):
+    """Query side of TreePartitioner (src/partitioning/tree_partitioner.rs:148-229) over given centres."""
+    _destroy = "scann_part_destroy"
+
+    def __init__(self, centers=None, device: int = 0):
+        super().__init__()
+        self.device = device
+        self.num_partitions = 0
+        if centers is not None:
+            self.build_from_centers(centers)
+
+    def build_from_centers(self, centers):
+        capi.require_gpu()
+        ptr, ms, keep = _dataset_ptr(centers, np.float32)
+        K, dim = int(centers.shape[0]), int(centers.shape[1])
+        capi.check(capi.load().scann_part_create(ptr, K, dim, self.device, ms, C.byref(self._h)))
+        self.num_partitions, self.dimensionality = K, dim
+
+    def partition(self, queries, num_partitions: int):
+        """Partitioner::partition (:196-229) for a batch → (tokens [nq, L], distances [nq, L])."""
+        if not (self._h and self._h.value):
+            raise ScannError(capi.FAILED_PRECONDITION, "Partitioner not built")
+        b = _Batch(queries, self.device)
+        L = int(num_partitions)
+        if b.device:
+            torch = _torch()
+            tokens = torch.empty((b.nq, L), dtype=torch.int32, device=b.arr.device)
+            dists = torch.empty((b.nq, L), dtype=torch.float32, device=b.arr.device)
+            pt, pd = C.c_void_p(tokens.data_ptr()), C.c_void_p(dists.data_ptr())
+        else:
+            tokens = np.empty((b.nq, L), np.uint32)
+            dists = np.empty((b.nq, L), np.float32)
+            pt, pd = capi.np_ptr(tokens), capi.np_ptr(dists)
+        if b.nq and L:
+            capi.check(capi.load().scann_part_select(self._h, b.ptr, b.nq, b.dim, L, pt, pd, b.memspace, b.stream))
+        return tokens, dists
+
+
+@dataclass
+class AsymmetricHasherConfig:
+    """AsymmetricHasherConfig (src/hashes/hasher.rs:19-69); the GPU path is the 16-code LUT16 variant."""
+    num_codes: int = 16
+    num_subspaces: int = 8
+    seed: Optional[int] = None
+
+
+@dataclass
+class TreeXHybridConfig:
+    """TreeXHybridConfig (src/tree_x_hybrid/mod.rs:23-78).  `distance_measure` is the reorder measure —
+    the reference hard-wires SquaredL2 (:124); SURVEY §5 adds the setter config C3 needs."""
+    num_partitions: int = 100
+    partitions_to_search: int = 10
+    hash_config: AsymmetricHasherConfig = field(default_factory=AsymmetricHasherConfig)
+    use_residuals: bool = True
+    pre_reorder_multiplier: float = 3.0
+    distance_measure: DistanceMeasure = DistanceMeasure.SquaredL2
+
+    def pre_reorder_k(self, k: int) -> int:
+        # (k as f32 * self.config.pre_reorder_multiplier) as usize  (tree_x_hybrid/mod.rs:263)
+        v = np.float32(k) * np.float32(self.pre_reorder_multiplier)
+        return max(int(v), 0)
+
+
+class TreeXHybridSearcher(_Handle):
+    """TreeXHybridSearcher (src/tree_x_hybrid/mod.rs:93-380) with the LUT16 scan.
+
+    ``build_from_index`` takes the arrays ``build`` (:131-209) leaves behind: centres, the residual codebook
+    [S,16,ds], PackedCodes4Bit rows grouped by partition, their datapoint ids, partition offsets and the
+    raw dataset.  (Index training is an index-build concern — see ``indexing.py``.)"""
+    _destroy = "scann_treeah_destroy"
+
+    def __init__(self, config: TreeXHybridConfig = TreeXHybridConfig(), device: int = 0):
+        super().__init__()
+        self.config = config
+        self.device = device
+        self.num_datapoints = 0
+        self.dimensionality = 0
+
+    def build_from_index(self, centers, codebook, packed, ids, part_offsets, raw=None):
+        capi.require_gpu()
+        if packed.shape[0] == 0:
+            raise ScannError(capi.INVALID_ARGUMENT, "Cannot build from empty dataset")
+        K, dim = int(centers.shape[0]), int(centers.shape[1])
+        S = int(codebook.shape[0])
+        if int(codebook.shape[1]) != 16:
+            raise ScannError(capi.UNIMPLEMENTED, "the GPU AH path is LUT16: num_codes must be 16")
+        if dim % S != 0:
+            raise ScannError(capi.INVALID_ARGUMENT,
+                             f"Dimensionality {dim} must be divisible by num_subspaces {S}")
+        n = int(packed.shape[0])
+        p_c, ms_c, k1 = _dataset_ptr(centers, np.float32)
+        p_cb, ms_cb, k2 = _dataset_ptr(codebook, np.float32)
+        p_pk, ms_pk, k3 = _dataset_ptr(packed, np.uint8)
+        p_id, ms_id, k4 = _dataset_ptr(ids, np.uint32)
+        p_off, ms_off, k5 = _dataset_ptr(part_offsets, np.uint64)
+        spaces = {ms_c, ms_cb, ms_pk, ms_id, ms_off}
+        p_raw, num_raw, stride = None, 0, 0
+        if raw is not None:
+            p_raw, ms_raw, k6 = _dataset_ptr(raw, np.float32)
+            num_raw, stride = int(raw.shape[0]), int(raw.shape[1])
+            spaces.add(ms_raw)
+        if len(spaces) != 1:
+            raise ScannError(capi.INVALID_ARGUMENT, "index arrays must all be host or all be device resident")
+        self.close()
+        capi.check(capi.load().scann_treeah_create(p_c, K, dim, p_cb, S, p_pk, p_id, p_off, n, p_raw, num_raw, stride,
+                                                   int(self.config.use_residuals), int(self.config.distance_measure),
+                                                   self.device, spaces.pop(), C.byref(self._h)))
+        self.num_datapoints, self.dimensionality, self.num_partitions, self.num_subspaces = n, dim, K, S
+        return self
+
+    def search_batched(self, queries, k: int, partitions_to_search: Optional[int] = None,
+                       pre_reorder_k: Optional[int] = None, want_candidates: bool = False):
+        if not (self._h and self._h.value):
+            raise ScannError(capi.FAILED_PRECONDITION, "searcher not built")
+        b = _Batch(queries, self.device)
+        L = int(partitions_to_search if partitions_to_search is not None else self.config.partitions_to_search)
+        R = int(pre_reorder_k if pre_reorder_k is not None else self.config.pre_reorder_k(k))
+        ids, dists, counts, pi, pd, pc = b.outputs(k)
+        cand = None
+        pci = pcd = pcc = None
+        if want_candidates:
+            if b.device:
+                torch = _torch()
+                ci = torch.empty((b.nq, max(R, 1)), dtype=torch.int32, device=b.arr.device)
+                cd = torch.empty((b.nq, max(R, 1)), dtype=torch.float32, device=b.arr.device)
+                cc = torch.zeros((b.nq,), dtype=torch.int32, device=b.arr.device)
+                pci, pcd, pcc = C.c_void_p(ci.data_ptr()), C.c_void_p(cd.data_ptr()), C.c_void_p(cc.data_ptr())
+            else:
+                ci = np.full((b.nq, max(R, 1)), 0xFFFFFFFF, np.uint32)
+                cd = np.full((b.nq, max(R, 1)), np.inf, np.float32)
+                cc = np.zeros((b.nq,), np.uint32)
+                pci, pcd, pcc = capi.np_ptr(ci), capi.np_ptr(cd), capi.np_ptr(cc)
+            cand = (ci, cd, cc)
+        if b.nq:
+            capi.check(capi.load().scann_treeah_search(self._h, b.ptr, b.nq, b.dim, L, R, k, pi, pd, pc, pci, pcd, pcc,
+                                                       b.memspace, b.stream))
+        if want_candidates:
+            return ids, dists, counts, cand
+        return ids, dists, counts
+
+    def search(self, query, k: int):
+        """search (:240-242) → [(index, distance)]"""
+        ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
+        return results_to_lists(ids, dists, counts)[0]
+
+    def last_scan_bytes(self):
+        by, pr = C.c_uint64(0), C.c_uint64(0)
+        capi.check(capi.load().scann_treeah_last_scan_bytes(self._h, C.byref(by), C.byref(pr)))
+        return int(by.value), int(pr.value)
+
+
+class AsymmetricHasher(TreeXHybridSearcher):
+    """Flat AsymmetricHasher (src/hashes/hasher.rs:75-259) on the LUT16 path: one partition holding every
+    point, no residuals.  search = approximate LUT16 distances; search_with_reordering re-ranks
+    `pre_reorder_k` candidates by exact SquaredL2 (hard-coded in the reference, hasher.rs:208)."""
+
+    def __init__(self, config: AsymmetricHasherConfig = AsymmetricHasherConfig(num_codes=16), device: int = 0):
+        super().__init__(TreeXHybridConfig(num_partitions=1, partitions_to_search=1, hash_config=config,
+                                           use_residuals=False, distance_measure=DistanceMeasure.SquaredL2), device)
+        self._with_raw = None
+
+    def build_from_index(self, codebook, packed, raw=None):
+        n = int(packed.shape[0])
+        dim = int(codebook.shape[0]) * int(codebook.shape[2])
+        centers = np.zeros((1, dim), np.float32)
+        ids = np.arange(n, dtype=np.uint32)
+        off = np.array([0, n], np.uint64)
+        self._raw = raw
+        self._args = (centers, codebook, packed, ids, off)
+        self._have = None
+        return self
+
+    def _ensure(self, with_raw: bool):
+        if self._have is not with_raw:
+            centers, cb, packed, ids, off = self._args
+            if with_raw and self._raw is None:
+                raise ScannError(capi.FAILED_PRECONDITION, "Dataset not stored")
+            TreeXHybridSearcher.build_from_index(self, centers, cb, packed, ids, off, self._raw if with_raw else None)
+            self._have = with_raw
+
+    def search_batched(self, queries, k: int):
+        self._ensure(False)
+        return TreeXHybridSearcher.search_batched(self, queries, k, 1, k)
+
+    def search_with_reordering(self, queries, k: int, pre_reorder_k: int):
+        self._ensure(True)
+        return TreeXHybridSearcher.search_batched(self, queries, k, 1, pre_reorder_k)
+
+
+def merge_topk(ids_parts, dists_parts, device: int = 0):
+    """k-way merge of per-shard results [parts, nq, k] by (distance, id)."""
+    capi.require_gpu()
+    if _is_torch(ids_parts) and ids_parts.is_cuda:
+        torch = _torch()
+        parts, nq, k = ids_parts.shape
+        ii = ids_parts.contiguous()
+        dd = dists_parts.to(torch.float32).contiguous()
+        oi = torch.empty((nq, k), dtype=torch.int32, device=ii.device)
+        od = torch.empty((nq, k), dtype=torch.float32, device=ii.device)
+        oc = torch.empty((nq,), dtype=torch.int32, device=ii.device)
+        capi.check(capi.load().scann_merge_topk(C.c_void_p(ii.data_ptr()), C.c_void_p(dd.data_ptr()), parts, nq, k,
+                                                C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()),
+                                                C.c_void_p(oc.data_ptr()), ii.device.index or 0, capi.DEVICE,
+                                                _stream_ptr(ii.device.index or 0)))
+        return oi, od, oc
+    ii = np.ascontiguousarray(ids_parts, np.uint32)
+    dd = capi.as_f32(dists_parts)
+    parts, nq, k = ii.shape
+    oi, od, oc = np.empty((nq, k), np.uint32), np.empty((nq, k), np.float32), np.zeros(nq, np.uint32)
+    capi.check(capi.load().scann_merge_topk(capi.np_ptr(ii), capi.np_ptr(dd), parts, nq, k, capi.np_ptr(oi),
+                                            capi.np_ptr(od), capi.np_ptr(oc), device, capi.HOST, None))
+    return oi, od, oc
+
+
+# ----------------------------------------------------------------------------------------- taps
+def lut16_build(codebook, queries, centroids=None, device: int = 0):
+    """Parity tap → (lut8 [nq, S, 16] u8, bias [nq], mult [nq])."""
+    capi.require_gpu()
+    cb, q = capi.as_f32(codebook), capi.as_f32(queries)
+    S, ncodes, ds = cb.shape
+    assert ncodes == 16
+    nq = q.shape[0]
+    cen = capi.as_f32(centroids) if centroids is not None else None
+    lut8 = np.empty((nq, S, 16), np.uint8)
+    bias, mult = np.empty(nq, np.float32), np.empty(nq, np.float32)
+    capi.check(capi.load().scann_lut16_build(capi.np_ptr(cb), S, ds, capi.np_ptr(q), nq, capi.np_ptr(cen),
+                                             capi.np_ptr(lut8), capi.np_ptr(bias), capi.np_ptr(mult), device, capi.HOST))
+    return lut8, bias, mult
+
+
+def lut16_scan(packed, S: int, lut8, device: int = 0):
+    """Parity tap → u32 sums [n] of one u8 table over PackedCodes4Bit rows."""
+    capi.require_gpu()
+    pk = np.ascontiguousarray(packed, np.uint8)
+    l8 = np.ascontiguousarray(lut8, np.uint8)
+    n = pk.shape[0]
+    sums = np.empty(n, np.uint32)
+    capi.check(capi.load().scann_lut16_scan(capi.np_ptr(pk), n, S, capi.np_ptr(l8), capi.np_ptr(sums), device, capi.HOST))
+    return sums
+
+
+def pq_encode(codebook, x, centers=None, assign=None, device: int = 0):
+    """Codebook::encode (+ residual) + PackedCodes4Bit::from_codes → packed [n, ceil(S/2)] u8.
+    numpy inputs (no residual) or torch CUDA tensors (residual allowed)."""
+    capi.require_gpu()
+    S, ncodes, ds = (int(v) for v in codebook.shape)
+    assert ncodes == 16
+    bpp = (S + 1) // 2
+    if _is_torch(x) and x.is_cuda:
+        torch = _torch()
+        xx = x.to(torch.float32).contiguous()
+        cb = codebook.to(torch.float32).contiguous()
+        n, stride = xx.shape
+        out = torch.empty((n, bpp), dtype=torch.uint8, device=xx.device)
+        pc = pa = None
+        if centers is not None:
+            cc = centers.to(torch.float32).contiguous()
+            aa = assign.to(torch.int32).contiguous()
+            pc, pa = C.c_void_p(cc.data_ptr()), C.c_void_p(aa.data_ptr())
+        capi.check(capi.load().scann_pq_encode(C.c_void_p(cb.data_ptr()), S, ds, C.c_void_p(xx.data_ptr()), n, stride,
+                                               pc, pa, C.c_void_p(out.data_ptr()), xx.device.index or 0, capi.DEVICE))
+        return out
+    cb, xx = capi.as_f32(codebook), capi.as_f32(x)
+    n, stride = xx.shape
+    if centers is not None:
+        # residual on the host side of the boundary is plain f32 subtraction (tree_x_hybrid/mod.rs:181-185)
+        xx = (xx - capi.as_f32(centers)[np.asarray(assign, np.int64)]).astype(np.float32)
+    out = np.empty((n, bpp), np.uint8)
+    capi.check(capi.load().scann_pq_encode(capi.np_ptr(cb), S, ds, capi.np_ptr(xx), n, stride, None, None,
+                                           capi.np_ptr(out), device, capi.HOST))
+    return out
