@@ -142,6 +142,12 @@ void scann_treeah_destroy(scann_treeah* h);
 /* introspection used by bench.py for the roofline arithmetic: algorithmic code bytes scanned by the
  * last scann_treeah_search call (Σ over (query, leaf) pairs of leaf_size * ceil(S/2)); host sync. */
 scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint64_t* pairs);
+/* live per-stage device timing for the roofline (CUDA events recorded on the search stream around each
+ * stage; no host synchronisation while enabled).  get_profile synchronises, returns the milliseconds
+ * accumulated since set_profiling(h, 1) / the previous get_profile as ms4 = {partition, worklist,
+ * lut16 scan, merge+reorder} and the number of kernel launches, and resets the accumulators. */
+scann_status scann_treeah_set_profiling(scann_treeah* h, int enable);
+scann_status scann_treeah_get_profile(scann_treeah* h, double* ms4, uint64_t* kernel_launches);
 
 /* ---------------------------------------------------------------------------------------------
  * Parity taps for the LUT16 pieces (bit-exact targets of BASELINE.json)

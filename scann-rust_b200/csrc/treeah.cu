@@ -439,6 +439,18 @@ struct scann_treeah {
   std::mutex mu;
   cudaStream_t stream = nullptr;
   int sms = 148;
+  // optional live profiling: 5 events per chunk bracket the 4 stages
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  uint64_t prof_launches = 0;
+  void mark(cudaStream_t s) {
+    if (!profiling) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, s);
+      prof_events.push_back(e);
+    }
+  }
 };
 
 namespace scann {
@@ -480,7 +492,9 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   uint32_t* cand_cnt = h->ws.take<uint32_t>(P);
 
   // 1. partition (K == 1 still goes through it: one centre, token 0)
+  h->mark(s);
   SCANN_TRY(launch_partition(h->centersT.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, s));
+  h->mark(s);
   // 2. worklist
   SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 2 * K * sizeof(uint32_t), s));
   SCANN_CUDA(cudaMemsetAsync(cand_cnt, 0, P * sizeof(uint32_t), s));
@@ -493,6 +507,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   wl_items_kernel<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
                                                                         pair_start, item_start, items);
   SCANN_CUDA(cudaGetLastError());
+  h->mark(s);
   // 3. scan
   ScanArgs a;
   a.codes = reinterpret_cast<const uint4*>(h->codes.p);
@@ -521,6 +536,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
     case 2: SCANN_TRY(launch_scan<2>(a, h->sms, s)); break;
     default: SCANN_TRY(launch_scan<1>(a, h->sms, s)); break;
   }
+  h->mark(s);
   // 4. merge + reorder
   MergeArgs m;
   m.cand = cand;
@@ -548,6 +564,8 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
                                   static_cast<int>(msm)));
   merge_reorder_kernel<<<static_cast<unsigned>(nq), 256, msm, s>>>(m);
   SCANN_CUDA(cudaGetLastError());
+  h->mark(s);
+  h->prof_launches += 8;  // center_dist, part_select, wl_count, wl_scan, wl_scatter, wl_items, lut16_scan, merge_reorder
   return SCANN_OK;
 }
 
@@ -774,6 +792,38 @@ scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint
   SCANN_CUDA(cudaMemcpy(v, h->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
   if (bytes) *bytes = v[0];
   if (pairs) *pairs = v[1];
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_set_profiling(scann_treeah* h, int enable) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear();
+  h->prof_launches = 0;
+  h->profiling = enable != 0;
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_get_profile(scann_treeah* h, double* ms4, uint64_t* kernel_launches) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr && ms4 != nullptr, SCANN_INVALID_ARGUMENT, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard g(h->device);
+  SCANN_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < 4; ++i) ms4[i] = 0.0;
+  for (size_t c = 0; c + 5 <= h->prof_events.size(); c += 5)
+    for (int i = 0; i < 4; ++i) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, h->prof_events[c + i], h->prof_events[c + i + 1]) == cudaSuccess) ms4[i] += ms;
+    }
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+  h->prof_events.clear();
+  if (kernel_launches) *kernel_launches = h->prof_launches;
+  h->prof_launches = 0;
   return SCANN_OK;
 }
 

@@ -400,6 +400,16 @@ class TreeXHybridSearcher(_Handle):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
 
+    def set_profiling(self, enable: bool):
+        capi.check(capi.load().scann_treeah_set_profiling(self._h, int(enable)))
+
+    def get_profile(self):
+        """→ ({'partition','worklist','scan','merge'} device milliseconds since the last call, kernel launches)"""
+        ms = (C.c_double * 4)()
+        n = C.c_uint64(0)
+        capi.check(capi.load().scann_treeah_get_profile(self._h, ms, C.byref(n)))
+        return dict(zip(("partition", "worklist", "scan", "merge"), [float(v) for v in ms])), int(n.value)
+
     def last_scan_bytes(self):
         by, pr = C.c_uint64(0), C.c_uint64(0)
         capi.check(capi.load().scann_treeah_last_scan_bytes(self._h, C.byref(by), C.byref(pr)))

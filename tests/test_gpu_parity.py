@@ -135,7 +135,42 @@ def test_partition_errors(gpu_lib):
 
 
 # ----------------------------------------------------------------------------- Tree-AH end to end
-def _treeah_case(gpu_lib, oracle, n, dim, K, S, nq, L, R, k, measure, seed, device_path=False, use_residuals=True):
+def _check_stages(oracle, x, om, qs, k, gpu, ora):
+    """Stage-wise parity of one Tree-AH batch.  Exact ties of the integer LUT16 score are the only licence
+    to differ (BASELINE.json: 'away from exact ties'), so the comparison is made tie-proof:
+      (1) the sorted approximate candidate distances are tie-independent -> bit-identical;
+      (2) candidate ids strictly below the cut-off value are the same set;
+      (3) the oracle's reorder (tree_x_hybrid/mod.rs:342-364) applied to the GPU's own candidate list must
+          reproduce the GPU's final ids and bit-identical exact distances.
+    Returns the end-to-end recall vs the oracle over the valid results (informational + bounded by callers)."""
+    ids, dists, counts, ci, cd, cc = gpu
+    oids, odists, ocounts, ocand, ocand_d, ocand_n = ora
+    nq = len(qs)
+    assert (cc == ocand_n).all()
+    assert (cd.view(np.uint32) == ocand_d.view(np.uint32)).all(), "approximate (LUT16) candidate distances differ"
+    hit = tot = 0
+    for qi in range(nq):
+        c = int(cc[qi])
+        if c:
+            cut = cd[qi, c - 1]
+            a = set(ci[qi, :c][cd[qi, :c] < cut].tolist())
+            b = set(ocand[qi, :c][ocand_d[qi, :c] < cut].tolist())
+            assert a == b, f"query {qi}: candidate sets differ away from the cut-off tie"
+        eids, ed = oracle.reorder(x, om, qs[qi], ci[qi, :c], k)
+        m = len(eids)
+        assert m == counts[qi] == ocounts[qi]
+        assert (dists[qi, :m].view(np.uint32) == ed.view(np.uint32)).all(), "exact reorder distances differ"
+        assert (ids[qi, :m] == eids).all() or len(set(ed.tolist())) < m, "reorder order differs without a tie"
+        assert (ids[qi, m:] == 0xFFFFFFFF).all() and np.isinf(dists[qi, m:]).all()
+        hit += len(set(ids[qi, :m].tolist()) & set(oids[qi, :m].tolist()))
+        tot += m
+        same = ids[qi, :m] == oids[qi, :m]
+        assert (dists[qi, :m][same].view(np.uint32) == odists[qi, :m][same].view(np.uint32)).all()
+    return hit / max(tot, 1)
+
+
+def _treeah_case(gpu_lib, oracle, n, dim, K, S, nq, L, R, k, measure, seed, device_path=False, use_residuals=True,
+                 min_recall=0.999):
     x, _ = helpers.clustered(n, dim, max(8, K), 0.35, seed)
     qs, _ = helpers.clustered(nq, dim, max(8, K), 0.35, seed)  # same latent centres (same seed → same lat)
     qs = (qs + 0.05 * helpers.gaussian(nq, dim, seed + 1)).astype(np.float32)
@@ -160,26 +195,9 @@ def _treeah_case(gpu_lib, oracle, n, dim, K, S, nq, L, R, k, measure, seed, devi
     else:
         s.build_from_index(idx["centers"], idx["codebook"], idx["packed"], idx["ids"], idx["part_offsets"], x)
         ids, dists, counts, (ci, cd, cc) = s.search_batched(qs, k, pre_reorder_k=R, want_candidates=True)
-    # (1) the R approximate distances are tie-independent: bit-identical sorted lists
-    assert (cc == ocand_n).all()
-    assert (cd.view(np.uint32) == ocand_d.view(np.uint32)).all(), "approximate (LUT16) candidate distances differ"
-    # (2) candidate ids strictly below the cut-off distance are the same set
-    for qi in range(nq):
-        c = int(cc[qi])
-        if c == 0:
-            continue
-        cut = cd[qi, c - 1]
-        a = set(ci[qi, :c][cd[qi, :c] < cut].tolist())
-        b = set(ocand[qi, :c][ocand_d[qi, :c] < cut].tolist())
-        assert a == b, f"query {qi}: candidate sets differ away from the cut-off tie"
-    # (3) final results: exact distances are the reference's floats; ids equal away from ties
-    assert (counts == ocounts).all()
-    compared, mism = helpers.ids_equal_away_from_ties(ids, dists, oids, odists, counts)
-    assert mism <= max(1, compared // 1000), f"{mism}/{compared} neighbour ids differ away from ties"
-    rec = helpers.recall(ids, oids, k)
-    assert rec >= 0.999, f"recall vs oracle {rec}"
-    same = ids == oids
-    assert (dists[same].view(np.uint32) == odists[same].view(np.uint32)).all(), "exact reorder distances differ"
+    rec = _check_stages(oracle, x, om, qs, k, (ids, dists, counts, ci, cd, cc),
+                        (oids, odists, ocounts, ocand, ocand_d, ocand_n))
+    assert rec >= min_recall, f"recall vs oracle {rec}"
     by, pairs = s.last_scan_bytes()
     sizes = np.diff(idx["part_offsets"].astype(np.int64))
     otok, _ = oracle.partition(idx["centers"], qs, min(L, K))
@@ -188,21 +206,25 @@ def _treeah_case(gpu_lib, oracle, n, dim, K, S, nq, L, R, k, measure, seed, devi
 
 
 def test_treeah_small_sql2(gpu_lib, oracle):
+    # coarse PQ (S=8) + small R: the approximate cut-off tie is large, so end-to-end recall vs the oracle is
+    # only loosely bounded here; the stage-wise checks inside _treeah_case are exact
     _treeah_case(gpu_lib, oracle, n=20_000, dim=32, K=32, S=8, nq=40, L=6, R=30, k=10,
-                 measure=gpu_lib.DistanceMeasure.SquaredL2, seed=1)
+                 measure=gpu_lib.DistanceMeasure.SquaredL2, seed=1, min_recall=0.9)
 
 
 @pytest.mark.parametrize("nq", [1, 7, 64, 700])
 def test_treeah_c3_shape_dot(gpu_lib, oracle, nq):
     # C3 geometry scaled down: D=96, S=48 (ds=2), 16 codes, Dot reorder, R=100, k=10.  nq sweeps the
     # queries-per-leaf group size G (1, 2, 4, 8 variants of the scan kernel).
+    # End-to-end recall vs the oracle is bounded by the cut-off tie only (FastTopNeighbors keeps a
+    # history-dependent subset of the tied points, top_k.rs:341-353): >= 0.998 here, stage checks exact.
     _treeah_case(gpu_lib, oracle, n=120_000, dim=96, K=60, S=48, nq=nq, L=16, R=100, k=10,
-                 measure=gpu_lib.DistanceMeasure.DotProduct, seed=3)
+                 measure=gpu_lib.DistanceMeasure.DotProduct, seed=3, min_recall=0.998)
 
 
 def test_treeah_device_pointers(gpu_lib, oracle):
     _treeah_case(gpu_lib, oracle, n=30_000, dim=64, K=20, S=16, nq=128, L=5, R=50, k=10,
-                 measure=gpu_lib.DistanceMeasure.SquaredL2, seed=4, device_path=True)
+                 measure=gpu_lib.DistanceMeasure.SquaredL2, seed=4, device_path=True, min_recall=0.97)
 
 
 def test_treeah_ragged_partitions_and_large_R(gpu_lib, oracle):
@@ -227,9 +249,9 @@ def test_treeah_ragged_partitions_and_large_R(gpu_lib, oracle):
         s = gpu_lib.TreeXHybridSearcher(gpu_lib.TreeXHybridConfig(num_partitions=K, partitions_to_search=L))
         s.build_from_index(idx["centers"], idx["codebook"], idx["packed"], idx["ids"], idx["part_offsets"], x)
         ids, dists, counts, (ci, cd, cc) = s.search_batched(q, k, pre_reorder_k=R, want_candidates=True)
-        assert (cc == ocn).all() and (counts == ocounts).all()
-        assert (cd.view(np.uint32) == ocd.view(np.uint32)).all()
-        assert helpers.recall(ids, oids, k) >= 0.99
+        rec = _check_stages(oracle, x, oracle.SQL2, q, k, (ids, dists, counts, ci, cd, cc),
+                            (oids, odists, ocounts, ocand, ocd, ocn))
+        assert rec >= 0.95, (L, R, k, rec)
 
 
 def test_treeah_no_raw_returns_approximate(gpu_lib, oracle):
