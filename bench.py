@@ -47,7 +47,7 @@ def parse():
     p.add_argument("--k", type=int, default=10)
     p.add_argument("--nq", type=int, default=10_000)
     p.add_argument("--latent", type=int, default=8192)
-    p.add_argument("--spread", type=float, default=0.35)
+    p.add_argument("--spread", type=float, default=0.5)
     p.add_argument("--decay", type=float, default=1.0)
     p.add_argument("--gt-queries", type=int, default=1000)
     p.add_argument("--cpu-queries", type=int, default=128)

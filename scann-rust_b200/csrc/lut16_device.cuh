@@ -26,6 +26,7 @@ namespace scann {
 constexpr int kBlockPts = 256;   // points per code block (32 lanes x 8 nibbles)
 constexpr int kScanWarps = 8;    // warps per CTA of the scan kernel
 constexpr int kTilePts = kBlockPts * kScanWarps;
+constexpr int kAccMode = 2;      // default accumulation pipe mode, see acc_add() (measured best on B200)
 
 #ifdef __CUDACC__
 
@@ -48,15 +49,40 @@ __device__ __forceinline__ float lut_entry(const float* __restrict__ qres, const
 //   global min/max over all S*16 entries; range < 1e-10 -> scale 1 (multiplier 1);
 //   else scale = 255/range, multiplier = 1/scale; q = round_half_away((v-min)*scale) saturated to u8.
 // lut8 receives S4*16 bytes ([s][16], rows S..S4-1 zeroed).  Lane 0 returns multiplier/bias.
+// The f32 entries are computed once and kept in registers between the min/max pass and the quantise
+// pass when the table is small enough (S <= 64, 32 entries per lane); larger tables recompute.
+__device__ __forceinline__ uint8_t lut16_quantize_entry(float v, float mn, float scale) {
+  float r = roundf(__fmul_rn(__fsub_rn(v, mn), scale));
+  if (!(r == r)) return 0;  // Rust `as u8`: NaN -> 0, saturating
+  if (r <= 0.0f) return 0;
+  if (r >= 255.0f) return 255;
+  return static_cast<uint8_t>(r);
+}
+
 __device__ __forceinline__ void warp_build_lut16(const float* __restrict__ qres, const float* __restrict__ cb,
                                                  int S, int S4, int ds, uint8_t* lut8, float* mult_out,
                                                  float* bias_out, int lane) {
   const int nent = S * 16;
+  const bool cached = nent <= 32 * 32;
+  float vals[32];
   float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
-  for (int e = lane; e < nent; e += 32) {
-    float v = lut_entry(qres, cb, e, ds);
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
+  if (cached) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int e = lane + 32 * t;
+      vals[t] = 0.0f;
+      if (e < nent) {
+        vals[t] = lut_entry(qres, cb, e, ds);
+        mn = fminf(mn, vals[t]);
+        mx = fmaxf(mx, vals[t]);
+      }
+    }
+  } else {
+    for (int e = lane; e < nent; e += 32) {
+      float v = lut_entry(qres, cb, e, ds);
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -69,16 +95,15 @@ __device__ __forceinline__ void warp_build_lut16(const float* __restrict__ qres,
     scale = __fdiv_rn(255.0f, range);
     mult = __fdiv_rn(1.0f, scale);
   }
-  for (int e = lane; e < S4 * 16; e += 32) {
-    uint8_t qv = 0;
-    if (e < nent) {
-      float v = roundf(__fmul_rn(__fsub_rn(lut_entry(qres, cb, e, ds), mn), scale));
-      if (!(v == v)) qv = 0;          // Rust `as u8`: NaN -> 0, saturating
-      else if (v <= 0.0f) qv = 0;
-      else if (v >= 255.0f) qv = 255;
-      else qv = static_cast<uint8_t>(v);
+  if (cached) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int e = lane + 32 * t;
+      if (e < S4 * 16) lut8[e] = e < nent ? lut16_quantize_entry(vals[t], mn, scale) : 0;
     }
-    lut8[e] = qv;
+  } else {
+    for (int e = lane; e < S4 * 16; e += 32)
+      lut8[e] = e < nent ? lut16_quantize_entry(lut_entry(qres, cb, e, ds), mn, scale) : 0;
   }
   if (lane == 0) {
     *mult_out = mult;
@@ -92,12 +117,56 @@ __device__ __forceinline__ float lut16_dequant(uint32_t sum, float mult, float b
   return __fadd_rn(__fmul_rn(static_cast<float>(sum), mult), bias_total);
 }
 
+// Packed per-lane accumulators of one (query, block): u16 halves hold the sums of points
+//   ea = (p0 | p2 << 16), xa = (p1 | p3 << 16), eb = (p4 | p6 << 16), xb = (p5 | p7 << 16)   (p_i = point lane*8+i)
+struct PackedSums {
+  uint32_t ea, xa, eb, xb;
+};
+__device__ __forceinline__ void unpack_sums(const PackedSums& p, uint32_t (&s)[8]) {
+  s[0] = p.ea & 0xFFFFu;
+  s[2] = p.ea >> 16;
+  s[1] = p.xa & 0xFFFFu;
+  s[3] = p.xa >> 16;
+  s[4] = p.eb & 0xFFFFu;
+  s[6] = p.eb >> 16;
+  s[5] = p.xb & 0xFFFFu;
+  s[7] = p.xb >> 16;
+}
+// smallest of the eight sums (two packed u16 minima, then the halves)
+__device__ __forceinline__ uint32_t min_sum(const PackedSums& p) {
+  uint32_t m = __vminu2(__vminu2(p.ea, p.xa), __vminu2(p.eb, p.xb));
+  return min(m & 0xFFFFu, m >> 16);
+}
+
+// Pipe balancing: the PRMT/LOP3 lookups saturate the ALU pipe, so the accumulation is issued on the
+// FMA pipe as integer multiply-adds.  `one` (== 1) and `sh24` (== 1 << 24) are kernel parameters so the
+// compiler cannot strength-reduce them back into ALU-pipe adds/shifts:
+//   acc_e = (r & 0x00FF00FF) * one + acc_e            IMAD
+//   acc_x = hi32(r * sh24) + acc_x  (= (r >> 8) + acc_x)   IMAD.HI
+struct AccMul {
+  uint32_t one, sh24;
+};
+template <int MODE>
+__device__ __forceinline__ void acc_add(uint32_t& acc_e, uint32_t& acc_x, uint32_t r, const AccMul& m) {
+  const uint32_t e = r & 0x00FF00FFu;
+  if (MODE == 0) {  // everything on the ALU pipe (IADD3 / LEA.HI)
+    acc_e += e;
+    acc_x += r >> 8;
+  } else if (MODE == 1) {  // both adds on the FMA pipe
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc_e) : "r"(e), "r"(m.one));
+    asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(acc_x) : "r"(r), "r"(m.sh24));
+  } else {  // masked add on the FMA pipe, shifted add on the ALU pipe
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc_e) : "r"(e), "r"(m.one));
+    acc_x += r >> 8;
+  }
+}
+
 // Scan one 256-point block for G queries.  lut: shared memory, [G][S4] uint4 (one 16-entry u8
-// table per (query, subspace)).  On return sums[g][i] is the u32 accumulator of point lane*8+i —
-// the same integer src/simd/dispatch.rs:259-295 computes.
-template <int G>
+// table per (query, subspace)).  On return out[g] holds the eight u32 accumulators of points
+// lane*8+0..7 in packed form — the same integers src/simd/dispatch.rs:259-295 computes.
+template <int G, int MODE>
 __device__ __forceinline__ void scan_block(const uint4* __restrict__ blk, int SG, const uint4* __restrict__ lut,
-                                           int S4, int lane, uint32_t (&sums)[G][8]) {
+                                           int S4, int lane, const AccMul mul, PackedSums (&out)[G]) {
   uint32_t accEA[G], accXA[G], accEB[G], accXB[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) accEA[g] = accXA[g] = accEB[g] = accXB[g] = 0;
@@ -125,32 +194,18 @@ __device__ __forceinline__ void scan_block(const uint4* __restrict__ blk, int SG
         const uint32_t loB = __byte_perm(T.x, T.y, selB);
         const uint32_t hiB = __byte_perm(T.z, T.w, selB);
         const uint32_t rB = (loB & ~mB) | (hiB & mB);
-        accEA[g] += rA & 0x00FF00FFu;
-        accXA[g] += rA >> 8;
-        accEB[g] += rB & 0x00FF00FFu;
-        accXB[g] += rB >> 8;
+        acc_add<MODE>(accEA[g], accXA[g], rA, mul);
+        acc_add<MODE>(accEB[g], accXB[g], rB, mul);
       }
     }
     c = cn;
   }
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    uint32_t e = accEA[g], x = accXA[g];
-    uint32_t s0 = e & 0xFFFFu, s2 = e >> 16;
-    x -= s2 << 8;
-    sums[g][0] = s0;
-    sums[g][1] = x & 0xFFFFu;
-    sums[g][2] = s2;
-    sums[g][3] = x >> 16;
-    e = accEB[g];
-    x = accXB[g];
-    s0 = e & 0xFFFFu;
-    s2 = e >> 16;
-    x -= s2 << 8;
-    sums[g][4] = s0;
-    sums[g][5] = x & 0xFFFFu;
-    sums[g][6] = s2;
-    sums[g][7] = x >> 16;
+    out[g].ea = accEA[g];
+    out[g].xa = accXA[g] - ((accEA[g] >> 16) << 8);  // Σb1 + 2^16 Σb3
+    out[g].eb = accEB[g];
+    out[g].xb = accXB[g] - ((accEB[g] >> 16) << 8);
   }
 }
 

@@ -68,7 +68,8 @@ __global__ void repack_flat_kernel(const uint8_t* __restrict__ packed, size_t n,
 // all u32 accumulators of one u8 table over the blocked codes (scan_block<1>, the hot path's lookup)
 __global__ void __launch_bounds__(256) lut16_scan_all_kernel(const uint4* __restrict__ codes, size_t nblocks, int S,
                                                              int SG, const uint8_t* __restrict__ lut8, size_t n,
-                                                             uint32_t* __restrict__ sums) {
+                                                             uint32_t* __restrict__ sums, uint32_t one,
+                                                             uint32_t sh24) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int S4 = SG * 4;
   for (int e = threadIdx.x; e < S4 * 16; e += blockDim.x) sm[e] = e < S * 16 ? lut8[e] : 0;
@@ -76,11 +77,16 @@ __global__ void __launch_bounds__(256) lut16_scan_all_kernel(const uint4* __rest
   const uint4* lut = reinterpret_cast<const uint4*>(sm);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (size_t b = static_cast<size_t>(blockIdx.x) * 8 + warp; b < nblocks; b += static_cast<size_t>(gridDim.x) * 8) {
-    uint32_t s1[1][8];
-    scan_block<1>(codes + b * SG * 32, SG, lut, S4, lane, s1);
+    PackedSums ps[1];
+    AccMul mul;
+    mul.one = one;
+    mul.sh24 = sh24;
+    scan_block<1, kAccMode>(codes + b * SG * 32, SG, lut, S4, lane, mul, ps);
+    uint32_t s1[8];
+    unpack_sums(ps[0], s1);
     size_t p0 = b * kBlockPts + lane * 8;
     for (int i = 0; i < 8; ++i)
-      if (p0 + i < n) sums[p0 + i] = s1[0][i];
+      if (p0 + i < n) sums[p0 + i] = s1[i];
   }
 }
 
@@ -204,7 +210,7 @@ scann_status scann_lut16_scan(const uint8_t* packed, size_t n, size_t S, const u
   SCANN_CUDA(cudaGetLastError());
   unsigned grid = static_cast<unsigned>(std::min<size_t>((nblocks + 7) / 8, 148 * 8));
   lut16_scan_all_kernel<<<grid, 256, SG * 4 * 16>>>(reinterpret_cast<const uint4*>(d_codes.p), nblocks,
-                                                    static_cast<int>(S), static_cast<int>(SG), pl, n, ps);
+                                                    static_cast<int>(S), static_cast<int>(SG), pl, n, ps, 1u, 1u << 24);
   SCANN_CUDA(cudaGetLastError());
   if (host) SCANN_CUDA(cudaMemcpy(sums, ps, n * 4, cudaMemcpyDeviceToHost));
   SCANN_CUDA(cudaDeviceSynchronize());

@@ -20,8 +20,10 @@
 // ties of the approximate distance (BASELINE.json exempts those).
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "kernels.h"
-#include "lut16_device.cuh"
+#include "lut16_scan_kernel.cuh"
 
 namespace scann {
 
@@ -142,167 +144,6 @@ __global__ void wl_items_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t 
   if (l >= K) return;
   uint32_t c = leaf_cnt[l], pb = pair_start[l], ib = item_start[l];
   for (uint32_t g = 0; g * G < c; ++g) items[ib + g] = make_uint4(l, pb + g * G, min(static_cast<uint32_t>(G), c - g * G), 0u);
-}
-
-// ------------------------------------------------------------------------------- the scan kernel
-struct ScanArgs {
-  const uint4* codes;
-  const uint32_t* blk_off;
-  const uint64_t* pt_off;
-  const float* centers;
-  const float* codebook;
-  const float* queries;
-  const uint4* items;
-  const uint32_t* sorted_pairs;
-  uint32_t* counters;  // [0] total items, [1] next item
-  uint2* cand;         // [P][R] {approx distance bits, position in leaf}
-  uint32_t* cand_cnt;  // [P]
-  int dim, S, ds, SG, L, R, cap, pos_bits, use_residuals;
-};
-
-template <int G>
-__global__ void __launch_bounds__(kScanWarps * 32, 2) lut16_scan_kernel(const ScanArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int S4 = a.SG * 4;
-  uint4* lut = reinterpret_cast<uint4*>(smem);                      // [G][S4]
-  float* qres = reinterpret_cast<float*>(lut + G * S4);             // [G][dim]
-  uint32_t* buf = reinterpret_cast<uint32_t*>(qres + ((G * a.dim + 3) & ~3));  // [G][cap], 16-B aligned
-  uint32_t* hist = buf + static_cast<size_t>(G) * a.cap;            // [kScanWarps][256]
-  float* s_mult = reinterpret_cast<float*>(hist + kScanWarps * 256);
-  float* s_bias = s_mult + G;
-  uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_bias + G);
-  uint32_t* s_cnt = s_thr + G;
-  uint32_t* s_pair = s_cnt + G;
-  uint32_t* s_item = s_pair + G;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t total_items = a.counters[0];
-  const uint32_t pos_mask = (1u << a.pos_bits) - 1u;
-
-  for (;;) {
-    __syncthreads();  // previous item's shared memory is dead
-    if (tid == 0) *s_item = atomicAdd(&a.counters[1], 1u);
-    __syncthreads();
-    const uint32_t item = *s_item;
-    if (item >= total_items) break;
-    const uint4 it = a.items[item];
-    const uint32_t leaf = it.x, pbeg = it.y;
-    const int ng = static_cast<int>(it.z);
-    const uint32_t blk0 = a.blk_off[leaf];
-    const int nblk = static_cast<int>(a.blk_off[leaf + 1] - blk0);
-    const uint32_t leaf_n = static_cast<uint32_t>(a.pt_off[leaf + 1] - a.pt_off[leaf]);
-
-    // (1) query residuals: q - centroid (src/tree_x_hybrid/mod.rs:309-316)
-    for (int idx = tid; idx < G * a.dim; idx += kScanWarps * 32) {
-      int g = idx / a.dim, d = idx - g * a.dim;
-      float v = 0.0f;
-      if (g < ng) {
-        uint32_t pair = a.sorted_pairs[pbeg + g];
-        uint32_t q = pair / static_cast<uint32_t>(a.L);
-        v = a.queries[static_cast<size_t>(q) * a.dim + d];
-        if (a.use_residuals) v = __fsub_rn(v, __ldg(a.centers + static_cast<size_t>(leaf) * a.dim + d));
-      }
-      qres[idx] = v;
-    }
-    const int nfull0 = min(kScanWarps, static_cast<int>(leaf_n / kBlockPts));  // full blocks of tile 0
-    if (tid < G) {
-      s_pair[tid] = tid < ng ? a.sorted_pairs[pbeg + tid] : 0xFFFFFFFFu;
-      s_cnt[tid] = static_cast<uint32_t>(nfull0) * kBlockPts;
-      s_thr[tid] = 0xFFFFFFFFu;
-    }
-    __syncthreads();
-
-    // (2) LUT16 build, warp g builds query g's table
-    for (int g = warp; g < G; g += kScanWarps) {
-      uint8_t* l8 = reinterpret_cast<uint8_t*>(lut + g * S4);
-      if (g < ng) {
-        float mult, bias;
-        warp_build_lut16(qres + g * a.dim, a.codebook, a.S, S4, a.ds, l8, &mult, &bias, lane);
-        if (lane == 0) {
-          s_mult[g] = mult;
-          s_bias[g] = __fmul_rn(bias, static_cast<float>(a.S));  // bias * S, rounded once (lut16_simd.rs:137)
-        }
-      } else {
-        for (int e = lane; e < S4 * 16; e += 32) l8[e] = 0;
-      }
-    }
-    __syncthreads();
-
-    // (3) stream the leaf, one 256-point block per warp per tile
-    const int ntiles = (nblk + kScanWarps - 1) / kScanWarps;
-    for (int t = 0; t < ntiles; ++t) {
-      const int b = t * kScanWarps + warp;
-      if (b < nblk) {
-        uint32_t sums[G][8];
-        scan_block<G>(a.codes + (static_cast<size_t>(blk0) + b) * a.SG * 32, a.SG, lut, S4, lane, sums);
-        const uint32_t pos0 = static_cast<uint32_t>(b) * kBlockPts + lane * 8;
-        if (t == 0 && b < nfull0) {
-          // no threshold yet: every point of a full block goes to its fixed slot
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (g < ng) {
-              uint4* dst = reinterpret_cast<uint4*>(buf + static_cast<size_t>(g) * a.cap + pos0);
-              dst[0] = make_uint4((sums[g][0] << a.pos_bits) | (pos0 + 0), (sums[g][1] << a.pos_bits) | (pos0 + 1),
-                                  (sums[g][2] << a.pos_bits) | (pos0 + 2), (sums[g][3] << a.pos_bits) | (pos0 + 3));
-              dst[1] = make_uint4((sums[g][4] << a.pos_bits) | (pos0 + 4), (sums[g][5] << a.pos_bits) | (pos0 + 5),
-                                  (sums[g][6] << a.pos_bits) | (pos0 + 6), (sums[g][7] << a.pos_bits) | (pos0 + 7));
-            }
-          }
-        } else {
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (g < ng) {
-              const uint32_t thr = s_thr[g];
-              uint32_t* bg = buf + static_cast<size_t>(g) * a.cap;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const uint32_t pos = pos0 + i;
-                const uint32_t key = (sums[g][i] << a.pos_bits) | pos;
-                if (pos < leaf_n && key < thr) {
-                  uint32_t slot = atomicAdd(&s_cnt[g], 1u);
-                  if (slot < static_cast<uint32_t>(a.cap)) bg[slot] = key;
-                }
-              }
-            }
-          }
-        }
-      }
-      __syncthreads();
-      // exact compaction to the R best when the buffer could overflow in the next tile
-      for (int g = warp; g < ng; g += kScanWarps) {
-        int c = static_cast<int>(min(s_cnt[g], static_cast<uint32_t>(a.cap)));
-        if (c > a.R && (t == ntiles - 1 || c > 2 * a.R)) {
-          uint32_t T = warp_select_u32(buf + static_cast<size_t>(g) * a.cap, c, a.R, hist + warp * 256, lane);
-          if (lane == 0) {
-            s_cnt[g] = static_cast<uint32_t>(a.R);
-            s_thr[g] = T;
-          }
-        }
-      }
-      __syncthreads();
-    }
-
-    // (4) write this item's candidates: approx distance = sum*multiplier + bias*S (lut16_simd.rs:136-140)
-    for (int g = warp; g < ng; g += kScanWarps) {
-      const int c = static_cast<int>(min(s_cnt[g], static_cast<uint32_t>(a.R)));
-      const uint32_t pair = s_pair[g];
-      const float mult = s_mult[g], biasS = s_bias[g];
-      const uint32_t* bg = buf + static_cast<size_t>(g) * a.cap;
-      uint2* out = a.cand + static_cast<size_t>(pair) * a.R;
-      for (int i = lane; i < c; i += 32) {
-        uint32_t key = bg[i];
-        float dist = lut16_dequant(key >> a.pos_bits, mult, biasS);
-        out[i] = make_uint2(__float_as_uint(dist), key & pos_mask);
-      }
-      if (lane == 0) a.cand_cnt[pair] = static_cast<uint32_t>(c);
-    }
-  }
-}
-
-static size_t scan_smem_bytes(int G, int S4, int dim, int cap) {
-  return static_cast<size_t>(G) * S4 * 16 + static_cast<size_t>((G * dim + 3) & ~3) * 4 +
-         static_cast<size_t>(G) * cap * 4 +
-         kScanWarps * 256 * 4 + static_cast<size_t>(G) * 5 * 4 + 16;
 }
 
 // --------------------------------------------------------------------------- merge + exact reorder
@@ -455,19 +296,38 @@ struct scann_treeah {
 
 namespace scann {
 
-template <int G>
-static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
+template <int G, int MODE>
+static scann_status launch_scan_mode(const ScanArgs& a, int sms, cudaStream_t s) {
   size_t smem = scan_smem_bytes(G, a.SG * 4, a.dim, a.cap);
   SCANN_REQUIRE(smem <= 227 * 1024, SCANN_RESOURCE_EXHAUSTED, "scan kernel needs %zu B of shared memory (R too large)",
                 smem);
-  SCANN_CUDA(cudaFuncSetAttribute(lut16_scan_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCANN_CUDA(cudaFuncSetAttribute(lut16_scan_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   int occ = 0;
-  SCANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lut16_scan_kernel<G>, kScanWarps * 32, smem));
+  SCANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lut16_scan_kernel<G, MODE>, kScanWarps * 32, smem));
   if (occ < 1) occ = 1;
-  lut16_scan_kernel<G><<<sms * occ, kScanWarps * 32, smem, s>>>(a);
+  lut16_scan_kernel<G, MODE><<<sms * occ, kScanWarps * 32, smem, s>>>(a);
   SCANN_CUDA(cudaGetLastError());
   return SCANN_OK;
+}
+
+// accumulation pipe mode (lut16_device.cuh acc_add): default kAccMode, SCANN_ACC_MODE=0|1|2 overrides (tuning)
+static int acc_mode() {
+  static int mode = [] {
+    const char* e = getenv("SCANN_ACC_MODE");
+    int m = e ? atoi(e) : kAccMode;
+    return (m < 0 || m > 2) ? kAccMode : m;
+  }();
+  return mode;
+}
+
+template <int G>
+static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
+  switch (acc_mode()) {
+    case 0: return launch_scan_mode<G, 0>(a, sms, s);
+    case 2: return launch_scan_mode<G, 2>(a, sms, s);
+    default: return launch_scan_mode<G, 1>(a, sms, s);
+  }
 }
 
 static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
@@ -490,6 +350,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   uint4* items = h->ws.take<uint4>(max_items);
   uint2* cand = h->ws.take<uint2>(P * R);
   uint32_t* cand_cnt = h->ws.take<uint32_t>(P);
+  uint32_t* qthr = h->ws.take<uint32_t>(nq);
 
   // 1. partition (K == 1 still goes through it: one centre, token 0)
   h->mark(s);
@@ -498,6 +359,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   // 2. worklist
   SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 2 * K * sizeof(uint32_t), s));
   SCANN_CUDA(cudaMemsetAsync(cand_cnt, 0, P * sizeof(uint32_t), s));
+  SCANN_CUDA(cudaMemsetAsync(qthr, 0xFF, nq * sizeof(uint32_t), s));
   unsigned pb = static_cast<unsigned>((P + 255) / 256);
   wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), leaf_cnt);
   wl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->pt_off.p,
@@ -521,6 +383,9 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   a.counters = counters;
   a.cand = cand;
   a.cand_cnt = cand_cnt;
+  a.qthr = qthr;
+  a.mul.one = 1u;
+  a.mul.sh24 = 1u << 24;
   a.dim = static_cast<int>(h->dim);
   a.S = static_cast<int>(h->S);
   a.ds = static_cast<int>(h->ds);
@@ -583,6 +448,7 @@ static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, siz
   add((P + K + 2) * 16);
   add(P * R * 8);
   add(P * 4);
+  add(nq * 4);
   if (host) {
     add(nq * h->dim * 4);
     add(nq * k * 4);
