@@ -246,10 +246,7 @@ def main():
     def step_device(qb):
         ids, dists, cnt = searcher.search_batched(qb, a.k, pre_reorder_k=R)
         if world > 1:
-            gi = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=dev)
-            gd = torch.empty((world,) + tuple(dists.shape), dtype=dists.dtype, device=dev)
-            dist.all_gather_into_tensor(gi, ids)
-            dist.all_gather_into_tensor(gd, dists)
+            gi, gd = pkg.distributed.all_gather_results(ids, dists)
             ids, dists, cnt = pkg.merge_topk(gi, gd, local_rank)
         return ids, dists, cnt
 
@@ -324,10 +321,8 @@ def main():
     def step_host(b):
         ids, dists, cnt = searcher.search_batched(hq_np[b], a.k, pre_reorder_k=R)
         if world > 1:
-            gi = torch.empty((world,) + ids.shape, dtype=torch.int32, device=dev)
-            gd = torch.empty((world,) + dists.shape, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(gi, torch.from_numpy(ids.view(np.int32)).to(dev))
-            dist.all_gather_into_tensor(gd, torch.from_numpy(dists).to(dev))
+            gi, gd = pkg.distributed.all_gather_results(torch.from_numpy(ids.view(np.int32)).to(dev),
+                                                        torch.from_numpy(dists).to(dev))
             mi, md, mc = pkg.merge_topk(gi, gd, local_rank)
             return mi.cpu().numpy(), md.cpu().numpy()
         return ids, dists

@@ -7,7 +7,7 @@ CUDA library or a device is missing.  (The directory name has a hyphen; import i
 ``importlib.import_module("scann-rust_b200")``.)
 """
 from . import build as build_lib  # noqa: F401
-from . import capi, indexing, scann, searchers  # noqa: F401
+from . import capi, distributed, indexing, scann, searchers  # noqa: F401
 from .capi import ScannError, device_count, load  # noqa: F401
 from .scann import Scann, ScannBuilder, ScannConfig, SearchMode  # noqa: F401
 from .searchers import (AsymmetricHasher, AsymmetricHasherConfig, BruteForceSearcher, DistanceMeasure,  # noqa: F401
