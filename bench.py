@@ -53,6 +53,8 @@ def parse():
     p.add_argument("--cpu-queries", type=int, default=128)
     p.add_argument("--ref-queries", type=int, default=128)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--shard", default="partition", choices=["partition", "rows"],
+                   help="multi-GPU sharding: whole partitions per GPU (default) or rows round-robin inside partitions")
     p.add_argument("--sweep-leaves", default="", help="comma list: print recall/QPS for each L (stderr) and exit")
     return p.parse_args()
 
@@ -120,6 +122,13 @@ class ClockSampler:
 
 def main():
     a = parse()
+    # keep stdout clean for the single JSON line: libraries (NCCL banner, …) write to fd 1
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     import torch
     import torch.distributed as dist
 
@@ -129,7 +138,7 @@ def main():
     if a.impl == "reference" and rank != 0:
         return 0
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device; the product path has no CPU fallback"}))
+        emit({"error": "no CUDA device; the product path has no CPU fallback"})
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -172,10 +181,18 @@ def main():
     off = torch.zeros((K + 1,), dtype=torch.int64, device=dev)
     off[1:] = torch.cumsum(counts, 0)
     shard_world = world if a.impl == "ours" else 1
-    if shard_world > 1:  # round-robin inside each partition
+    if shard_world > 1:
         pos = torch.arange(a.n, device=dev, dtype=torch.int64)
         leaf_sorted = assign.long()[order]
-        keep = ((pos - off[leaf_sorted]) % shard_world) == rank
+        if a.shard == "rows":  # round-robin inside each partition
+            keep = ((pos - off[leaf_sorted]) % shard_world) == rank
+        else:  # whole partitions per GPU, dealt largest-first in snake order so shard sizes balance
+            by_size = torch.argsort(counts, descending=True)
+            slot = torch.arange(K, device=dev) % (2 * shard_world)
+            owner_sorted = torch.where(slot < shard_world, slot, 2 * shard_world - 1 - slot)
+            owner = torch.empty(K, dtype=torch.int64, device=dev)
+            owner[by_size] = owner_sorted
+            keep = owner[leaf_sorted] == rank
         order = order[keep]
         cnt = torch.bincount(leaf_sorted[keep], minlength=K)
         off = torch.zeros((K + 1,), dtype=torch.int64, device=dev)
@@ -201,7 +218,8 @@ def main():
                             "L2-normalised; seeds db 42 / queries 123+ / train 7",
               "l2_policy": "inputs larger than L2: 24 B/point codes of the probed leaves (7.7 MB/query, 240 MB index) "
                            "+ 3.84 GB raw rows; two alternating query batches",
-              "parallelism": f"row-sharded x{shard_world}" if shard_world > 1 else "single GPU"}
+              "parallelism": (f"{a.shard}-sharded x{shard_world}, NCCL all-gather of (id, dist) top-k + merge kernel"
+                              if shard_world > 1 else "single GPU")}
 
     # ---------------- the CPU arm (oracle = C++ restatement of the reference algorithm) ----------------
     def cpu_arm(nq_cpu, repeats=1):
@@ -225,7 +243,7 @@ def main():
         nqc, nthreads, times, _ = cpu_arm(a.ref_queries, a.warmup + a.steps)
         tt = times[a.warmup:]
         val = nqc * len(tt) / sum(tt)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "queries/sec", "value": val, "unit": "queries/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sum(tt) / len(tt), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8 LUT / u32 accumulate, f32 reorder",
@@ -234,7 +252,7 @@ def main():
                              "sample": f"{nqc} queries per step of the same index; oracle/ C++ restatement of the "
                                        "reference algorithm (the Rust crate cannot be built in this image)"},
             "e2e": {"value": val, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})
         return 0
 
     # ---------------- the GPU searcher ----------------
@@ -382,7 +400,7 @@ def main():
         out["cpu_baseline"] = {"value": nqc / times[0], "unit": "queries/s", "cores": nthreads, "kind": "port",
                                "sample": f"{nqc} queries of the same batch on the same index; oracle/ C++ restatement "
                                          "of the reference algorithm, one task per query over all host threads"}
-    print(json.dumps(out))
+    emit(out)
     return 0
 
 

@@ -61,12 +61,14 @@ __global__ void repack_blocked_kernel(const uint8_t* __restrict__ packed, const 
 }
 
 // --------------------------------------------------------------------------------------- worklist
+// Pairs that probe a leaf with no rows on this shard (empty partition, or a partition owned by another
+// GPU) produce no work item; their candidate count stays 0.
 __global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K,
-                                uint32_t* __restrict__ leaf_cnt) {
+                                const uint64_t* __restrict__ pt_off, uint32_t* __restrict__ leaf_cnt) {
   size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint32_t leaf = tokens[p];
-  if (leaf < K) atomicAdd(&leaf_cnt[leaf], 1u);
+  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[leaf], 1u);
 }
 
 // single block: exclusive scans of pair counts and item counts per leaf; also accumulates the
@@ -126,12 +128,12 @@ __global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restric
 }
 
 __global__ void wl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K,
-                                  const uint32_t* __restrict__ pair_start, uint32_t* __restrict__ cursor,
-                                  uint32_t* __restrict__ sorted_pairs) {
+                                  const uint64_t* __restrict__ pt_off, const uint32_t* __restrict__ pair_start,
+                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted_pairs) {
   size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint32_t leaf = tokens[p];
-  if (leaf < K) {
+  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) {
     uint32_t slot = atomicAdd(&cursor[leaf], 1u);
     sorted_pairs[pair_start[leaf] + slot] = static_cast<uint32_t>(p);
   }
@@ -361,11 +363,12 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   SCANN_CUDA(cudaMemsetAsync(cand_cnt, 0, P * sizeof(uint32_t), s));
   SCANN_CUDA(cudaMemsetAsync(qthr, 0xFF, nq * sizeof(uint32_t), s));
   unsigned pb = static_cast<unsigned>((P + 255) / 256);
-  wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), leaf_cnt);
+  wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), h->pt_off.p, leaf_cnt);
   wl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->pt_off.p,
                                     static_cast<uint32_t>((h->S + 1) / 2), pair_start, item_start, counters,
                                     h->stats.p);
-  wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), pair_start, cursor, sorted_pairs);
+  wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), h->pt_off.p, pair_start, cursor,
+                                       sorted_pairs);
   wl_items_kernel<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
                                                                         pair_start, item_start, items);
   SCANN_CUDA(cudaGetLastError());

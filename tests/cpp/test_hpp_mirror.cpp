@@ -1,0 +1,61 @@
+// Drives the C++ host mirror (include/scann_b200.hpp) with the reference's brute-force / partitioner unit
+// tests (src/brute_force/searcher.rs:280-377, src/partitioning/tree_partitioner.rs:289-304).
+// Built by tests/test_cpp_mirror.py with g++ against libscann_b200.so; run on a GPU box.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "scann_b200.hpp"
+
+#define CHECK(cond)                                                      \
+  do {                                                                   \
+    if (!(cond)) {                                                       \
+      std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+      return 1;                                                          \
+    }                                                                    \
+  } while (0)
+
+int main() {
+  using namespace scann;
+  const float ds5[5 * 3] = {0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, 1, 1, 1};
+  auto bf = BruteForceSearcher::create(ds5, 5, 3, 3, DistanceMeasure::SquaredL2);
+  CHECK(bf.ok());
+  auto r = bf.value.search({0.f, 0.f, 0.f}, 3);  // test_brute_force_search
+  CHECK(r.ok() && r.value.size() == 3 && r.value[0].first == 0 && std::fabs(r.value[0].second) < 1e-6f);
+  auto all = bf.value.search({0.5f, 0.5f, 0.5f}, 5);  // test_brute_force_search_all
+  CHECK(all.ok() && all.value.size() == 5);
+  for (size_t i = 1; i < all.value.size(); ++i) CHECK(all.value[i].second >= all.value[i - 1].second);
+  auto batch = bf.value.search_batched({{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}}, 2);  // test_brute_force_batched
+  CHECK(batch.ok() && batch.value.size() == 2 && batch.value[0].size() == 2 && batch.value[1][0].first == 4);
+  auto bad = bf.value.search({1.f, 2.f}, 5);  // test_brute_force_dimension_mismatch
+  CHECK(!bad.ok() && bad.error.code == ErrorCode::InvalidArgument);
+  auto clamp = bf.value.search({0.f, 0.f, 0.f}, 50);  // k clamped to n
+  CHECK(clamp.ok() && clamp.value.size() == 5);
+  auto empty = BruteForceSearcher::create(nullptr, 0, 3, 3, DistanceMeasure::SquaredL2);  // test_brute_force_empty_dataset
+  CHECK(empty.ok());
+  auto er = empty.value.search({1.f, 2.f, 3.f}, 5);
+  CHECK(er.ok() && er.value.empty());
+
+  const float dot3[3 * 2] = {1, 0, 0, 1, 1, 1};
+  auto dp = BruteForceSearcher::create(dot3, 3, 2, 2, DistanceMeasure::DotProduct);
+  CHECK(dp.ok());
+  auto dr = dp.value.search({1.f, 0.f}, 3);  // test_brute_force_search_dot_product
+  CHECK(dr.ok() && dr.value.size() == 3 && dr.value[0].second == -1.0f && dr.value[2].second == 0.0f);
+
+  const float centers[4 * 2] = {1, 0, 0, 1, 5, 5, 0, -1};
+  auto part = TreePartitioner::from_centers(centers, 4, 2);
+  CHECK(part.ok());
+  auto pr = part.value.partition({0.f, 0.f}, 3);
+  CHECK(pr.ok() && pr.value.tokens.size() == 3 && pr.value.tokens[0] == 0 && pr.value.tokens[1] == 1 &&
+        pr.value.tokens[2] == 3);
+  auto pall = part.value.partition({0.f, 0.f}, 10);  // more than K → K results
+  CHECK(pall.ok() && pall.value.tokens.size() == 4);
+  TreePartitioner unbuilt;
+  auto pu = unbuilt.partition({0.f, 0.f}, 1);
+  CHECK(!pu.ok() && pu.error.code == ErrorCode::FailedPrecondition);
+
+  TreeXHybridConfig cfg;
+  CHECK(cfg.pre_reorder_k(10) == 30);
+  std::puts("hpp mirror ok");
+  return 0;
+}
