@@ -18,4 +18,8 @@ scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, 
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
                                uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s);
 
+// runtime.cu — accumulation mode of the LUT16 scan for a table of S subspaces (lut16_device.cuh scan_block):
+// default 3 (IDP.2A, needs S <= 128) else 2; SCANN_ACC_MODE=0|1|2|3 overrides (tuning / parity tests)
+int scan_acc_mode(int S);
+
 }  // namespace scann

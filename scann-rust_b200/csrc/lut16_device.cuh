@@ -26,7 +26,7 @@ namespace scann {
 constexpr int kBlockPts = 256;   // points per code block (32 lanes x 8 nibbles)
 constexpr int kScanWarps = 8;    // warps per CTA of the scan kernel
 constexpr int kTilePts = kBlockPts * kScanWarps;
-constexpr int kAccMode = 2;      // default accumulation pipe mode, see acc_add() (measured best on B200)
+constexpr int kAccMode = 3;      // default accumulation mode, see scan_block() (measured best on B200)
 
 #ifdef __CUDACC__
 
@@ -144,7 +144,7 @@ __device__ __forceinline__ uint32_t min_sum(const PackedSums& p) {
 //   acc_e = (r & 0x00FF00FF) * one + acc_e            IMAD
 //   acc_x = hi32(r * sh24) + acc_x  (= (r >> 8) + acc_x)   IMAD.HI
 struct AccMul {
-  uint32_t one, sh24;
+  uint32_t one, sh24, w15;  // 1, 1 << 24, (1 | 2^15 << 16): the IDP.2A weight pair of MODE 3
 };
 template <int MODE>
 __device__ __forceinline__ void acc_add(uint32_t& acc_e, uint32_t& acc_x, uint32_t r, const AccMul& m) {
@@ -164,6 +164,13 @@ __device__ __forceinline__ void acc_add(uint32_t& acc_e, uint32_t& acc_x, uint32
 // Scan one 256-point block for G queries.  lut: shared memory, [G][S4] uint4 (one 16-entry u8
 // table per (query, subspace)).  On return out[g] holds the eight u32 accumulators of points
 // lane*8+0..7 in packed form — the same integers src/simd/dispatch.rs:259-295 computes.
+//
+// MODE 3 (S <= 128): the four bytes of a lookup result r are accumulated by two IDP.2A instructions on
+// the FMA pipe with the constant weight pair w = (1, 2^15):
+//   acc01 += b0 + 2^15 * b1      (dp2a.lo)        acc23 += b2 + 2^15 * b3      (dp2a.hi)
+// Each per-point sum is < 2^15 for S <= 128 (128 * 255 = 32640), so the two 15-bit fields never carry
+// into each other and the accumulators stay below 2^30.  No mask, no shift: the ALU pipe only carries
+// the three lookup instructions (PRMT, PRMT, LOP3) per four lookups.
 template <int G, int MODE>
 __device__ __forceinline__ void scan_block(const uint4* __restrict__ blk, int SG, const uint4* __restrict__ lut,
                                            int S4, int lane, const AccMul mul, PackedSums (&out)[G]) {
@@ -194,18 +201,32 @@ __device__ __forceinline__ void scan_block(const uint4* __restrict__ blk, int SG
         const uint32_t loB = __byte_perm(T.x, T.y, selB);
         const uint32_t hiB = __byte_perm(T.z, T.w, selB);
         const uint32_t rB = (loB & ~mB) | (hiB & mB);
-        acc_add<MODE>(accEA[g], accXA[g], rA, mul);
-        acc_add<MODE>(accEB[g], accXB[g], rB, mul);
+        if (MODE == 3) {
+          asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(accEA[g]) : "r"(mul.w15), "r"(rA));
+          asm("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(accXA[g]) : "r"(mul.w15), "r"(rA));
+          asm("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(accEB[g]) : "r"(mul.w15), "r"(rB));
+          asm("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(accXB[g]) : "r"(mul.w15), "r"(rB));
+        } else {
+          acc_add<MODE>(accEA[g], accXA[g], rA, mul);
+          acc_add<MODE>(accEB[g], accXB[g], rB, mul);
+        }
       }
     }
     c = cn;
   }
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    out[g].ea = accEA[g];
-    out[g].xa = accXA[g] - ((accEA[g] >> 16) << 8);  // Σb1 + 2^16 Σb3
-    out[g].eb = accEB[g];
-    out[g].xb = accXB[g] - ((accEB[g] >> 16) << 8);
+    if (MODE == 3) {  // (p0 | p1 << 15), (p2 | p3 << 15)  ->  (p0 | p2 << 16), (p1 | p3 << 16)
+      out[g].ea = (accEA[g] & 0x7FFFu) | ((accXA[g] & 0x7FFFu) << 16);
+      out[g].xa = (accEA[g] >> 15) | ((accXA[g] >> 15) << 16);
+      out[g].eb = (accEB[g] & 0x7FFFu) | ((accXB[g] & 0x7FFFu) << 16);
+      out[g].xb = (accEB[g] >> 15) | ((accXB[g] >> 15) << 16);
+    } else {
+      out[g].ea = accEA[g];
+      out[g].xa = accXA[g] - ((accEA[g] >> 16) << 8);  // Σb1 + 2^16 Σb3
+      out[g].eb = accEB[g];
+      out[g].xb = accXB[g] - ((accEB[g] >> 16) << 8);
+    }
   }
 }
 

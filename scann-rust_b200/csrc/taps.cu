@@ -66,6 +66,7 @@ __global__ void repack_flat_kernel(const uint8_t* __restrict__ packed, size_t n,
 }
 
 // all u32 accumulators of one u8 table over the blocked codes (scan_block<1>, the hot path's lookup)
+template <int MODE>
 __global__ void __launch_bounds__(256) lut16_scan_all_kernel(const uint4* __restrict__ codes, size_t nblocks, int S,
                                                              int SG, const uint8_t* __restrict__ lut8, size_t n,
                                                              uint32_t* __restrict__ sums, uint32_t one,
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(256) lut16_scan_all_kernel(const uint4* __rest
     AccMul mul;
     mul.one = one;
     mul.sh24 = sh24;
-    scan_block<1, kAccMode>(codes + b * SG * 32, SG, lut, S4, lane, mul, ps);
+    mul.w15 = 0x80000001u;
+    scan_block<1, MODE>(codes + b * SG * 32, SG, lut, S4, lane, mul, ps);
     uint32_t s1[8];
     unpack_sums(ps[0], s1);
     size_t p0 = b * kBlockPts + lane * 8;
@@ -209,8 +211,18 @@ scann_status scann_lut16_scan(const uint8_t* packed, size_t n, size_t S, const u
                                                                           static_cast<int>(SG), words, d_codes.p);
   SCANN_CUDA(cudaGetLastError());
   unsigned grid = static_cast<unsigned>(std::min<size_t>((nblocks + 7) / 8, 148 * 8));
-  lut16_scan_all_kernel<<<grid, 256, SG * 4 * 16>>>(reinterpret_cast<const uint4*>(d_codes.p), nblocks,
-                                                    static_cast<int>(S), static_cast<int>(SG), pl, n, ps, 1u, 1u << 24);
+  // same accumulation mode as the product path would pick for this S (treeah.cu launch_scan)
+  const int mode = scan_acc_mode(static_cast<int>(S));
+  auto launch = [&](auto kern) {
+    kern<<<grid, 256, SG * 4 * 16>>>(reinterpret_cast<const uint4*>(d_codes.p), nblocks, static_cast<int>(S),
+                                     static_cast<int>(SG), pl, n, ps, 1u, 1u << 24);
+  };
+  switch (mode) {
+    case 0: launch(lut16_scan_all_kernel<0>); break;
+    case 1: launch(lut16_scan_all_kernel<1>); break;
+    case 3: launch(lut16_scan_all_kernel<3>); break;
+    default: launch(lut16_scan_all_kernel<2>); break;
+  }
   SCANN_CUDA(cudaGetLastError());
   if (host) SCANN_CUDA(cudaMemcpy(sums, ps, n * 4, cudaMemcpyDeviceToHost));
   SCANN_CUDA(cudaDeviceSynchronize());

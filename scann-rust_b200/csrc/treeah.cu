@@ -313,22 +313,13 @@ static scann_status launch_scan_mode(const ScanArgs& a, int sms, cudaStream_t s)
   return SCANN_OK;
 }
 
-// accumulation pipe mode (lut16_device.cuh acc_add): default kAccMode, SCANN_ACC_MODE=0|1|2 overrides (tuning)
-static int acc_mode() {
-  static int mode = [] {
-    const char* e = getenv("SCANN_ACC_MODE");
-    int m = e ? atoi(e) : kAccMode;
-    return (m < 0 || m > 2) ? kAccMode : m;
-  }();
-  return mode;
-}
-
 template <int G>
 static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
-  switch (acc_mode()) {
+  switch (scan_acc_mode(a.S)) {
     case 0: return launch_scan_mode<G, 0>(a, sms, s);
-    case 2: return launch_scan_mode<G, 2>(a, sms, s);
-    default: return launch_scan_mode<G, 1>(a, sms, s);
+    case 1: return launch_scan_mode<G, 1>(a, sms, s);
+    case 3: return launch_scan_mode<G, 3>(a, sms, s);
+    default: return launch_scan_mode<G, 2>(a, sms, s);
   }
 }
 
@@ -389,6 +380,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   a.qthr = qthr;
   a.mul.one = 1u;
   a.mul.sh24 = 1u << 24;
+  a.mul.w15 = 0x80000001u;
   a.dim = static_cast<int>(h->dim);
   a.S = static_cast<int>(h->S);
   a.ds = static_cast<int>(h->ds);

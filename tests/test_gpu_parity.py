@@ -64,6 +64,21 @@ def test_lut16_scan_accumulators_bit_exact(gpu_lib, oracle, S, n):
     assert (got == want).all()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("S", [48, 128, 129])
+def test_lut16_scan_every_accumulation_mode(gpu_lib, oracle, monkeypatch, mode, S):
+    # the four accumulation variants of scan_block (ALU adds, IMAD/IMAD.HI, IMAD/LEA.HI, IDP.2A) give the same
+    # integers; S = 128 with all-255 tables is the largest sum the 15-bit IDP.2A fields must hold (32640),
+    # S = 129 must fall back to mode 2 by itself
+    monkeypatch.setenv("SCANN_ACC_MODE", str(mode))
+    rng = np.random.default_rng(S * 7 + mode)
+    n = 10_007
+    codes = rng.integers(0, 16, (n, S), dtype=np.uint8)
+    packed = oracle.pack4(codes)
+    lut8 = np.full((S, 16), 255, np.uint8) if S >= 128 else rng.integers(0, 256, (S, 16), dtype=np.uint8)
+    assert (gpu_lib.lut16_scan(packed, S, lut8) == oracle.lut16_scan_u32(packed, lut8, S)).all()
+
+
 def test_lut16_scan_1m_x_96(gpu_lib, oracle):
     # SURVEY §7.2 minimum slice: 1M x 96 synthetic codes, S = 48: all u32 accumulators bit-identical
     rng = np.random.default_rng(5)
