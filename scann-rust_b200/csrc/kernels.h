@@ -18,6 +18,33 @@ scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, 
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
                                uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s);
 
+// tc_gemm.cu — tcgen05/TMEM/TMA ranking contraction (bf16 operands, f32 accumulation).  See the file header.
+struct TcScoreParams {
+  const void* q_bf16;        // [tc_queries_pad(nq, dim)][tc_kpad(dim)] from tc_prepare_queries
+  size_t nq, dim;
+  const void* rows_bf16;     // [rows_pad_total][tc_kpad(dim)] from tc_prepare_rows
+  size_t rows_pad_total;
+  const float* hx;           // [rows_pad_total]
+  size_t row0, nrows;        // rows [row0, row0 + nrows) of this launch; row0 % 128 == 0
+  bool filter;               // false: dense scores, true: threshold filter into candidate lists
+  float* dense;              // [nq][ld], column = row - row0 (columns up to the next multiple of 128 are written)
+  size_t ld;
+  const float* thr;          // [nq]
+  unsigned long long* cand;  // [nq][cap]  (f32_key(v) << 32 | row)
+  size_t cap;
+  uint32_t* cand_cnt;        // [nq]
+  int sms;
+};
+size_t tc_kpad(size_t dim);
+bool tc_supported(size_t dim);                      // dim <= 256
+size_t tc_rows_pad(size_t n);                       // multiple of 128
+size_t tc_queries_pad(size_t nq, size_t dim);       // multiple of 128 or 256
+scann_status tc_prepare_rows(const void* rows, bool i8, size_t n, size_t dim, size_t stride, float scale,
+                             bool want_norm, void* dst_bf16, float* hx, float* norm_max, cudaStream_t s);
+scann_status tc_prepare_queries(const float* q, size_t nq, size_t dim, float scale, void* dst_bf16, float* qn,
+                                cudaStream_t s);
+scann_status launch_tc_scores(const TcScoreParams& p, cudaStream_t s);
+
 // runtime.cu — accumulation mode of the LUT16 scan for a table of S subspaces (lut16_device.cuh scan_block):
 // default 3 (IDP.2A, needs S <= 128) else 2; SCANN_ACC_MODE=0|1|2|3 overrides (tuning / parity tests)
 int scan_acc_mode(int S);

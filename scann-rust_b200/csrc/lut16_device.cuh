@@ -24,8 +24,6 @@
 namespace scann {
 
 constexpr int kBlockPts = 256;   // points per code block (32 lanes x 8 nibbles)
-constexpr int kScanWarps = 8;    // warps per CTA of the scan kernel
-constexpr int kTilePts = kBlockPts * kScanWarps;
 constexpr int kAccMode = 3;      // default accumulation mode, see scan_block() (measured best on B200)
 
 #ifdef __CUDACC__

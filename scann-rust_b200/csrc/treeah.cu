@@ -298,28 +298,45 @@ struct scann_treeah {
 
 namespace scann {
 
-template <int G, int MODE>
-static scann_status launch_scan_mode(const ScanArgs& a, int sms, cudaStream_t s) {
-  size_t smem = scan_smem_bytes(G, a.SG * 4, a.dim, a.cap);
+template <int G, int MODE, int NW>
+static scann_status launch_scan_mode(ScanArgs a, int sms, cudaStream_t s) {
+  a.cap = (NW * kBlockPts + 2 * a.R + 31) / 32 * 32;  // one tile of unfiltered points + 2R carried
+  size_t smem = scan_smem_bytes(G, a.SG * 4, a.dim, a.cap, NW);
   SCANN_REQUIRE(smem <= 227 * 1024, SCANN_RESOURCE_EXHAUSTED, "scan kernel needs %zu B of shared memory (R too large)",
                 smem);
-  SCANN_CUDA(cudaFuncSetAttribute(lut16_scan_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCANN_CUDA(cudaFuncSetAttribute(lut16_scan_kernel<G, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   int occ = 0;
-  SCANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lut16_scan_kernel<G, MODE>, kScanWarps * 32, smem));
+  SCANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lut16_scan_kernel<G, MODE, NW>, NW * 32, smem));
   if (occ < 1) occ = 1;
-  lut16_scan_kernel<G, MODE><<<sms * occ, kScanWarps * 32, smem, s>>>(a);
+  lut16_scan_kernel<G, MODE, NW><<<sms * occ, NW * 32, smem, s>>>(a);
   SCANN_CUDA(cudaGetLastError());
   return SCANN_OK;
+}
+
+// warps per scan CTA: default 8 (2 CTAs/SM), SCANN_SCAN_WARPS=4 selects 4 (4 CTAs/SM).  Measured on B200 at C3:
+// 8 warps 35.6 ms, 4 warps 35.8 ms, 2 warps 44.7 ms (profiles/r1_scan_kernel.md).
+static int scan_warps() {
+  const char* e = getenv("SCANN_SCAN_WARPS");
+  int w = e ? atoi(e) : 8;
+  return (w == 4 || w == 8) ? w : 8;
+}
+
+template <int G, int MODE>
+static scann_status launch_scan_nw(const ScanArgs& a, int sms, cudaStream_t s) {
+  switch (scan_warps()) {
+    case 4: return launch_scan_mode<G, MODE, 4>(a, sms, s);
+    default: return launch_scan_mode<G, MODE, 8>(a, sms, s);
+  }
 }
 
 template <int G>
 static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
   switch (scan_acc_mode(a.S)) {
-    case 0: return launch_scan_mode<G, 0>(a, sms, s);
-    case 1: return launch_scan_mode<G, 1>(a, sms, s);
-    case 3: return launch_scan_mode<G, 3>(a, sms, s);
-    default: return launch_scan_mode<G, 2>(a, sms, s);
+    case 0: return launch_scan_nw<G, 0>(a, sms, s);
+    case 1: return launch_scan_nw<G, 1>(a, sms, s);
+    case 3: return launch_scan_nw<G, 3>(a, sms, s);
+    default: return launch_scan_nw<G, 2>(a, sms, s);
   }
 }
 
@@ -387,7 +404,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   a.SG = static_cast<int>(h->SG);
   a.L = static_cast<int>(L);
   a.R = static_cast<int>(R);
-  a.cap = static_cast<int>((kTilePts + 2 * R + 31) / 32 * 32);
+  a.cap = 0;  // set per CTA shape in launch_scan_mode
   a.pos_bits = h->pos_bits;
   a.use_residuals = h->use_residuals;
   switch (G) {
