@@ -324,6 +324,8 @@ def main():
     prof, launches = searcher.get_profile()
     searcher.set_profiling(False)
     scan_bytes, pairs = searcher.last_scan_bytes()  # algorithmic bytes of one step (this rank's shard)
+    log(f"[rank {rank}] {ms / a.steps:.3f} ms/step; stages " +
+        ", ".join(f"{k2} {v / a.steps:.3f}" for k2, v in prof.items()) + f"; scan bytes {scan_bytes / 1e9:.1f} GB")
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

@@ -83,6 +83,9 @@ scann_status scann_bf_create(const float* db, size_t n, size_t dim, size_t strid
 scann_status scann_bf_search(scann_bf* h, const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids,
                              float* dists, uint32_t* counts, int memspace, void* stream);
 void scann_bf_destroy(scann_bf* h);
+/* introspection: query chunks answered by the tensor-core ranking path (csrc/tc_gemm.cu + exact re-score)
+ * and by the CUDA-core path (dim > 256, list overflow) since the handle was created */
+scann_status scann_bf_path_stats(scann_bf* h, uint64_t* tc_chunks, uint64_t* legacy_chunks);
 
 /* ---------------------------------------------------------------------------------------------
  * ScalarQuantizedBruteForceSearcher  (src/brute_force/scalar_quantized.rs:99-326)
@@ -101,6 +104,7 @@ scann_status scann_sq8_create(const int8_t* codes, size_t n, size_t dim, float s
 scann_status scann_sq8_search(scann_sq8* h, const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids,
                               float* dists, uint32_t* counts, int memspace, void* stream);
 void scann_sq8_destroy(scann_sq8* h);
+scann_status scann_sq8_path_stats(scann_sq8* h, uint64_t* tc_chunks, uint64_t* legacy_chunks);
 
 /* ---------------------------------------------------------------------------------------------
  * TreePartitioner, query side  (src/partitioning/tree_partitioner.rs:175-229)
@@ -162,6 +166,23 @@ scann_status scann_lut16_build(const float* codebook, size_t S, size_t ds, const
                                float* mult, int device, int memspace);
 scann_status scann_lut16_scan(const uint8_t* packed, size_t n, size_t S, const uint8_t* lut8, uint32_t* sums,
                               int device, int memspace);
+
+/* ---------------------------------------------------------------------------------------------
+ * Parity tap for the tensor-core ranking contraction (csrc/tc_gemm.cu; tcgen05 + TMEM + TMA) that stands in
+ * for the inner loops of BruteForceSearcher::compute_distances (src/brute_force/searcher.rs:113-139),
+ * ScalarQuantizedBruteForceSearcher::compute_distances (src/brute_force/scalar_quantized.rs:204-246) and
+ * TreePartitioner::compute_center_distances (src/partitioning/tree_partitioner.rs:175-194) as a RANKING
+ * device: v[q][r] = hx[r] - bf16(q * qscale) . bf16(x_r) with f32 accumulation; hx = |x_r|^2 / 2 (of
+ * (i8)x * scale for rows_i8) when want_norm, else 0; qscale = scale for i8 rows, 1 otherwise.
+ *   thr == NULL: dense[nq*n] receives every score.
+ *   thr != NULL: rows with v <= thr[q] are appended to cand[q*cap ...] as (ordered_key(v) << 32 | row) in
+ *                arbitrary order; cand_cnt[q] counts them (values above cap mean overflow).
+ * Host buffers only.  No value this tap returns is ever a search result: the searchers re-score the survivors
+ * exactly in the reference's summation order.
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const void* rows, int rows_i8, size_t n,
+                             size_t stride, float scale, int want_norm, const float* thr, float* dense,
+                             uint64_t* cand, size_t cap, uint32_t* cand_cnt, int device);
 
 /* ---------------------------------------------------------------------------------------------
  * Index-build helpers with the reference's exact semantics (needed to build the

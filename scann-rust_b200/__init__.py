@@ -13,4 +13,4 @@ from .scann import Scann, ScannBuilder, ScannConfig, SearchMode  # noqa: F401
 from .searchers import (AsymmetricHasher, AsymmetricHasherConfig, BruteForceSearcher, DistanceMeasure,  # noqa: F401
                         ScalarQuantizedBruteForceSearcher, ScalarQuantizedConfig, TreePartitioner, TreeXHybridConfig,
                         TreeXHybridSearcher, lut16_build, lut16_scan, merge_topk, pq_encode, results_to_lists,
-                        scalar_quantize)
+                        scalar_quantize, tc_scores)

@@ -30,12 +30,12 @@ HOST, DEVICE = 0, 1
 # every symbol include/scann_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "scann_last_error", "scann_version", "scann_device_count",
-    "scann_bf_create", "scann_bf_search", "scann_bf_destroy",
+    "scann_bf_create", "scann_bf_search", "scann_bf_destroy", "scann_bf_path_stats", "scann_sq8_path_stats",
     "scann_sq8_quantize", "scann_sq8_create", "scann_sq8_search", "scann_sq8_destroy",
     "scann_part_create", "scann_part_select", "scann_part_destroy",
     "scann_treeah_create", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
     "scann_treeah_set_profiling", "scann_treeah_get_profile",
-    "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk",
+    "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_tc_scores",
 ]
 
 
@@ -72,6 +72,8 @@ def load():
     L.scann_bf_create.argtypes = [vp, sz, sz, sz, i32, i32, i32, C.POINTER(vp)]
     L.scann_bf_search.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, i32, vp]
     L.scann_bf_destroy.argtypes = [vp]
+    L.scann_bf_path_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.scann_sq8_path_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.scann_bf_destroy.restype = None
     L.scann_sq8_quantize.argtypes = [vp, sz, sz, sz, vp, vp, i32, i32]
     L.scann_sq8_create.argtypes = [vp, sz, sz, f32, i32, i32, i32, C.POINTER(vp)]
@@ -94,6 +96,7 @@ def load():
     L.scann_lut16_scan.argtypes = [vp, sz, sz, vp, vp, i32, i32]
     L.scann_pq_encode.argtypes = [vp, sz, sz, vp, sz, sz, vp, vp, vp, i32, i32]
     L.scann_merge_topk.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, i32, i32, vp]
+    L.scann_tc_scores.argtypes = [vp, sz, sz, vp, i32, sz, sz, f32, i32, vp, vp, vp, sz, vp, i32]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("scann_last_error", "scann_version") and not name.endswith("_destroy"):

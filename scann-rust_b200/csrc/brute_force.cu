@@ -12,8 +12,17 @@
 //   3. rescore_topk_kernel exact distance of the kc candidates in the reference's AVX2+FMA order
 //                          (bit-identical floats), final order (distance, id), top-k   (select.cu)
 // The GEMM scores only rank candidates; every distance that is returned comes from step 3.
-// Round-1 note: step 1 runs on the CUDA cores; the tcgen05/TMA version of the contraction replaces this
-// kernel only (same tile buffer, same epilogue).
+//
+// Default path for dim <= 256 — tensor cores (tc_gemm.cu: tcgen05.mma bf16, TMEM accumulators, TMA operands):
+//   a. DENSE scores v = hx - q~.x~ of a strided sample of <= 16384 rows; per query the k-th smallest v_k (an
+//      upper bound of the k-th best over all rows).
+//   b. thr[q] = v_k + 2*eps_q, eps_q = a rigorous bound on |v - exact| (bf16 operand rounding: 2^-8 |q| max|x|,
+//      plus f32 accumulation slack).  Any row with v > thr is beaten by the k sample rows whatever the
+//      rounding did, so it cannot be among the exact top-k.
+//   c. FILTER pass over all rows appends the rows with v <= thr to per-query lists (a few hundred to ~1-2k).
+//   d. rescore_lists_kernel: exact distances of the list in the reference's AVX2 order, (distance, id) order.
+// Results are therefore the exact top-k by the reference's own f32 distances, not "top-k up to GEMM rounding".
+// A list overflow (cap 4096: huge k, or massively duplicated rows) sends that query chunk through steps 1-3.
 #include <string.h>
 
 #include <algorithm>
@@ -200,6 +209,34 @@ __global__ void state_to_cand_kernel(const uint64_t* __restrict__ state, size_t 
   cand[i] = k == ~0ull ? 0xFFFFFFFFu : static_cast<uint32_t>(k & 0xFFFFFFFFu);
 }
 
+
+// thr[q] = (k-th smallest sample score) + 2*eps_q (see the file header).  state: [nq][kc] ascending keys from
+// bf_select_kernel; qn = |q|^2; xmax2 = max_r |x_r|^2 of the values the exact kernels see.
+__global__ void bf_thr_kernel(const uint64_t* __restrict__ state, int kc, const float* __restrict__ qn, float xmax2,
+                              size_t nq, float* __restrict__ thr) {
+  const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const uint64_t key = state[q * kc + (kc - 1)];
+  const float inf = __int_as_float(0x7F800000);
+  float vk = key == ~0ull ? inf : key_f32(static_cast<uint32_t>(key >> 32));
+  const float nqr = sqrtf(qn[q]), nx = sqrtf(xmax2);
+  // bf16 RN: |q~.x~ - q.x| <= (2^-8 + 2^-18) sum|q_j x_j| <= 1.001 * 2^-8 |q||x|; the second term covers the f32
+  // accumulation of the tensor core, of hx and of the reference's own AVX2 sum (all <= ~dim * 2^-23 relative)
+  const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+  float t = vk + 2.0f * eps;
+  t = t + fabsf(t) * 1e-6f;
+  thr[q] = (t == t) ? t : inf;  // NaN anywhere -> keep everything (overflows into the exact legacy path)
+}
+
+__global__ void bf_overflow_kernel(const uint32_t* __restrict__ cnt, size_t nq, uint32_t cap, uint32_t* flag) {
+  const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q < nq && cnt[q] > cap) atomicOr(flag, 1u);
+}
+
+constexpr size_t kTcQTile = 4096;      // queries per tensor-core chunk
+constexpr size_t kTcSampleTiles = 128; // 128-row tiles in the threshold sample (16384 rows)
+constexpr size_t kTcCap = 4096;        // candidate list capacity per query
+
 struct BfCore {
   int device = 0;
   size_t n = 0, dim = 0, dim_pad = 0, n_pad = 0;
@@ -209,6 +246,14 @@ struct BfCore {
   DevBuf<float> rows_f;   // [n_pad][dim_pad]
   DevBuf<int8_t> rows_i;  // [n_pad][dim_pad]
   DevBuf<float> xn;       // [n_pad]
+  // tensor-core ranking operands (tc_gemm.cu)
+  bool tc = false;
+  DevBuf<uint16_t> rows_bf;  // [tc_rows_pad(n)][tc_kpad(dim)] bf16
+  DevBuf<float> hx;          // [tc_rows_pad(n)]
+  DevBuf<float> d_small;     // [0] max |x|^2, [1] overflow flag (as u32)
+  float xmax2 = 0.0f;
+  uint32_t* h_flag = nullptr;  // pinned
+  uint64_t stat_tc_chunks = 0, stat_legacy_chunks = 0;
   Workspace ws;
   std::mutex mu;
   cudaStream_t stream = nullptr;
@@ -250,6 +295,154 @@ struct BfCore {
       SCANN_CUDA(cudaGetLastError());
       SCANN_CUDA(cudaStreamSynchronize(stream));
     }
+    const char* no_tc = getenv("SCANN_BF_NO_TC");
+    if (tc_supported(dim) && !(no_tc && no_tc[0] == '1')) {
+      const size_t kpad = tc_kpad(dim), rpad = tc_rows_pad(n);
+      SCANN_TRY(rows_bf.alloc(rpad * kpad));
+      SCANN_TRY(hx.alloc(rpad));
+      SCANN_TRY(d_small.alloc(2));
+      SCANN_TRY(tc_prepare_rows(i8 ? static_cast<const void*>(rows_i.p) : static_cast<const void*>(rows_f.p), i8, n,
+                                dim, dim_pad, scale, measure != SCANN_DOT, rows_bf.p, hx.p, d_small.p, stream));
+      SCANN_CUDA(cudaMemcpyAsync(&xmax2, d_small.p, sizeof(float), cudaMemcpyDeviceToHost, stream));
+      SCANN_CUDA(cudaStreamSynchronize(stream));
+      SCANN_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_flag), sizeof(uint32_t)));
+      tc = true;
+    }
+    return SCANN_OK;
+  }
+
+  // ---- legacy CUDA-core chunk (dim > 256, list overflow, SCANN_BF_NO_TC=1): steps 1-3 of the file header ----
+  // qsrc: device queries [nqc][dim]; writes device outputs oid/od [nqc][k], oc [nqc]
+  scann_status legacy_chunk(const float* qsrc, size_t nqc, size_t k, size_t kc, uint32_t* oid, float* od, uint32_t* oc,
+                            cudaStream_t s) {
+    const size_t qt = std::min<size_t>(kQTile, (nqc + kBM - 1) / kBM * kBM);
+    const size_t nt = std::min<size_t>(kNTile, n_pad);
+    float* Apad = ws.take<float>(qt * dim_pad);
+    float* qn = ws.take<float>(qt);
+    float* scores = ws.take<float>(qt * nt);
+    uint64_t* state = ws.take<uint64_t>(qt * kc);
+    uint32_t* cand = ws.take<uint32_t>(qt * kc);
+    const int p2 = next_pow2(static_cast<int>(kc));
+    const size_t sel_smem = (kc + kBfChunk + p2) * 8 + 264 * 4;
+    SCANN_CUDA(cudaFuncSetAttribute(bf_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sel_smem)));
+    for (size_t q0 = 0; q0 < nqc; q0 += qt) {
+      const size_t nq1 = std::min(qt, nqc - q0);
+      const size_t rows_pad = (nq1 + kBM - 1) / kBM * kBM;
+      const float* q1 = qsrc + q0 * dim;
+      pad_queries_kernel<<<static_cast<unsigned>((rows_pad + 7) / 8), 256, 0, s>>>(q1, nq1, dim, dim_pad, rows_pad,
+                                                                                   Apad, qn);
+      for (size_t r0 = 0; r0 < n; r0 += nt) {
+        const size_t ncols = std::min(nt, n - r0);
+        const size_t cols_pad = (ncols + kBN - 1) / kBN * kBN;
+        dim3 grid(static_cast<unsigned>(cols_pad / kBN), static_cast<unsigned>(rows_pad / kBM));
+        if (i8)
+          bf_gemm_kernel<true><<<grid, 256, 0, s>>>(Apad, rows_i.p + r0 * dim_pad, static_cast<int>(dim_pad), qn,
+                                                    xn.p + r0, scale, measure, scores, static_cast<int>(nt));
+        else
+          bf_gemm_kernel<false><<<grid, 256, 0, s>>>(Apad, rows_f.p + r0 * dim_pad, static_cast<int>(dim_pad), qn,
+                                                     xn.p + r0, 1.0f, measure, scores, static_cast<int>(nt));
+        const int have = static_cast<int>(std::min(kc, r0));
+        bf_select_kernel<<<static_cast<unsigned>(nq1), 256, sel_smem, s>>>(scores, static_cast<int>(nt),
+                                                                           static_cast<int>(ncols),
+                                                                           static_cast<uint32_t>(r0), state, have,
+                                                                           static_cast<int>(kc));
+      }
+      SCANN_CUDA(cudaGetLastError());
+      state_to_cand_kernel<<<static_cast<unsigned>((nq1 * kc + 255) / 256), 256, 0, s>>>(state, nq1 * kc, cand);
+      SCANN_TRY(launch_rescore_topk(rescore_params(q1), cand, nq1, kc, k, oid + q0 * k, od + q0 * k, oc + q0, s));
+    }
+    ++stat_legacy_chunks;
+    return SCANN_OK;
+  }
+  size_t legacy_need(size_t nqc, size_t kc) const {
+    const size_t qt = std::min<size_t>(kQTile, (nqc + kBM - 1) / kBM * kBM);
+    const size_t nt = std::min<size_t>(kNTile, n_pad);
+    return Workspace::padded(qt * dim_pad * 4) + Workspace::padded(qt * 4) + Workspace::padded(qt * nt * 4) +
+           Workspace::padded(qt * kc * 8) + Workspace::padded(qt * kc * 4);
+  }
+
+  RescoreParams rescore_params(const float* q) const {
+    RescoreParams rp;
+    rp.queries = q;
+    rp.dim = dim;
+    rp.raw = i8 ? nullptr : rows_f.p;
+    rp.raw_i8 = i8 ? rows_i.p : nullptr;
+    rp.scale = scale;
+    rp.stride = dim_pad;
+    rp.measure = measure;
+    return rp;
+  }
+
+  // ---- tensor-core chunk: steps a-d of the file header.  *overflow = 1 when some list overflowed (outputs are then
+  // not written and the caller runs legacy_chunk).  Synchronises the stream (the overflow flag is read on the host).
+  size_t tc_sample_tiles() const { return std::min<size_t>(kTcSampleTiles, tc_rows_pad(n) / 128); }
+  size_t tc_need(size_t nqc, size_t kk) const {
+    const size_t qpad = tc_queries_pad(nqc, dim);
+    return Workspace::padded(qpad * tc_kpad(dim) * 2) + Workspace::padded(qpad * 4) +
+           Workspace::padded(nqc * tc_sample_tiles() * 128 * 4) + Workspace::padded(nqc * kk * 8) +
+           Workspace::padded(nqc * 4) * 2 + Workspace::padded(nqc * kTcCap * 8);
+  }
+  scann_status tc_chunk(const float* qsrc, size_t nqc, size_t k, size_t kk, uint32_t* oid, float* od, uint32_t* oc,
+                        cudaStream_t s, bool* overflow) {
+    const size_t kpad = tc_kpad(dim), qpad = tc_queries_pad(nqc, dim), rpad = tc_rows_pad(n);
+    const size_t tiles = rpad / 128, stiles = tc_sample_tiles(), scols = stiles * 128;
+    uint16_t* qbf = ws.take<uint16_t>(qpad * kpad);
+    float* qn = ws.take<float>(qpad);
+    float* dense = ws.take<float>(nqc * scols);
+    uint64_t* state = ws.take<uint64_t>(nqc * kk);
+    float* thr = ws.take<float>(nqc);
+    uint32_t* cnt = ws.take<uint32_t>(nqc);
+    unsigned long long* lists = ws.take<unsigned long long>(nqc * kTcCap);
+    uint32_t* flag = reinterpret_cast<uint32_t*>(d_small.p + 1);
+    SCANN_TRY(tc_prepare_queries(qsrc, nqc, dim, i8 ? scale : 1.0f, qbf, qn, s));
+    TcScoreParams p;
+    p.q_bf16 = qbf;
+    p.nq = nqc;
+    p.dim = dim;
+    p.rows_bf16 = rows_bf.p;
+    p.rows_pad_total = rpad;
+    p.hx = hx.p;
+    p.row0 = 0;
+    p.nrows = scols;
+    p.tile_stride = tiles / stiles;  // >= 1; the sample is every tile_stride-th 128-row tile
+    p.filter = false;
+    p.dense = dense;
+    p.ld = scols;
+    p.thr = nullptr;
+    p.cand = nullptr;
+    p.cap = kTcCap;
+    p.cand_cnt = nullptr;
+    p.sms = sm_count(device);
+    SCANN_TRY(launch_tc_scores(p, s));  // a. sample scores
+    {
+      const int p2 = next_pow2(static_cast<int>(kk));
+      const size_t sel_smem = (kk + kBfChunk + p2) * 8 + 264 * 4;
+      SCANN_CUDA(cudaFuncSetAttribute(bf_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(sel_smem)));
+      bf_select_kernel<<<static_cast<unsigned>(nqc), 256, sel_smem, s>>>(dense, static_cast<int>(scols),
+                                                                         static_cast<int>(scols), 0u, state, 0,
+                                                                         static_cast<int>(kk));
+      bf_thr_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(state, static_cast<int>(kk), qn, xmax2,
+                                                                             nqc, thr);  // b. certified threshold
+    }
+    SCANN_CUDA(cudaMemsetAsync(cnt, 0, nqc * 4, s));
+    SCANN_CUDA(cudaMemsetAsync(flag, 0, 4, s));
+    p.nrows = rpad;
+    p.tile_stride = 1;
+    p.filter = true;
+    p.dense = nullptr;
+    p.thr = thr;
+    p.cand = lists;
+    p.cand_cnt = cnt;
+    SCANN_TRY(launch_tc_scores(p, s));  // c. all rows, survivors into the lists
+    bf_overflow_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(cnt, nqc, kTcCap, flag);
+    SCANN_CUDA(cudaMemcpyAsync(h_flag, flag, 4, cudaMemcpyDeviceToHost, s));
+    // d. exact re-score (harmless if a list overflowed: the outputs are rewritten by the legacy chunk)
+    SCANN_TRY(launch_rescore_lists(rescore_params(qsrc), lists, cnt, nqc, kTcCap, k, n, oid, od, oc, s));
+    SCANN_CUDA(cudaStreamSynchronize(s));
+    *overflow = *h_flag != 0;
+    if (!*overflow) ++stat_tc_chunks;
     return SCANN_OK;
   }
 
@@ -271,75 +464,48 @@ struct BfCore {
                   "Query dimensionality %zu does not match dataset dimensionality %zu", qdim, dim);
     SCANN_REQUIRE(k >= 1 && ids && dists, SCANN_INVALID_ARGUMENT, "k must be >= 1 and outputs non-NULL");
     const size_t kk = std::min(k, n);                  // k clamped to n (searcher.rs:91)
-    const size_t kc = std::min(n, kk + kBfMargin);     // candidates carried per query
+    const size_t kc = std::min(n, kk + kBfMargin);     // candidates carried per query (legacy path)
     SCANN_REQUIRE(kc <= 2048, SCANN_INVALID_ARGUMENT, "k = %zu too large (max %d)", k, 2048 - kBfMargin);
-    const size_t qt = std::min<size_t>(kQTile, (nq + kBM - 1) / kBM * kBM);
-    const size_t nt = std::min<size_t>(kNTile, n_pad);
-
-    size_t need = Workspace::padded(qt * dim_pad * 4) + Workspace::padded(qt * 4) + Workspace::padded(qt * nt * 4) +
-                  Workspace::padded(qt * kc * 8) + Workspace::padded(qt * kc * 4) + 4096;
+    // tensor cores when the expected list length (k scaled from the sample to all rows) leaves head-room in the lists
+    const bool use_tc = tc && static_cast<double>(kk) * static_cast<double>(tc_rows_pad(n)) /
+                                      static_cast<double>(tc_sample_tiles() * 128) <= kTcCap / 2;
+    const size_t chunk = std::min<size_t>(use_tc ? kTcQTile : kQTile, nq);
+    size_t need = legacy_need(chunk, kc);
+    if (use_tc) need = std::max(need, tc_need(chunk, kk));
     if (host)
-      need += Workspace::padded(qt * dim * 4) + 2 * Workspace::padded(qt * k * 4) + Workspace::padded(qt * 4);
+      need += Workspace::padded(chunk * dim * 4) + 2 * Workspace::padded(chunk * k * 4) + Workspace::padded(chunk * 4);
+    need += 4096;
     SCANN_TRY(ws.reserve(need));
-    float* Apad = ws.take<float>(qt * dim_pad);
-    float* qn = ws.take<float>(qt);
-    float* scores = ws.take<float>(qt * nt);
-    uint64_t* state = ws.take<uint64_t>(qt * kc);
-    uint32_t* cand = ws.take<uint32_t>(qt * kc);
     float* hq = nullptr;
     uint32_t *hids = nullptr, *hcounts = nullptr;
     float* hd = nullptr;
     if (host) {
-      hq = ws.take<float>(qt * dim);
-      hids = ws.take<uint32_t>(qt * k);
-      hd = ws.take<float>(qt * k);
-      hcounts = ws.take<uint32_t>(qt);
+      hq = ws.take<float>(chunk * dim);
+      hids = ws.take<uint32_t>(chunk * k);
+      hd = ws.take<float>(chunk * k);
+      hcounts = ws.take<uint32_t>(chunk);
     }
-    const int p2 = next_pow2(static_cast<int>(kc));
-    const size_t sel_smem = (kc + kBfChunk + p2) * 8 + 264 * 4;
-    SCANN_CUDA(cudaFuncSetAttribute(bf_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sel_smem)));
+    const size_t ws_mark = ws.used;
 
-    for (size_t q0 = 0; q0 < nq; q0 += qt) {
-      const size_t nqc = std::min(qt, nq - q0);
-      const size_t rows_pad = (nqc + kBM - 1) / kBM * kBM;
+    for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+      const size_t nqc = std::min(chunk, nq - q0);
       const float* qsrc = queries + q0 * dim;
       if (host) {
         SCANN_CUDA(cudaMemcpyAsync(hq, qsrc, nqc * dim * 4, cudaMemcpyHostToDevice, s));
         qsrc = hq;
       }
-      pad_queries_kernel<<<static_cast<unsigned>((rows_pad + 7) / 8), 256, 0, s>>>(qsrc, nqc, dim, dim_pad, rows_pad,
-                                                                                   Apad, qn);
-      for (size_t r0 = 0; r0 < n; r0 += nt) {
-        const size_t ncols = std::min(nt, n - r0);
-        const size_t cols_pad = (ncols + kBN - 1) / kBN * kBN;
-        dim3 grid(static_cast<unsigned>(cols_pad / kBN), static_cast<unsigned>(rows_pad / kBM));
-        if (i8)
-          bf_gemm_kernel<true><<<grid, 256, 0, s>>>(Apad, rows_i.p + r0 * dim_pad, static_cast<int>(dim_pad), qn,
-                                                    xn.p + r0, scale, measure, scores, static_cast<int>(nt));
-        else
-          bf_gemm_kernel<false><<<grid, 256, 0, s>>>(Apad, rows_f.p + r0 * dim_pad, static_cast<int>(dim_pad), qn,
-                                                     xn.p + r0, 1.0f, measure, scores, static_cast<int>(nt));
-        const int have = static_cast<int>(std::min(kc, r0));
-        bf_select_kernel<<<static_cast<unsigned>(nqc), 256, sel_smem, s>>>(scores, static_cast<int>(nt),
-                                                                           static_cast<int>(ncols),
-                                                                           static_cast<uint32_t>(r0), state, have,
-                                                                           static_cast<int>(kc));
-      }
-      SCANN_CUDA(cudaGetLastError());
-      state_to_cand_kernel<<<static_cast<unsigned>((nqc * kc + 255) / 256), 256, 0, s>>>(state, nqc * kc, cand);
-      RescoreParams rp;
-      rp.queries = qsrc;
-      rp.dim = dim;
-      rp.raw = i8 ? nullptr : rows_f.p;
-      rp.raw_i8 = i8 ? rows_i.p : nullptr;
-      rp.scale = scale;
-      rp.stride = dim_pad;
-      rp.measure = measure;
       uint32_t* oid = host ? hids : ids + q0 * k;
       float* od = host ? hd : dists + q0 * k;
       uint32_t* oc = host ? hcounts : counts + q0;
-      SCANN_TRY(launch_rescore_topk(rp, cand, nqc, kc, k, oid, od, oc, s));
+      bool overflow = true;
+      if (use_tc) {
+        ws.used = ws_mark;
+        SCANN_TRY(tc_chunk(qsrc, nqc, k, kk, oid, od, oc, s, &overflow));
+      }
+      if (overflow) {
+        ws.used = ws_mark;
+        SCANN_TRY(legacy_chunk(qsrc, nqc, k, kc, oid, od, oc, s));
+      }
       if (host) {
         SCANN_CUDA(cudaMemcpyAsync(ids + q0 * k, hids, nqc * k * 4, cudaMemcpyDeviceToHost, s));
         SCANN_CUDA(cudaMemcpyAsync(dists + q0 * k, hd, nqc * k * 4, cudaMemcpyDeviceToHost, s));
@@ -357,6 +523,11 @@ struct BfCore {
     rows_f.free_();
     rows_i.free_();
     xn.free_();
+    rows_bf.free_();
+    hx.free_();
+    d_small.free_();
+    if (h_flag) cudaFreeHost(h_flag);
+    h_flag = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -463,6 +634,15 @@ scann_status scann_bf_search(scann_bf* h, const float* queries, size_t nq, size_
   return h->core.search(queries, nq, qdim, k, ids, dists, counts, memspace, stream);
 }
 
+scann_status scann_bf_path_stats(scann_bf* h, uint64_t* tc_chunks, uint64_t* legacy_chunks) {
+  using namespace scann;
+  SCANN_REQUIRE(h && tc_chunks && legacy_chunks, SCANN_INVALID_ARGUMENT, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->core.mu);
+  *tc_chunks = h->core.stat_tc_chunks;
+  *legacy_chunks = h->core.stat_legacy_chunks;
+  return SCANN_OK;
+}
+
 void scann_bf_destroy(scann_bf* h) {
   if (!h) return;
   h->core.destroy();
@@ -495,6 +675,15 @@ scann_status scann_sq8_search(scann_sq8* h, const float* queries, size_t nq, siz
                               float* dists, uint32_t* counts, int memspace, void* stream) {
   SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
   return h->core.search(queries, nq, qdim, k, ids, dists, counts, memspace, stream);
+}
+
+scann_status scann_sq8_path_stats(scann_sq8* h, uint64_t* tc_chunks, uint64_t* legacy_chunks) {
+  using namespace scann;
+  SCANN_REQUIRE(h && tc_chunks && legacy_chunks, SCANN_INVALID_ARGUMENT, "NULL argument");
+  std::lock_guard<std::mutex> lock(h->core.mu);
+  *tc_chunks = h->core.stat_tc_chunks;
+  *legacy_chunks = h->core.stat_legacy_chunks;
+  return SCANN_OK;
 }
 
 void scann_sq8_destroy(scann_sq8* h) {

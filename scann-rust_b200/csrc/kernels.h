@@ -15,6 +15,10 @@ void launch_transpose(const float* in, size_t rows, size_t cols, float* out, cud
 //   cand: [nq][kc] candidate row ids (0xFFFFFFFF = empty); writes ids/dists [nq][k], counts [nq]
 scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, size_t nq, size_t kc, size_t k,
                                  uint32_t* ids, float* dists, uint32_t* counts, cudaStream_t s);
+//   lists: [nq][cap] (key << 32 | row) entries, cnt [nq] entries appended (clamped to cap); rows >= n_rows ignored
+scann_status launch_rescore_lists(const RescoreParams& rp, const unsigned long long* lists, const uint32_t* cnt,
+                                  size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
+                                  uint32_t* counts, cudaStream_t s);
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
                                uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s);
 
@@ -26,8 +30,9 @@ struct TcScoreParams {
   size_t rows_pad_total;
   const float* hx;           // [rows_pad_total]
   size_t row0, nrows;        // rows [row0, row0 + nrows) of this launch; row0 % 128 == 0
+  size_t tile_stride = 1;    // > 1: a sample — the t-th 128-row tile starts at row0 + t * tile_stride * 128
   bool filter;               // false: dense scores, true: threshold filter into candidate lists
-  float* dense;              // [nq][ld], column = row - row0 (columns up to the next multiple of 128 are written)
+  float* dense;              // [nq][ld], column = t * 128 + (row inside tile t); whole tiles are written
   size_t ld;
   const float* thr;          // [nq]
   unsigned long long* cand;  // [nq][cap]  (f32_key(v) << 32 | row)

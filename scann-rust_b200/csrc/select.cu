@@ -77,6 +77,77 @@ scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, 
   return SCANN_OK;
 }
 
+// Variable-length variant for the tensor-core ranking path (tc_gemm.cu FILTER lists): lists[q][0 .. min(cnt[q], cap))
+// hold (key << 32 | row) entries in arbitrary order; only the row id is used.  Same exact distances, same
+// (distance, id) order, first k written.  One CTA per query; the sort is sized to this query's list.
+template <bool I8>
+__global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams rp,
+                                                            const unsigned long long* __restrict__ lists,
+                                                            const uint32_t* __restrict__ cnt, int cap, int k,
+                                                            uint32_t n_rows, uint32_t* __restrict__ ids,
+                                                            float* __restrict__ dists,
+                                                            uint32_t* __restrict__ counts) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int tid = threadIdx.x;
+  const size_t q = blockIdx.x;
+  const int c = static_cast<int>(min(cnt[q], static_cast<uint32_t>(cap)));
+  const int p2 = next_pow2(c < 1 ? 1 : c);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                              // [next_pow2(cap)]
+  float* qs = reinterpret_cast<float*>(keys + next_pow2(cap < 1 ? 1 : cap));   // [dim]
+  const int dim = static_cast<int>(rp.dim);
+  for (int d = tid; d < dim; d += 256) qs[d] = rp.queries[q * rp.dim + d];
+  for (int j = tid; j < p2; j += 256) keys[j] = ~0ull;
+  __syncthreads();
+  const unsigned long long* lq = lists + q * static_cast<size_t>(cap);
+  const int grp = tid >> 3, sub = tid & 7;
+  for (int j0 = 0; j0 < c; j0 += 32) {
+    const int j = j0 + grp;
+    uint32_t id = j < c ? static_cast<uint32_t>(lq[j] & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+    const bool valid = id < n_rows;  // padding rows of the operand tiles can enter a list when thr = +inf
+    if (!valid) id = 0;
+    const void* row = I8 ? static_cast<const void*>(rp.raw_i8 + static_cast<size_t>(id) * rp.stride)
+                         : static_cast<const void*>(rp.raw + static_cast<size_t>(id) * rp.stride);
+    const float d = exact_pair_distance<I8>(qs, row, dim, rp.measure, rp.scale, sub);
+    if (valid && sub == 0) keys[j] = (static_cast<uint64_t>(f32_key(d)) << 32) | id;
+  }
+  __syncthreads();
+  block_bitonic_sort<256>(keys, p2);
+  for (int j = tid; j < k; j += 256) {
+    const uint64_t key = j < p2 ? keys[j] : ~0ull;
+    const bool ok = key != ~0ull;
+    ids[q * k + j] = ok ? static_cast<uint32_t>(key & 0xFFFFFFFFu) : 0xFFFFFFFFu;
+    dists[q * k + j] = ok ? key_f32(static_cast<uint32_t>(key >> 32)) : __int_as_float(0x7F800000);
+  }
+  if (tid == 0) {
+    int m = 0;
+    const int lim = k < p2 ? k : p2;
+    for (int j = 0; j < lim; ++j)
+      if (keys[j] != ~0ull) ++m;
+    counts[q] = static_cast<uint32_t>(m);
+  }
+}
+
+scann_status launch_rescore_lists(const RescoreParams& rp, const unsigned long long* lists, const uint32_t* cnt,
+                                  size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
+                                  uint32_t* counts, cudaStream_t s) {
+  if (nq == 0) return SCANN_OK;
+  SCANN_REQUIRE(cap >= 1 && cap <= 8192, SCANN_INVALID_ARGUMENT, "candidate list capacity %zu out of range", cap);
+  const size_t smem = static_cast<size_t>(next_pow2(static_cast<int>(cap))) * 8 + rp.dim * 4 + 16;
+  if (rp.raw_i8) {
+    SCANN_CUDA(cudaFuncSetAttribute(rescore_lists_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+    rescore_lists_kernel<true><<<static_cast<unsigned>(nq), 256, smem, s>>>(
+        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), ids, dists, counts);
+  } else {
+    SCANN_CUDA(cudaFuncSetAttribute(rescore_lists_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+    rescore_lists_kernel<false><<<static_cast<unsigned>(nq), 256, smem, s>>>(
+        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), ids, dists, counts);
+  }
+  SCANN_CUDA(cudaGetLastError());
+  return SCANN_OK;
+}
+
 // ---- multi-GPU merge: [parts][nq][k] -> [nq][k] by (distance, id) -----------------
 __global__ void __launch_bounds__(128) merge_topk_kernel(const uint32_t* __restrict__ ids_in,
                                                          const float* __restrict__ dists_in, int parts, size_t nq,

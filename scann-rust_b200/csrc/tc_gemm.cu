@@ -116,6 +116,7 @@ struct TcArgs {
   uint32_t q_tiles;         // query super-tiles of MT * 128
   uint32_t row0;            // first row of this launch (multiple of 128)
   uint32_t n_tiles;         // 128-row tiles in this launch
+  uint32_t tile_stride;     // tile t covers rows row0 + t * tile_stride * 128 .. + 128 (1 = contiguous; > 1 = sample)
   uint32_t tiles_per_unit;  // row tiles per work unit
   uint32_t n_units;         // ceil(n_tiles / tiles_per_unit)
   const float* hx;          // [>= row0 + n_tiles * 128]
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           mbar_expect_tx(bar(kFull + stage), KA * kTcAtomBytes);
           for (int ka = 0; ka < KA; ++ka)
             tma_load_2d(smem_u32(sB + (stage * KA + ka) * kTcAtomBytes), &tmB, bar(kFull + stage), ka * kTcAtomK,
-                        static_cast<int>(a.row0 + t * kTcBN));
+                        static_cast<int>(a.row0 + t * a.tile_stride * kTcBN));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -264,7 +265,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       for (uint32_t t = t0; t < t1; ++t) {
         mbar_wait(bar(kTFull + as), asphase);
         tc_fence_after();
-        const uint32_t row_tile = a.row0 + t * kTcBN + c0;  // first row of this warp's columns
+        const uint32_t row_tile = a.row0 + t * a.tile_stride * kTcBN + c0;  // first row of this warp's columns
+        const uint32_t col_tile = t * kTcBN + c0;                            // DENSE output column of that row
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (as * MT + mt) * kTcBN + c0;
         for (int cc = 0; cc < ncols; cc += 32) {
           uint32_t vr[32];
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           for (int j = 0; j < 32; ++j) v[j] = __fsub_rn(h[j], __uint_as_float(vr[j]));
           if (!a.filter) {
             if (qvalid) {
-              float4* o = reinterpret_cast<float4*>(a.dense + static_cast<size_t>(q) * a.ld + (row_tile - a.row0) + cc);
+              float4* o = reinterpret_cast<float4*>(a.dense + static_cast<size_t>(q) * a.ld + col_tile + cc);
 #pragma unroll
               for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
@@ -476,6 +478,7 @@ scann_status launch_tc_scores(const TcScoreParams& p, cudaStream_t s) {
   a.q_tiles = static_cast<uint32_t>(tc_queries_pad(p.nq, p.dim) / (mt * kTcBM));
   a.row0 = static_cast<uint32_t>(p.row0);
   a.n_tiles = static_cast<uint32_t>((p.nrows + kTcBN - 1) / kTcBN);
+  a.tile_stride = static_cast<uint32_t>(p.tile_stride < 1 ? 1 : p.tile_stride);
   // enough units to fill the machine a few times over, but runs long enough to amortise the A load
   uint32_t want_units = static_cast<uint32_t>(std::max(1, 4 * p.sms / static_cast<int>(a.q_tiles)));
   uint32_t tpu = (a.n_tiles + want_units - 1) / want_units;
@@ -499,3 +502,73 @@ scann_status launch_tc_scores(const TcScoreParams& p, cudaStream_t s) {
 }
 
 }  // namespace scann
+
+// ------------------------------------------------------------------------------------------ C ABI (parity tap)
+extern "C" {
+
+scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const void* rows, int rows_i8, size_t n,
+                             size_t stride, float scale, int want_norm, const float* thr, float* dense,
+                             uint64_t* cand, size_t cap, uint32_t* cand_cnt, int device) {
+  using namespace scann;
+  SCANN_REQUIRE(queries && rows && nq > 0 && n > 0 && dim > 0 && stride >= dim, SCANN_INVALID_ARGUMENT, "bad arguments");
+  SCANN_REQUIRE(thr ? (cand && cand_cnt && cap > 0) : dense != nullptr, SCANN_INVALID_ARGUMENT, "missing output");
+  SCANN_REQUIRE(tc_supported(dim), SCANN_INVALID_ARGUMENT, "dimension %zu too large for the tensor-core path", dim);
+  SCANN_TRY(check_device(device));
+  DeviceGuard g(device);
+  const size_t kpad = tc_kpad(dim), rpad = tc_rows_pad(n), qpad = tc_queries_pad(nq, dim);
+  const size_t esz = rows_i8 ? 1 : 4;
+  DevBuf<float> d_q, d_hx, d_qn, d_dense, d_thr;
+  DevBuf<uint8_t> d_rows;
+  DevBuf<uint16_t> d_rb, d_qb;
+  DevBuf<unsigned long long> d_cand;
+  DevBuf<uint32_t> d_cnt;
+  cudaStream_t s = 0;
+  SCANN_TRY(d_q.upload(queries, nq * dim, SCANN_HOST, s));
+  SCANN_TRY(d_rows.upload(static_cast<const uint8_t*>(rows), n * stride * esz, SCANN_HOST, s));
+  SCANN_TRY(d_rb.alloc(rpad * kpad));
+  SCANN_TRY(d_qb.alloc(qpad * kpad));
+  SCANN_TRY(d_hx.alloc(rpad));
+  SCANN_TRY(d_qn.alloc(qpad));
+  SCANN_TRY(tc_prepare_rows(d_rows.p, rows_i8 != 0, n, dim, stride, scale, want_norm != 0, d_rb.p, d_hx.p, nullptr, s));
+  SCANN_TRY(tc_prepare_queries(d_q.p, nq, dim, rows_i8 ? scale : 1.0f, d_qb.p, d_qn.p, s));
+  TcScoreParams p;
+  p.q_bf16 = d_qb.p;
+  p.nq = nq;
+  p.dim = dim;
+  p.rows_bf16 = d_rb.p;
+  p.rows_pad_total = rpad;
+  p.hx = d_hx.p;
+  p.row0 = 0;
+  p.nrows = n;
+  p.filter = thr != nullptr;
+  p.dense = nullptr;
+  p.ld = rpad;
+  p.thr = nullptr;
+  p.cand = nullptr;
+  p.cap = cap;
+  p.cand_cnt = nullptr;
+  p.sms = sm_count(device);
+  if (thr) {
+    SCANN_TRY(d_thr.upload(thr, nq, SCANN_HOST, s));
+    SCANN_TRY(d_cand.alloc(nq * cap));
+    SCANN_TRY(d_cnt.alloc(nq));
+    SCANN_CUDA(cudaMemsetAsync(d_cnt.p, 0, nq * 4, s));
+    p.thr = d_thr.p;
+    p.cand = d_cand.p;
+    p.cand_cnt = d_cnt.p;
+  } else {
+    SCANN_TRY(d_dense.alloc(nq * rpad));
+    p.dense = d_dense.p;
+  }
+  SCANN_TRY(launch_tc_scores(p, s));
+  if (thr) {
+    SCANN_CUDA(cudaMemcpyAsync(cand, d_cand.p, nq * cap * 8, cudaMemcpyDeviceToHost, s));
+    SCANN_CUDA(cudaMemcpyAsync(cand_cnt, d_cnt.p, nq * 4, cudaMemcpyDeviceToHost, s));
+  } else {
+    SCANN_CUDA(cudaMemcpy2DAsync(dense, n * 4, d_dense.p, rpad * 4, n * 4, nq, cudaMemcpyDeviceToHost, s));
+  }
+  SCANN_CUDA(cudaStreamSynchronize(s));
+  return SCANN_OK;
+}
+
+}  // extern "C"

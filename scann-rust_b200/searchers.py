@@ -171,6 +171,12 @@ class BruteForceSearcher(_Handle):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
 
+    def path_stats(self):
+        """(query chunks answered by the tcgen05 ranking path, by the CUDA-core path) since construction."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        capi.check(capi.load().scann_bf_path_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
 
 @dataclass
 class ScalarQuantizedConfig:
@@ -253,6 +259,12 @@ class ScalarQuantizedBruteForceSearcher(_Handle):
     def search(self, query, k: int):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
+
+    def path_stats(self):
+        """(query chunks answered by the tcgen05 ranking path, by the CUDA-core path) since construction."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        capi.check(capi.load().scann_sq8_path_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 class TreePartitioner(_Handle):
@@ -504,6 +516,29 @@ def lut16_scan(packed, S: int, lut8, device: int = 0):
     sums = np.empty(n, np.uint32)
     capi.check(capi.load().scann_lut16_scan(capi.np_ptr(pk), n, S, capi.np_ptr(l8), capi.np_ptr(sums), device, capi.HOST))
     return sums
+
+
+def tc_scores(queries, rows, scale: float = 1.0, want_norm: bool = True, thr=None, cap: int = 0, device: int = 0):
+    """Parity tap of the tcgen05 ranking contraction (csrc/tc_gemm.cu): v = hx - bf16(q)·bf16(x).
+    rows f32 or int8 [n, dim]; → dense [nq, n] f32, or with thr [nq]: (cand [nq, cap] u64, counts [nq])."""
+    capi.require_gpu()
+    q = capi.as_f32(queries)
+    i8 = np.asarray(rows).dtype == np.int8
+    r = np.ascontiguousarray(rows, np.int8 if i8 else np.float32)
+    nq, dim = q.shape
+    n, stride = r.shape
+    if thr is None:
+        dense = np.empty((nq, n), np.float32)
+        capi.check(capi.load().scann_tc_scores(capi.np_ptr(q), nq, dim, capi.np_ptr(r), int(i8), n, stride, scale,
+                                               int(want_norm), None, capi.np_ptr(dense), None, 0, None, device))
+        return dense
+    t = capi.as_f32(thr)
+    cand = np.zeros((nq, cap), np.uint64)
+    cnt = np.zeros(nq, np.uint32)
+    capi.check(capi.load().scann_tc_scores(capi.np_ptr(q), nq, dim, capi.np_ptr(r), int(i8), n, stride, scale,
+                                           int(want_norm), capi.np_ptr(t), None, capi.np_ptr(cand), cap,
+                                           capi.np_ptr(cnt), device))
+    return cand, cnt
 
 
 def pq_encode(codebook, x, centers=None, assign=None, device: int = 0):
