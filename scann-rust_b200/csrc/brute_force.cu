@@ -381,7 +381,7 @@ struct BfCore {
     const size_t qpad = tc_queries_pad(nqc, dim);
     return Workspace::padded(qpad * tc_kpad(dim) * 2) + Workspace::padded(qpad * 4) +
            Workspace::padded(nqc * tc_sample_tiles() * 128 * 4) + Workspace::padded(nqc * kk * 8) +
-           Workspace::padded(nqc * 4) * 2 + Workspace::padded(nqc * kTcCap * 8);
+           Workspace::padded(nqc * 4) * 2 + Workspace::padded(nqc * kTcCap * 4);
   }
   scann_status tc_chunk(const float* qsrc, size_t nqc, size_t k, size_t kk, uint32_t* oid, float* od, uint32_t* oc,
                         cudaStream_t s, bool* overflow) {
@@ -393,7 +393,7 @@ struct BfCore {
     uint64_t* state = ws.take<uint64_t>(nqc * kk);
     float* thr = ws.take<float>(nqc);
     uint32_t* cnt = ws.take<uint32_t>(nqc);
-    unsigned long long* lists = ws.take<unsigned long long>(nqc * kTcCap);
+    uint32_t* lists = ws.take<uint32_t>(nqc * kTcCap);
     uint32_t* flag = reinterpret_cast<uint32_t*>(d_small.p + 1);
     SCANN_TRY(tc_prepare_queries(qsrc, nqc, dim, i8 ? scale : 1.0f, qbf, qn, s));
     TcScoreParams p;

@@ -15,8 +15,8 @@ void launch_transpose(const float* in, size_t rows, size_t cols, float* out, cud
 //   cand: [nq][kc] candidate row ids (0xFFFFFFFF = empty); writes ids/dists [nq][k], counts [nq]
 scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, size_t nq, size_t kc, size_t k,
                                  uint32_t* ids, float* dists, uint32_t* counts, cudaStream_t s);
-//   lists: [nq][cap] (key << 32 | row) entries, cnt [nq] entries appended (clamped to cap); rows >= n_rows ignored
-scann_status launch_rescore_lists(const RescoreParams& rp, const unsigned long long* lists, const uint32_t* cnt,
+//   lists: [nq][cap] row ids, cnt [nq] entries appended (clamped to cap); rows >= n_rows ignored
+scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists, const uint32_t* cnt,
                                   size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
                                   uint32_t* counts, cudaStream_t s);
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
@@ -35,7 +35,7 @@ struct TcScoreParams {
   float* dense;              // [nq][ld], column = t * 128 + (row inside tile t); whole tiles are written
   size_t ld;
   const float* thr;          // [nq]
-  unsigned long long* cand;  // [nq][cap]  (f32_key(v) << 32 | row)
+  uint32_t* cand;            // [nq][cap] row ids, arbitrary order
   size_t cap;
   uint32_t* cand_cnt;        // [nq]
   int sms;

@@ -78,11 +78,11 @@ scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, 
 }
 
 // Variable-length variant for the tensor-core ranking path (tc_gemm.cu FILTER lists): lists[q][0 .. min(cnt[q], cap))
-// hold (key << 32 | row) entries in arbitrary order; only the row id is used.  Same exact distances, same
+// hold row ids in arbitrary order.  Same exact distances, same
 // (distance, id) order, first k written.  One CTA per query; the sort is sized to this query's list.
 template <bool I8>
 __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams rp,
-                                                            const unsigned long long* __restrict__ lists,
+                                                            const uint32_t* __restrict__ lists,
                                                             const uint32_t* __restrict__ cnt, int cap, int k,
                                                             uint32_t n_rows, uint32_t* __restrict__ ids,
                                                             float* __restrict__ dists,
@@ -98,11 +98,11 @@ __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams 
   for (int d = tid; d < dim; d += 256) qs[d] = rp.queries[q * rp.dim + d];
   for (int j = tid; j < p2; j += 256) keys[j] = ~0ull;
   __syncthreads();
-  const unsigned long long* lq = lists + q * static_cast<size_t>(cap);
+  const uint32_t* lq = lists + q * static_cast<size_t>(cap);
   const int grp = tid >> 3, sub = tid & 7;
   for (int j0 = 0; j0 < c; j0 += 32) {
     const int j = j0 + grp;
-    uint32_t id = j < c ? static_cast<uint32_t>(lq[j] & 0xFFFFFFFFull) : 0xFFFFFFFFu;
+    uint32_t id = j < c ? lq[j] : 0xFFFFFFFFu;
     const bool valid = id < n_rows;  // padding rows of the operand tiles can enter a list when thr = +inf
     if (!valid) id = 0;
     const void* row = I8 ? static_cast<const void*>(rp.raw_i8 + static_cast<size_t>(id) * rp.stride)
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams 
   }
 }
 
-scann_status launch_rescore_lists(const RescoreParams& rp, const unsigned long long* lists, const uint32_t* cnt,
+scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists, const uint32_t* cnt,
                                   size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
                                   uint32_t* counts, cudaStream_t s) {
   if (nq == 0) return SCANN_OK;

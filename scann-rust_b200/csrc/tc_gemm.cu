@@ -10,19 +10,21 @@
 // callers keep the best k + margin rows by v, re-score those exactly in the reference's own summation order
 // and certify the margin against the bf16 error bound (brute_force.cu); no value computed here is returned.
 //
-// Kernel shape (one persistent CTA per SM, 320 threads):
+// Kernel shape (one persistent CTA per SM, 576 threads):
 //   warp 0      TMA producer   queries -> resident A tiles, rows -> STAGES-deep ring of B tiles
 //                              (cp.async.bulk.tensor.2d, 128-byte swizzle, mbarrier complete_tx)
 //   warp 1      MMA issuer     one elected lane: tcgen05.mma.cta_group::1.kind::f16, M = 128, N = 128, K = 16;
 //                              MT query tiles share every B tile; accumulators double-buffered in TMEM;
 //                              tcgen05.commit releases the B slot and publishes the accumulator
-//   warps 2-9   epilogue       tcgen05.ld 32x32b.x32 (thread = one query row), then either
+//   warps 2-17  epilogue       tcgen05.ld 32x32b.x32 (thread = one query row), then either
 //                              DENSE : v -> out[q][row]                                  (first rows / centroids)
-//                              FILTER: v <= thr[q] -> append (key(v), row) to the query's candidate list
+//                              FILTER: v <= thr[q] -> append the row id to the query's candidate list
 // A work unit is (query super-tile of MT*128 queries, run of row tiles).  Units that run at the same time
 // share the row run, so the rows are read from HBM once and from L2 by the other CTAs.
 #include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -36,9 +38,15 @@ constexpr int kTcBM = 128;       // queries per MMA = TMEM lanes
 constexpr int kTcBN = 128;       // rows per B tile = accumulator columns
 constexpr int kTcAtomK = 64;     // bf16 elements per 128-byte swizzle atom
 constexpr int kTcAtomBytes = kTcBM * 128;  // one (128 rows x 128 B) atom tile
-constexpr int kTcEpiWarps = 8;
+constexpr int kTcEpiWarps = 16;  // 4 per TMEM lane quadrant: the epilogue is latency-bound, warps hide it
 constexpr int kTcThreads = 32 * (2 + kTcEpiWarps);
 constexpr int kTcTmemCols = 512;
+// FILTER staging: every epilogue warp queues its survivors (row, lane) in shared memory and flushes the queue with
+// one global atomic per entry, all lanes at once — a survivor costs a shared-memory atomic instead of a serialised
+// round trip to L2 (at ~1 survivor per 1024 scores nearly every 32x32 chunk has one).
+constexpr int kWqCap = 256;                          // entries per warp queue
+constexpr int kWqStep = 128;                         // most entries one filter step can add (32 lanes x 4 columns)
+constexpr int kWqBytes = kWqCap * 4 + kWqCap + 16;   // rows u32, lanes u8, count u32 (+ pad)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -124,7 +132,7 @@ struct TcArgs {
   float* dense;             // DENSE: [nq][ld], column = row - row0
   size_t ld;
   const float* thr;         // FILTER: [nq] keep v <= thr
-  unsigned long long* cand; // FILTER: [nq][cap] (f32_key(v) << 32 | row)
+  uint32_t* cand;           // FILTER: [nq][cap] row ids in arbitrary order
   uint32_t cap;
   uint32_t* cand_cnt;       // FILTER: [nq] appended (may exceed cap = overflow)
 };
@@ -142,6 +150,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   constexpr int kFull = 0, kEmpty = STAGES, kAFull = 2 * STAGES, kAEmpty = 2 * STAGES + 1, kTFull = 2 * STAGES + 2,
                 kTEmpty = 2 * STAGES + 4, kNumBars = 2 * STAGES + 6;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  uint8_t* wq_base = reinterpret_cast<uint8_t*>(tmem_slot + 4);  // [kTcEpiWarps][kWqBytes]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -249,10 +258,29 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ===================================================================== epilogue warps
     const int e = warp - 2;
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int grp = e >> 2;     // MT = 2: query tile; MT = 1: column half
-    const int mt = MT == 2 ? grp : 0;
-    const int c0 = MT == 2 ? 0 : grp * (kTcBN / 2);
-    const int ncols = MT == 2 ? kTcBN : kTcBN / 2;
+    const int grp = e >> 2;     // 0..3: MT = 2 -> (query tile, column half); MT = 1 -> column quarter
+    const int mt = MT == 2 ? grp >> 1 : 0;
+    constexpr int ncols = MT == 2 ? kTcBN / 2 : kTcBN / 4;
+    const int c0 = (MT == 2 ? (grp & 1) : grp) * ncols;
+    constexpr int nchunks = ncols / 32;
+    uint32_t* const wq_rows = reinterpret_cast<uint32_t*>(wq_base + e * kWqBytes);
+    uint8_t* const wq_lanes = reinterpret_cast<uint8_t*>(wq_rows + kWqCap);
+    volatile uint32_t* const wq_cnt = reinterpret_cast<uint32_t*>(wq_lanes + kWqCap);
+    if (lane == 0) *wq_cnt = 0;
+    __syncwarp();
+    uint32_t qwarp = 0;  // first query of this warp in the current unit
+    auto flush = [&]() {
+      __syncwarp();
+      const uint32_t nw = *wq_cnt;
+      for (uint32_t i = lane; i < nw; i += 32) {
+        const uint32_t qq = qwarp + wq_lanes[i];
+        const uint32_t slot = atomicAdd(a.cand_cnt + qq, 1u);
+        if (slot < a.cap) a.cand[static_cast<size_t>(qq) * a.cap + slot] = wq_rows[i];
+      }
+      __syncwarp();
+      if (lane == 0) *wq_cnt = 0;
+      __syncwarp();
+    };
     uint32_t as = 0, asphase = 0;
     for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const uint32_t qt = u % a.q_tiles, nu = u / a.q_tiles;
@@ -260,15 +288,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint32_t t1 = min(t0 + a.tiles_per_unit, a.n_tiles);
       const uint32_t q = (qt * MT + mt) * kTcBM + quad * 32 + lane;
       const bool qvalid = q < a.nq;
+      qwarp = q - lane;
       float thr = __int_as_float(0xFF800000);  // -inf: nothing passes
       if (a.filter && qvalid) thr = a.thr[q];
       for (uint32_t t = t0; t < t1; ++t) {
+        if (t + 1 < t1 && lane < ncols / 32)  // pull the next tile's hx lines into L1 while this tile is filtered
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a.hx + a.row0 + (t + 1) * a.tile_stride * kTcBN + c0 + lane * 32));
         mbar_wait(bar(kTFull + as), asphase);
         tc_fence_after();
         const uint32_t row_tile = a.row0 + t * a.tile_stride * kTcBN + c0;  // first row of this warp's columns
         const uint32_t col_tile = t * kTcBN + c0;                            // DENSE output column of that row
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (as * MT + mt) * kTcBN + c0;
-        for (int cc = 0; cc < ncols; cc += 32) {
+#pragma unroll 1
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int cc = ch * 32;
           uint32_t vr[32];
           tc_ld32(taddr + cc, vr);
           const float4* h4 = reinterpret_cast<const float4*>(a.hx + row_tile + cc);
@@ -282,6 +315,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             h[4 * j + 3] = x.w;
           }
           tc_wait_ld();
+          if (ch + 1 == nchunks) {
+            // the whole accumulator is in registers: hand it back to the MMA warp before the last chunk's work
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kTEmpty + as));
+          }
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __fsub_rn(h[j], __uint_as_float(vr[j]));
@@ -297,29 +336,33 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               float m = v[8 * g8];
 #pragma unroll
               for (int j = 1; j < 8; ++j) m = fminf(m, v[8 * g8 + j]);
-              if (m <= thr) {
+              const bool hit = m <= thr;
+              if (__any_sync(0xFFFFFFFFu, hit)) {  // warp-uniform: the queue room check and flush are collective
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float x = v[8 * g8 + j];
-                  if (x <= thr) {
-                    const uint32_t slot = atomicAdd(a.cand_cnt + q, 1u);
-                    if (slot < a.cap)
-                      a.cand[static_cast<size_t>(q) * a.cap + slot] =
-                          (static_cast<unsigned long long>(f32_key(x)) << 32) | (row_tile + cc + 8 * g8 + j);
+                for (int h4 = 0; h4 < 2; ++h4) {
+                  if (*wq_cnt > kWqCap - kWqStep) flush();
+                  if (hit) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      if (v[8 * g8 + 4 * h4 + j] <= thr) {
+                        const uint32_t sl = atomicAdd(const_cast<uint32_t*>(wq_cnt), 1u);
+                        wq_rows[sl] = row_tile + cc + 8 * g8 + 4 * h4 + j;
+                        wq_lanes[sl] = static_cast<uint8_t>(lane);
+                      }
+                    }
                   }
+                  __syncwarp();
                 }
               }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kTEmpty + as));
         if (++as == 2) {
           as = 0;
           asphase ^= 1;
         }
       }
+      if (a.filter) flush();  // the queue's lane -> query mapping changes with the unit
     }
   }
 
@@ -413,11 +456,12 @@ scann_status make_map(CUtensorMap* map, const void* base, size_t rows, size_t kp
 
 template <int MT, int KA>
 scann_status launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int sms, cudaStream_t s) {
-  constexpr int kBudget = 220 * 1024;
+  constexpr int kBudget = 225 * 1024 - kTcEpiWarps * kWqBytes;  // operand tiles
   constexpr int kStagesRaw = (kBudget - MT * KA * kTcAtomBytes) / (KA * kTcAtomBytes);
   constexpr int STAGES = kStagesRaw > 6 ? 6 : kStagesRaw;
   static_assert(STAGES >= 2, "operand tiles do not fit");
-  const size_t smem = 1024 + static_cast<size_t>(MT + STAGES) * KA * kTcAtomBytes + (2 * STAGES + 6) * 8 + 16;
+  const size_t smem = 1024 + static_cast<size_t>(MT + STAGES) * KA * kTcAtomBytes + (2 * STAGES + 6) * 8 + 16 +
+                      kTcEpiWarps * kWqBytes;
   auto kern = tc_score_kernel<MT, KA, STAGES>;
   SCANN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const uint32_t total = a.q_tiles * a.n_units;
@@ -508,7 +552,7 @@ extern "C" {
 
 scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const void* rows, int rows_i8, size_t n,
                              size_t stride, float scale, int want_norm, const float* thr, float* dense,
-                             uint64_t* cand, size_t cap, uint32_t* cand_cnt, int device) {
+                             uint32_t* cand, size_t cap, uint32_t* cand_cnt, int device) {
   using namespace scann;
   SCANN_REQUIRE(queries && rows && nq > 0 && n > 0 && dim > 0 && stride >= dim, SCANN_INVALID_ARGUMENT, "bad arguments");
   SCANN_REQUIRE(thr ? (cand && cand_cnt && cap > 0) : dense != nullptr, SCANN_INVALID_ARGUMENT, "missing output");
@@ -520,8 +564,7 @@ scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const 
   DevBuf<float> d_q, d_hx, d_qn, d_dense, d_thr;
   DevBuf<uint8_t> d_rows;
   DevBuf<uint16_t> d_rb, d_qb;
-  DevBuf<unsigned long long> d_cand;
-  DevBuf<uint32_t> d_cnt;
+  DevBuf<uint32_t> d_cand, d_cnt;
   cudaStream_t s = 0;
   SCANN_TRY(d_q.upload(queries, nq * dim, SCANN_HOST, s));
   SCANN_TRY(d_rows.upload(static_cast<const uint8_t*>(rows), n * stride * esz, SCANN_HOST, s));
@@ -562,7 +605,7 @@ scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const 
   }
   SCANN_TRY(launch_tc_scores(p, s));
   if (thr) {
-    SCANN_CUDA(cudaMemcpyAsync(cand, d_cand.p, nq * cap * 8, cudaMemcpyDeviceToHost, s));
+    SCANN_CUDA(cudaMemcpyAsync(cand, d_cand.p, nq * cap * 4, cudaMemcpyDeviceToHost, s));
     SCANN_CUDA(cudaMemcpyAsync(cand_cnt, d_cnt.p, nq * 4, cudaMemcpyDeviceToHost, s));
   } else {
     SCANN_CUDA(cudaMemcpy2DAsync(dense, n * 4, d_dense.p, rpad * 4, n * 4, nq, cudaMemcpyDeviceToHost, s));
