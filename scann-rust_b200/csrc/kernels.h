@@ -9,6 +9,21 @@ namespace scann {
 //   centersT: [dim][K] transposed centres; scratch: [nq][K] f32; tokens [nq][L]; dists [nq][L] or null
 scann_status launch_partition(const float* centersT, size_t K, size_t dim, const float* queries, size_t nq, size_t L,
                               uint32_t* tokens, float* dists, float* scratch, cudaStream_t s);
+// tensor-core variant (tc_gemm.cu scores + exact re-score of the survivors; identical tokens and distances)
+struct PartTc {
+  DevBuf<uint16_t> cbf;  // centres as bf16 [tc_rows_pad(K)][tc_kpad(dim)]
+  DevBuf<float> hx;      // |c|^2 / 2
+  DevBuf<float> small;
+  float cmax2 = 0.0f;    // max |c|^2
+  bool ready = false;
+};
+bool part_tc_usable(size_t K, size_t dim);
+size_t part_tc_scratch_bytes(size_t K, size_t dim, size_t nq);
+scann_status part_tc_prepare(const float* centers /* device [K][dim] */, size_t K, size_t dim, PartTc* out,
+                             cudaStream_t s);
+scann_status launch_partition_tc(const PartTc& tc, const float* centers, size_t K, size_t dim, const float* queries,
+                                 size_t nq, size_t L, uint32_t* tokens, float* dists, void* scratch, int sms,
+                                 cudaStream_t s);
 void launch_transpose(const float* in, size_t rows, size_t cols, float* out, cudaStream_t s);
 
 // select.cu — final exact re-score + (dist, id) order, and the multi-GPU merge

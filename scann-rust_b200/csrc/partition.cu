@@ -12,6 +12,10 @@
 // first L (:206-222).  Stable order by OrderedFloat == ascending (dist, id), so an exact radix select
 // of the L smallest 64-bit keys (f32_key(dist) << 32 | id) followed by a bitonic sort of the winners
 // returns the identical token list.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace scann {
@@ -75,6 +79,278 @@ __global__ void __launch_bounds__(256) part_select_kernel(const float* __restric
   }
 }
 
+// ---- tensor-core centroid scoring (tc_gemm.cu) + exact top-L -------------------------------------------------------
+// The north-star shape of this stage: the query x centroid contraction runs on tcgen05 (bf16 operands, f32 TMEM
+// accumulators) and produces RANKING scores v = |c|^2/2 - q~.c~ = (|q - c|^2 - |q|^2)/2 + rounding.  One warp per query
+// then (1) radix-selects the L-th smallest score v_L, (2) keeps every centre with v <= v_L + 2*eps (eps = rigorous
+// bound on |v - exact|, as in brute_force.cu: any centre outside the set is beaten by L centres inside it), (3) scores
+// the ~L survivors exactly in the reference's sequential un-fused order (tree_partitioner.rs:175-192) and (4) sorts them
+// by (distance, id) = the reference's stable sort.  Tokens and distances are bit-identical to the exact kernel's.
+constexpr int kPtWarps = 4;      // queries per CTA
+constexpr int kPtCap = 512;      // survivors per query held in shared memory (L <= 1024 -> see launch)
+
+__device__ __forceinline__ float exact_center_distance(const float* __restrict__ qs, const float* __restrict__ c,
+                                                       int dim) {
+  float acc = 0.0f;
+  if ((dim & 3) == 0) {
+    const float4* c4 = reinterpret_cast<const float4*>(c);
+    for (int d = 0; d < dim; d += 4) {
+      const float4 x = __ldg(c4 + (d >> 2));
+      float df = __fsub_rn(qs[d], x.x);
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+      df = __fsub_rn(qs[d + 1], x.y);
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+      df = __fsub_rn(qs[d + 2], x.z);
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+      df = __fsub_rn(qs[d + 3], x.w);
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+    }
+  } else {
+    for (int d = 0; d < dim; ++d) {
+      const float df = __fsub_rn(qs[d], __ldg(c + d));
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+    }
+  }
+  return acc;
+}
+
+template <int CAP>
+__global__ void __launch_bounds__(kPtWarps * 32) part_tc_select_kernel(
+    float* __restrict__ dense, int ld, const float* __restrict__ centers, int K, int dim,
+    const float* __restrict__ queries, const float* __restrict__ qn, float cmax2, int nq, int L,
+    uint32_t* __restrict__ tokens, float* __restrict__ dists) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kPtWarps + warp;
+  if (q >= nq) return;
+  const int P2 = CAP;  // power of two
+  uint8_t* base = sm + static_cast<size_t>(warp) * (P2 * 8 + 256 * 4 + P2 * 4 + ((dim + 3) & ~3) * 4);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(base);          // [CAP]
+  uint32_t* hist = reinterpret_cast<uint32_t*>(keys + P2);     // [256]
+  uint32_t* cand = hist + 256;                                 // [CAP]
+  float* qs = reinterpret_cast<float*>(cand + P2);             // [dim]
+  for (int d = lane; d < dim; d += 32) qs[d] = queries[static_cast<size_t>(q) * dim + d];
+  float* row = dense + static_cast<size_t>(q) * ld;
+  const int Leff = L < K ? L : K;
+  const float inf = __int_as_float(0x7F800000);
+
+  // (1) L-th smallest ranking score: 4 x 8-bit radix passes over the row (L2-resident)
+  uint32_t prefix = 0, mask = 0, need = static_cast<uint32_t>(Leff);
+  for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
+    __syncwarp();
+    for (int i = lane; i < K; i += 32) {
+      const uint32_t k = f32_key(row[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    uint32_t h[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = hist[lane * 8 + j];
+      s += h[j];
+    }
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t excl = incl - s;
+    const bool mine = (excl < need) && (need <= incl);
+    uint32_t dg = 0, below = 0;
+    if (mine) {
+      uint32_t run = excl;
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!found && run + h[j] >= need) {
+          dg = lane * 8 + j;
+          below = run;
+          found = true;
+        }
+        if (!found) run += h[j];
+      }
+    }
+    const uint32_t owner = __ffs(__ballot_sync(0xFFFFFFFFu, mine)) - 1;
+    dg = __shfl_sync(0xFFFFFFFFu, dg, owner);
+    below = __shfl_sync(0xFFFFFFFFu, below, owner);
+    need -= below;
+    prefix |= dg << shift;
+    mask |= 0xFFu << shift;
+    __syncwarp();
+  }
+  // (2) certified threshold (same bound as bf_thr_kernel in brute_force.cu)
+  const float vL = key_f32(prefix);
+  const float nqr = sqrtf(qn[q]), nx = sqrtf(cmax2);
+  const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+  float thr = vL + 2.0f * eps;
+  thr = thr + fabsf(thr) * 1e-6f;
+  if (!(thr == thr)) thr = inf;
+
+  // (3) survivors
+  int m = 0;
+  for (int b0 = 0; b0 < K; b0 += 32) {
+    const int i = b0 + lane;
+    const bool keep = i < K && !(row[i] > thr);  // NaN scores are kept (scored exactly below)
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (keep) {
+      const int pos = m + __popc(bal & lanemask_lt());
+      if (pos < CAP) cand[pos] = static_cast<uint32_t>(i);
+    }
+    m += __popc(bal);
+  }
+  __syncwarp();
+  uint32_t* tok = tokens + static_cast<size_t>(q) * L;
+  float* dst = dists ? dists + static_cast<size_t>(q) * L : nullptr;
+  if (m <= CAP) {
+    // (4) exact distances of the survivors, (5) bitonic sort by (distance, id)
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    for (int j = lane; j < p2; j += 32) {
+      uint64_t key = ~0ull;
+      if (j < m) {
+        const uint32_t id = cand[j];
+        const float d = exact_center_distance(qs, centers + static_cast<size_t>(id) * dim, dim);
+        key = (static_cast<uint64_t>(f32_key(d)) << 32) | id;
+      }
+      keys[j] = key;
+    }
+    __syncwarp();
+    for (int kk = 2; kk <= p2; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < p2; i += 32) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const bool asc = (i & kk) == 0;
+            const uint64_t x = keys[i], y = keys[ixj];
+            if ((x > y) == asc) {
+              keys[i] = y;
+              keys[ixj] = x;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int j = lane; j < L; j += 32) {
+      const bool ok = j < Leff;
+      const uint64_t key = ok ? keys[j] : ~0ull;
+      tok[j] = ok ? static_cast<uint32_t>(key & 0xFFFFFFFFu) : 0xFFFFFFFFu;
+      if (dst) dst[j] = ok ? key_f32(static_cast<uint32_t>(key >> 32)) : inf;
+    }
+  } else {
+    // more survivors than shared memory holds (massively tied centres): exact distance of every centre into the row,
+    // then L rounds of "smallest (distance, id) key above the previous one".  Slow, correct, never on real indices.
+    for (int i = lane; i < K; i += 32) row[i] = exact_center_distance(qs, centers + static_cast<size_t>(i) * dim, dim);
+    __syncwarp();
+    uint64_t last = 0;
+    bool first = true;
+    for (int j = 0; j < L; ++j) {
+      uint64_t best = ~0ull;
+      if (j < Leff) {
+        for (int i = lane; i < K; i += 32) {
+          const uint64_t key = (static_cast<uint64_t>(f32_key(row[i])) << 32) | static_cast<uint32_t>(i);
+          if ((first || key > last) && key < best) best = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const uint64_t other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+          best = other < best ? other : best;
+        }
+        last = best;
+        first = false;
+      }
+      if (lane == 0) {
+        const bool ok = j < Leff;
+        tok[j] = ok ? static_cast<uint32_t>(best & 0xFFFFFFFFu) : 0xFFFFFFFFu;
+        if (dst) dst[j] = ok ? key_f32(static_cast<uint32_t>(best >> 32)) : inf;
+      }
+    }
+  }
+}
+
+static size_t part_tc_smem(int cap, size_t dim) {
+  return static_cast<size_t>(kPtWarps) * (cap * 8 + 256 * 4 + cap * 4 + ((dim + 3) & ~size_t(3)) * 4);
+}
+
+bool part_tc_usable(size_t K, size_t dim) {
+  const char* e = getenv("SCANN_PART_NO_TC");
+  if (e && e[0] == '1') return false;
+  return tc_supported(dim) && K >= 256;  // small K: the exact kernel alone is cheaper than the extra launches
+}
+
+size_t part_tc_scratch_bytes(size_t K, size_t dim, size_t nq) {
+  return Workspace::padded(tc_queries_pad(nq, dim) * tc_kpad(dim) * 2) + Workspace::padded(tc_queries_pad(nq, dim) * 4) +
+         Workspace::padded(nq * tc_rows_pad(K) * 4) + 1024;
+}
+
+scann_status part_tc_prepare(const float* centers, size_t K, size_t dim, PartTc* out, cudaStream_t s) {
+  const size_t kpad = tc_kpad(dim), rpad = tc_rows_pad(K);
+  SCANN_TRY(out->cbf.alloc(rpad * kpad));
+  SCANN_TRY(out->hx.alloc(rpad));
+  SCANN_TRY(out->small.alloc(1));
+  SCANN_TRY(tc_prepare_rows(centers, false, K, dim, dim, 1.0f, true, out->cbf.p, out->hx.p, out->small.p, s));
+  SCANN_CUDA(cudaMemcpyAsync(&out->cmax2, out->small.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+  SCANN_CUDA(cudaStreamSynchronize(s));
+  out->ready = true;
+  return SCANN_OK;
+}
+
+scann_status launch_partition_tc(const PartTc& tc, const float* centers, size_t K, size_t dim, const float* queries,
+                                 size_t nq, size_t L, uint32_t* tokens, float* dists, void* scratch, int sms,
+                                 cudaStream_t s) {
+  if (nq == 0 || L == 0) return SCANN_OK;
+  SCANN_REQUIRE(L <= 1024, SCANN_INVALID_ARGUMENT, "partitions_to_search %zu > 1024 unsupported", L);
+  const size_t kpad = tc_kpad(dim), rpad = tc_rows_pad(K), qpad = tc_queries_pad(nq, dim);
+  uint8_t* p = static_cast<uint8_t*>(scratch);
+  uint16_t* qbf = reinterpret_cast<uint16_t*>(p);
+  p += Workspace::padded(qpad * kpad * 2);
+  float* qn = reinterpret_cast<float*>(p);
+  p += Workspace::padded(qpad * 4);
+  float* dense = reinterpret_cast<float*>(p);
+  SCANN_TRY(tc_prepare_queries(queries, nq, dim, 1.0f, qbf, qn, s));
+  TcScoreParams sp;
+  sp.q_bf16 = qbf;
+  sp.nq = nq;
+  sp.dim = dim;
+  sp.rows_bf16 = tc.cbf.p;
+  sp.rows_pad_total = rpad;
+  sp.hx = tc.hx.p;
+  sp.row0 = 0;
+  sp.nrows = rpad;
+  sp.filter = false;
+  sp.dense = dense;
+  sp.ld = rpad;
+  sp.thr = nullptr;
+  sp.cand = nullptr;
+  sp.cap = 0;
+  sp.cand_cnt = nullptr;
+  sp.sms = sms;
+  SCANN_TRY(launch_tc_scores(sp, s));
+  const unsigned grid = static_cast<unsigned>((nq + kPtWarps - 1) / kPtWarps);
+  if (L <= 384) {
+    const size_t smem = part_tc_smem(512, dim);
+    SCANN_CUDA(cudaFuncSetAttribute(part_tc_select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+    part_tc_select_kernel<512><<<grid, kPtWarps * 32, smem, s>>>(dense, static_cast<int>(rpad), centers,
+                                                               static_cast<int>(K), static_cast<int>(dim), queries, qn,
+                                                               tc.cmax2, static_cast<int>(nq), static_cast<int>(L),
+                                                               tokens, dists);
+  } else {
+    const size_t smem = part_tc_smem(2048, dim);
+    SCANN_CUDA(cudaFuncSetAttribute(part_tc_select_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+    part_tc_select_kernel<2048><<<grid, kPtWarps * 32, smem, s>>>(dense, static_cast<int>(rpad), centers,
+                                                                static_cast<int>(K), static_cast<int>(dim), queries,
+                                                                qn, tc.cmax2, static_cast<int>(nq),
+                                                                static_cast<int>(L), tokens, dists);
+  }
+  SCANN_CUDA(cudaGetLastError());
+  return SCANN_OK;
+}
+
 __global__ void transpose_kernel(const float* __restrict__ in, size_t rows, size_t cols, float* __restrict__ out) {
   __shared__ float tile[32][33];
   size_t c0 = static_cast<size_t>(blockIdx.x) * 32, r0 = static_cast<size_t>(blockIdx.y) * 32;
@@ -127,7 +403,9 @@ scann_status launch_partition(const float* centersT, size_t K, size_t dim, const
 struct scann_part {
   int device = 0;
   size_t K = 0, dim = 0;
-  scann::DevBuf<float> centersT;
+  scann::DevBuf<float> centersT, centers;
+  scann::PartTc ptc;
+  int sms = 148;
   scann::Workspace ws;
   std::mutex mu;
   cudaStream_t stream = nullptr;
@@ -158,6 +436,11 @@ scann_status scann_part_create(const float* centers, size_t K, size_t dim, int d
     if ((st = tmp.upload(centers, K * dim, memspace, h->stream)) != SCANN_OK) break;
     if ((st = h->centersT.alloc(K * dim)) != SCANN_OK) break;
     launch_transpose(tmp.p, K, dim, h->centersT.p, h->stream);
+    h->sms = sm_count(device);
+    if (part_tc_usable(K, dim)) {
+      if ((st = h->centers.upload(tmp.p, K * dim, SCANN_DEVICE, h->stream)) != SCANN_OK) break;
+      if ((st = part_tc_prepare(h->centers.p, K, dim, &h->ptc, h->stream)) != SCANN_OK) break;
+    }
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) {
       st = cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
       break;
@@ -188,11 +471,18 @@ scann_status scann_part_select(scann_part* h, const float* queries, size_t nq, s
   size_t chunk = (size_t(256) << 20) / (h->K * sizeof(float));
   if (chunk < 1) chunk = 1;
   if (chunk > nq) chunk = nq;
-  size_t need = Workspace::padded(chunk * h->K * sizeof(float));
+  size_t need = Workspace::padded(std::max(chunk * h->K * sizeof(float),
+                                           h->ptc.ready ? part_tc_scratch_bytes(h->K, h->dim, chunk) : size_t(0)));
   if (memspace == SCANN_HOST)
     need += Workspace::padded(chunk * h->dim * 4) + Workspace::padded(chunk * L * 4) * 2;
   SCANN_TRY(h->ws.reserve(need));
-  float* scratch = h->ws.take<float>(chunk * h->K);
+  float* scratch = reinterpret_cast<float*>(h->ws.take<uint8_t>(std::max(
+      chunk * h->K * sizeof(float), h->ptc.ready ? part_tc_scratch_bytes(h->K, h->dim, chunk) : size_t(0))));
+  auto run = [&](const float* q, size_t nqc, uint32_t* tok, float* dd) -> scann_status {
+    if (h->ptc.ready)
+      return launch_partition_tc(h->ptc, h->centers.p, h->K, h->dim, q, nqc, L, tok, dd, scratch, h->sms, s);
+    return launch_partition(h->centersT.p, h->K, h->dim, q, nqc, L, tok, dd, scratch, s);
+  };
   float* dq = nullptr;
   uint32_t* dtok = nullptr;
   float* ddist = nullptr;
@@ -206,13 +496,12 @@ scann_status scann_part_select(scann_part* h, const float* queries, size_t nq, s
     const float* qin = queries + q0 * h->dim;
     if (memspace == SCANN_HOST) {
       SCANN_CUDA(cudaMemcpyAsync(dq, qin, nqc * h->dim * 4, cudaMemcpyHostToDevice, s));
-      SCANN_TRY(launch_partition(h->centersT.p, h->K, h->dim, dq, nqc, L, dtok, ddist, scratch, s));
+      SCANN_TRY(run(dq, nqc, dtok, ddist));
       SCANN_CUDA(cudaMemcpyAsync(tokens + q0 * L, dtok, nqc * L * 4, cudaMemcpyDeviceToHost, s));
       if (dists) SCANN_CUDA(cudaMemcpyAsync(dists + q0 * L, ddist, nqc * L * 4, cudaMemcpyDeviceToHost, s));
       SCANN_CUDA(cudaStreamSynchronize(s));
     } else {
-      SCANN_TRY(launch_partition(h->centersT.p, h->K, h->dim, qin, nqc, L, tokens + q0 * L,
-                                 dists ? dists + q0 * L : nullptr, scratch, s));
+      SCANN_TRY(run(qin, nqc, tokens + q0 * L, dists ? dists + q0 * L : nullptr));
     }
   }
   return SCANN_OK;
@@ -224,6 +513,10 @@ void scann_part_destroy(scann_part* h) {
     scann::DeviceGuard g(h->device);
     h->ws.release();
     h->centersT.free_();
+    h->centers.free_();
+    h->ptc.cbf.free_();
+    h->ptc.hx.free_();
+    h->ptc.small.free_();
     if (h->stream) cudaStreamDestroy(h->stream);
   }
   delete h;

@@ -73,7 +73,10 @@ __global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, u
 
 // single block: exclusive scans of pair counts and item counts per leaf; also accumulates the
 // algorithmic scan bytes of this batch (Σ pairs * leaf_size * bytes_per_point) for the roofline.
+// Leaves are laid out in `perm` order = descending leaf size (longest items first), so the persistent scan kernel's
+// atomic-counter schedule ends on the smallest items and the tail stays short.
 __global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
+                                                       const uint32_t* __restrict__ perm,
                                                        const uint64_t* __restrict__ pt_off, uint32_t bpp,
                                                        uint32_t* __restrict__ pair_start,
                                                        uint32_t* __restrict__ item_start,
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restric
   const uint32_t b = threadIdx.x * per, e = min(K, b + per);
   uint32_t pc = 0, ic = 0;
   unsigned long long bytes = 0;
-  for (uint32_t l = b; l < e; ++l) {
+  for (uint32_t i = b; i < e; ++i) {
+    const uint32_t l = perm[i];
     uint32_t c = leaf_cnt[l];
     pc += c;
     ic += (c + G - 1) / G;
@@ -110,7 +114,8 @@ __global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restric
     __syncthreads();
   }
   uint32_t pbase = s_pair[threadIdx.x] - pc, ibase = s_item[threadIdx.x] - ic;
-  for (uint32_t l = b; l < e; ++l) {
+  for (uint32_t i = b; i < e; ++i) {
+    const uint32_t l = perm[i];
     uint32_t c = leaf_cnt[l];
     pair_start[l] = pbase;
     item_start[l] = ibase;
@@ -275,9 +280,10 @@ struct scann_treeah {
   int use_residuals = 1, reorder_measure = SCANN_SQL2, pos_bits = 18;
   uint32_t max_leaf = 0;
   scann::DevBuf<float> centers, centersT, codebook, raw;
-  scann::DevBuf<uint32_t> codes, ids, blk_off;
+  scann::DevBuf<uint32_t> codes, ids, blk_off, leaf_perm;  // leaf_perm: leaves by descending size
   scann::DevBuf<uint64_t> pt_off;
   scann::DevBuf<unsigned long long> stats;  // [0] algorithmic scan bytes, [1] pairs of the last search
+  scann::PartTc ptc;                        // tensor-core centroid scoring operands (partition.cu)
   scann::Workspace ws;
   std::mutex mu;
   cudaStream_t stream = nullptr;
@@ -349,7 +355,8 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   int G = avg >= 6.0 ? 8 : (avg >= 3.0 ? 4 : (avg >= 1.5 ? 2 : 1));
   size_t max_items = P / G + std::min<size_t>(K, P) + 1;
 
-  float* scratch = h->ws.take<float>(nq * K);
+  float* scratch = reinterpret_cast<float*>(h->ws.take<uint8_t>(
+      std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0))));
   uint32_t* tokens = h->ws.take<uint32_t>(P);
   uint32_t* leaf_cnt = h->ws.take<uint32_t>(2 * K);  // counts + cursors
   uint32_t* cursor = leaf_cnt + K;
@@ -364,7 +371,10 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
 
   // 1. partition (K == 1 still goes through it: one centre, token 0)
   h->mark(s);
-  SCANN_TRY(launch_partition(h->centersT.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, s));
+  if (h->ptc.ready)
+    SCANN_TRY(launch_partition_tc(h->ptc, h->centers.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, h->sms, s));
+  else
+    SCANN_TRY(launch_partition(h->centersT.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, s));
   h->mark(s);
   // 2. worklist
   SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 2 * K * sizeof(uint32_t), s));
@@ -372,7 +382,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   SCANN_CUDA(cudaMemsetAsync(qthr, 0xFF, nq * sizeof(uint32_t), s));
   unsigned pb = static_cast<unsigned>((P + 255) / 256);
   wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), h->pt_off.p, leaf_cnt);
-  wl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->pt_off.p,
+  wl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p,
                                     static_cast<uint32_t>((h->S + 1) / 2), pair_start, item_start, counters,
                                     h->stats.p);
   wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), h->pt_off.p, pair_start, cursor,
@@ -442,7 +452,9 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   merge_reorder_kernel<<<static_cast<unsigned>(nq), 256, msm, s>>>(m);
   SCANN_CUDA(cudaGetLastError());
   h->mark(s);
-  h->prof_launches += 8;  // center_dist, part_select, wl_count, wl_scan, wl_scatter, wl_items, lut16_scan, merge_reorder
+  // center_dist, part_select (or tc_prep_queries, tc_score, part_tc_select), wl_count, wl_scan, wl_scatter, wl_items,
+  // lut16_scan, merge_reorder
+  h->prof_launches += h->ptc.ready ? 9 : 8;
   return SCANN_OK;
 }
 
@@ -450,7 +462,7 @@ static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, siz
   size_t K = h->K, P = nq * L;
   size_t b = 0;
   auto add = [&](size_t bytes) { b += Workspace::padded(bytes); };
-  add(nq * K * 4);
+  add(std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0)));
   add(P * 4);
   add(2 * K * 4);
   add((K + 1) * 4);
@@ -561,10 +573,16 @@ scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, con
     if ((st = h->centers.upload(centers, K * dim, memspace, s)) != SCANN_OK) break;
     if ((st = h->centersT.alloc(K * dim)) != SCANN_OK) break;
     launch_transpose(h->centers.p, K, dim, h->centersT.p, s);
+    if (part_tc_usable(K, dim) && (st = part_tc_prepare(h->centers.p, K, dim, &h->ptc, s)) != SCANN_OK) break;
     if ((st = h->codebook.upload(codebook, S * 16 * h->ds, memspace, s)) != SCANN_OK) break;
     if ((st = h->ids.upload(ids, n, memspace, s)) != SCANN_OK) break;
     if ((st = h->pt_off.upload(off.data(), K + 1, SCANN_HOST, s)) != SCANN_OK) break;
     if ((st = h->blk_off.upload(blk_off.data(), K + 1, SCANN_HOST, s)) != SCANN_OK) break;
+    std::vector<uint32_t> perm(K);
+    for (size_t l = 0; l < K; ++l) perm[l] = static_cast<uint32_t>(l);
+    std::stable_sort(perm.begin(), perm.end(),
+                     [&](uint32_t x, uint32_t y) { return off[x + 1] - off[x] > off[y + 1] - off[y]; });
+    if ((st = h->leaf_perm.upload(perm.data(), K, SCANN_HOST, s)) != SCANN_OK) break;
     if ((st = d_blk_leaf.upload(blk_leaf.data(), nb, SCANN_HOST, s)) != SCANN_OK) break;
     if ((st = d_packed.upload(packed, n * bpp, memspace, s)) != SCANN_OK) break;
     size_t words = static_cast<size_t>(nb) * h->SG * 128;
@@ -719,6 +737,10 @@ void scann_treeah_destroy(scann_treeah* h) {
     h->ids.free_();
     h->blk_off.free_();
     h->pt_off.free_();
+    h->leaf_perm.free_();
+    h->ptc.cbf.free_();
+    h->ptc.hx.free_();
+    h->ptc.small.free_();
     h->stats.free_();
     if (h->stream) cudaStreamDestroy(h->stream);
   }

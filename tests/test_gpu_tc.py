@@ -138,3 +138,38 @@ def test_sq8_tensor_core_path_is_exact(gpu_lib, oracle, measure):
     assert (dists.view(np.uint32) == odists.view(np.uint32)).all()
     compared, mism = helpers.ids_equal_away_from_ties(ids, dists, oids, odists, counts, rel_gap=0.0)
     assert mism == 0
+
+
+# ----------------------------------------------------------------------------- partitioner on the tensor-core path
+@pytest.mark.parametrize("K,dim,nq,L", [(2000, 96, 1000, 64), (8192, 128, 300, 128), (300, 64, 100, 300),
+                                        (5000, 200, 50, 1000), (1000, 7, 64, 10), (256, 96, 33, 500)])
+def test_partition_tensor_core_bit_exact(gpu_lib, oracle, K, dim, nq, L):
+    x, _ = helpers.clustered(K + nq, dim, 40, 0.4, K + dim)
+    centers, q = np.ascontiguousarray(x[:K]), np.ascontiguousarray(x[K:])
+    part = gpu_lib.TreePartitioner(centers)
+    tokens, dists = part.partition(q, L)
+    otok, odist = oracle.partition(centers, q, L)
+    assert (tokens == otok).all()
+    assert (dists.view(np.uint32) == odist.view(np.uint32)).all()
+
+
+def test_partition_tensor_core_tied_centres_fallback(gpu_lib, oracle):
+    # 700 identical centres tie at every threshold: more survivors than the shared-memory list holds
+    rng = np.random.default_rng(5)
+    centers = np.tile(rng.normal(0, 1, (1, 32)).astype(np.float32), (700, 1))
+    centers[::7] += rng.normal(0, 1, (100, 32)).astype(np.float32)
+    q = rng.normal(0, 1, (20, 32)).astype(np.float32)
+    part = gpu_lib.TreePartitioner(centers)
+    tokens, dists = part.partition(q, 50)
+    otok, odist = oracle.partition(centers, q, 50)
+    assert (tokens == otok).all() and (dists.view(np.uint32) == odist.view(np.uint32)).all()
+
+
+def test_partition_cuda_core_path_still_bit_exact(gpu_lib, oracle, monkeypatch):
+    monkeypatch.setenv("SCANN_PART_NO_TC", "1")
+    rng = np.random.default_rng(6)
+    centers = rng.normal(0, 1, (1500, 96)).astype(np.float32)
+    q = rng.normal(0, 1, (100, 96)).astype(np.float32)
+    tokens, dists = gpu_lib.TreePartitioner(centers).partition(q, 64)
+    otok, odist = oracle.partition(centers, q, 64)
+    assert (tokens == otok).all() and (dists.view(np.uint32) == odist.view(np.uint32)).all()
