@@ -55,6 +55,10 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--shard", default="partition", choices=["partition", "rows"],
                    help="multi-GPU sharding: whole partitions per GPU (default) or rows round-robin inside partitions")
+    p.add_argument("--emulate-shard", type=int, default=0,
+                   help="single-GPU tuning aid: build and search only shard 0 of N (not a bench mode)")
+    p.add_argument("--split", action="store_true",
+                   help="single-GPU tuning aid: use the two-phase search_begin/search_end path (no reduction)")
     p.add_argument("--sweep-leaves", default="", help="comma list: print recall/QPS for each L (stderr) and exit")
     return p.parse_args()
 
@@ -176,38 +180,46 @@ def main():
         dist.broadcast(codebook, 0)
     K = centers.shape[0]
     assign = ix.assign_partitions(x, centers, local_rank)
-    order = torch.argsort(assign.long(), stable=True)
-    counts = torch.bincount(assign.long(), minlength=K)
-    off = torch.zeros((K + 1,), dtype=torch.int64, device=dev)
-    off[1:] = torch.cumsum(counts, 0)
     shard_world = world if a.impl == "ours" else 1
-    if shard_world > 1:
-        pos = torch.arange(a.n, device=dev, dtype=torch.int64)
-        leaf_sorted = assign.long()[order]
-        if a.shard == "rows":  # round-robin inside each partition
-            keep = ((pos - off[leaf_sorted]) % shard_world) == rank
-        else:  # whole partitions per GPU, dealt largest-first in snake order so shard sizes balance
-            by_size = torch.argsort(counts, descending=True)
-            slot = torch.arange(K, device=dev) % (2 * shard_world)
-            owner_sorted = torch.where(slot < shard_world, slot, 2 * shard_world - 1 - slot)
-            owner = torch.empty(K, dtype=torch.int64, device=dev)
-            owner[by_size] = owner_sorted
-            keep = owner[leaf_sorted] == rank
-        order = order[keep]
-        cnt = torch.bincount(leaf_sorted[keep], minlength=K)
-        off = torch.zeros((K + 1,), dtype=torch.int64, device=dev)
-        off[1:] = torch.cumsum(cnt, 0)
-        del pos, leaf_sorted, keep
-    bpp = (a.subspaces + 1) // 2
-    packed = torch.empty((order.numel(), bpp), dtype=torch.uint8, device=dev)
-    for s in range(0, order.numel(), 1 << 21):
-        idx = order[s:s + (1 << 21)]
-        packed[s:s + (1 << 21)] = pkg.pq_encode(codebook, x[idx].contiguous(), centers, assign[idx].contiguous(),
-                                                local_rank)
-    ids32 = order.to(torch.int32).contiguous()
+    shard_rank = rank
+    if a.emulate_shard > 1 and world == 1:
+        shard_world, shard_rank = a.emulate_shard, 0
+    order_all = torch.argsort(assign.long(), stable=True)
+    counts = torch.bincount(assign.long(), minlength=K)
+    off_all = torch.zeros((K + 1,), dtype=torch.int64, device=dev)
+    off_all[1:] = torch.cumsum(counts, 0)
+
+    def build_shard(sw, sr):
+        """rows of shard sr of sw (sw == 1: everything) -> (packed codes grouped by partition, ids, offsets)"""
+        order, off = order_all, off_all
+        if sw > 1:
+            pos = torch.arange(a.n, device=dev, dtype=torch.int64)
+            leaf_sorted = assign.long()[order]
+            if a.shard == "rows":  # round-robin inside each partition (SURVEY §8e)
+                keep = ((pos - off[leaf_sorted]) % sw) == sr
+            else:  # whole partitions per GPU, dealt largest-first in snake order so shard sizes balance
+                by_size = torch.argsort(counts, descending=True)
+                slot = torch.arange(K, device=dev) % (2 * sw)
+                owner_sorted = torch.where(slot < sw, slot, 2 * sw - 1 - slot)
+                owner = torch.empty(K, dtype=torch.int64, device=dev)
+                owner[by_size] = owner_sorted
+                keep = owner[leaf_sorted] == sr
+            order = order[keep]
+            cnt = torch.bincount(leaf_sorted[keep], minlength=K)
+            off = torch.zeros((K + 1,), dtype=torch.int64, device=dev)
+            off[1:] = torch.cumsum(cnt, 0)
+        bpp = (a.subspaces + 1) // 2
+        packed = torch.empty((order.numel(), bpp), dtype=torch.uint8, device=dev)
+        for s0 in range(0, order.numel(), 1 << 21):
+            idx = order[s0:s0 + (1 << 21)]
+            packed[s0:s0 + (1 << 21)] = pkg.pq_encode(codebook, x[idx].contiguous(), centers, assign[idx].contiguous(),
+                                                      local_rank)
+        return packed, order.to(torch.int32).contiguous(), off
+
+    packed, ids32, off = build_shard(shard_world, shard_rank)
     torch.cuda.synchronize()
-    log(f"[rank {rank}] index K={K} S={a.subspaces} rows={order.numel()} in {time.time() - t0:.1f}s "
-        f"(leaf sizes min/mean/max {int((off[1:] - off[:-1]).min())}/{order.numel() / K:.0f}/"
+    log(f"[rank {rank}] index K={K} S={a.subspaces} rows={ids32.numel()} in {time.time() - t0:.1f}s "
+        f"(leaf sizes min/mean/max {int((off[1:] - off[:-1]).min())}/{ids32.numel() / K:.0f}/"
         f"{int((off[1:] - off[:-1]).max())})")
 
     workload = (f"Tree-AH {a.n}x{a.dim} K={K} LUT16 S={a.subspaces} ds={a.dim // a.subspaces} L={a.leaves} "
@@ -260,12 +272,25 @@ def main():
                                 pre_reorder_multiplier=a.reorder / a.k, distance_measure=pkg.DistanceMeasure.DotProduct)
     searcher = pkg.TreeXHybridSearcher(cfg, local_rank).build_from_index(centers, codebook, packed, ids32, off, x)
     R = a.reorder
+    xchg_events = []  # (start, end) CUDA events around the all-gather + merge of the timed steps
 
-    def step_device(qb):
-        ids, dists, cnt = searcher.search_batched(qb, a.k, pre_reorder_k=R)
+    def step_device(qb, timed=False):
+        if world > 1 or a.split:
+            tau = searcher.search_begin(qb, a.k, pre_reorder_k=R)
+            if world > 1:
+                dist.all_reduce(tau, op=dist.ReduceOp.MIN)
+            ids, dists, cnt = searcher.search_end(tau)
+        else:
+            ids, dists, cnt = searcher.search_batched(qb, a.k, pre_reorder_k=R)
         if world > 1:
+            if timed:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             gi, gd = pkg.distributed.all_gather_results(ids, dists)
             ids, dists, cnt = pkg.merge_topk(gi, gd, local_rank)
+            if timed:
+                ev[1].record()
+                xchg_events.append(ev)
         return ids, dists, cnt
 
     # recall vs exact ground truth (own brute-force searcher, DotProduct)
@@ -317,14 +342,15 @@ def main():
     barrier()
     e0.record()
     for s in range(a.steps):
-        step_device(queries[s % n_batches])
+        step_device(queries[s % n_batches], timed=True)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     prof, launches = searcher.get_profile()
     searcher.set_profiling(False)
     scan_bytes, pairs = searcher.last_scan_bytes()  # algorithmic bytes of one step (this rank's shard)
-    log(f"[rank {rank}] {ms / a.steps:.3f} ms/step; stages " +
+    xchg_ms = sum(e[0].elapsed_time(e[1]) for e in xchg_events) / max(1, len(xchg_events))
+    log(f"[rank {rank}] {ms / a.steps:.3f} ms/step; all-gather+merge {xchg_ms:.3f}; stages " +
         ", ".join(f"{k2} {v / a.steps:.3f}" for k2, v in prof.items()) + f"; scan bytes {scan_bytes / 1e9:.1f} GB")
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -339,12 +365,10 @@ def main():
     hq_np = [t.numpy() for t in hq]
 
     def step_host(b):
-        ids, dists, cnt = searcher.search_batched(hq_np[b], a.k, pre_reorder_k=R)
-        if world > 1:
-            gi, gd = pkg.distributed.all_gather_results(torch.from_numpy(ids.view(np.int32)).to(dev),
-                                                        torch.from_numpy(dists).to(dev))
-            mi, md, mc = pkg.merge_topk(gi, gd, local_rank)
+        if world > 1:  # pinned host queries -> device -> split search + exchange -> host results
+            mi, md, mc = step_device(hq[b].to(dev, non_blocking=True))
             return mi.cpu().numpy(), md.cpu().numpy()
+        ids, dists, cnt = searcher.search_batched(hq_np[b], a.k, pre_reorder_k=R)
         return ids, dists
 
     for w in range(max(1, a.warmup)):

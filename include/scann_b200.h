@@ -143,6 +143,21 @@ scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t n
                                  size_t k, uint32_t* ids, float* dists, uint32_t* counts, uint32_t* cand_ids,
                                  float* cand_dists, uint32_t* cand_counts, int memspace, void* stream);
 void scann_treeah_destroy(scann_treeah* h);
+/* Split search for a SHARDED index (one process per GPU, every shard sees the whole query batch).
+ *   scann_treeah_search_begin: partition -> worklist -> LUT16 scan of every query's CLOSEST leaf when this shard
+ *       owns it.  tau_out[q] (device, nq floats) receives the bound that leaf proves: the R-th smallest approximate
+ *       distance it holds (+inf when the leaf lives on another shard or has fewer than R points).
+ *   the caller min-reduces tau over the shards (e.g. ncclAllReduce MIN, 4 B per query);
+ *   scann_treeah_search_end: scans the remaining leaves under tau_in (device, nq floats, or NULL) — a point above
+ *       tau_in[q] cannot be among the global top-R of query q because the closest leaf already holds R points at or
+ *       below it — then merges and re-scores exactly as scann_treeah_search does.
+ * The bounds are data-defined (not timing-defined), so results are deterministic and every shard's list is a
+ * superset of the global top-R restricted to the shard.  Device pointers only; begin/end must be paired on one
+ * thread (the handle stays locked in between); the batch must fit one chunk (nq*L*R*8 <= 1 GiB). */
+scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L,
+                                       size_t R, size_t k, float* tau_out, void* stream);
+scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint32_t* ids, float* dists,
+                                     uint32_t* counts, void* stream);
 /* introspection used by bench.py for the roofline arithmetic: algorithmic code bytes scanned by the
  * last scann_treeah_search call (Σ over (query, leaf) pairs of leaf_size * ceil(S/2)); host sync. */
 scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint64_t* pairs);

@@ -34,7 +34,7 @@ SYMBOLS = [
     "scann_sq8_quantize", "scann_sq8_create", "scann_sq8_search", "scann_sq8_destroy",
     "scann_part_create", "scann_part_select", "scann_part_destroy",
     "scann_treeah_create", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
-    "scann_treeah_set_profiling", "scann_treeah_get_profile",
+    "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end",
     "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_tc_scores",
 ]
 
@@ -90,6 +90,8 @@ def load():
     L.scann_treeah_destroy.argtypes = [vp]
     L.scann_treeah_destroy.restype = None
     L.scann_treeah_last_scan_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.scann_treeah_search_begin.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp, vp]
+    L.scann_treeah_search_end.argtypes = [vp, vp, vp, vp, vp, vp]
     L.scann_treeah_set_profiling.argtypes = [vp, i32]
     L.scann_treeah_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.scann_lut16_build.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, vp, i32, i32]

@@ -32,7 +32,8 @@ struct ScanArgs {
   const float* queries;
   const uint4* items;
   const uint32_t* sorted_pairs;
-  uint32_t* counters;  // [0] total items, [1] next item
+  uint32_t* counters;  // [0] total items, [1] next item, [2] class-A items (closest-leaf pairs, scanned first)
+  int end_idx;         // this launch stops at counters[end_idx]: 0 = every item, 2 = the class-A items only
   uint32_t* qthr;      // [nq] f32_key of the best known bound on the R-th approx distance (0xFFFFFFFF = none)
   uint2* cand;         // [P][R] {approx distance bits, position in leaf}
   uint32_t* cand_cnt;  // [P]
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const Scan
   uint32_t* s_item = s_tau + G;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t total_items = a.counters[0];
+  const uint32_t total_items = a.counters[a.end_idx];
   const uint32_t pos_mask = (1u << a.pos_bits) - 1u;
 
   for (;;) {

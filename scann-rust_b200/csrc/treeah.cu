@@ -63,34 +63,45 @@ __global__ void repack_blocked_kernel(const uint8_t* __restrict__ packed, const 
 // --------------------------------------------------------------------------------------- worklist
 // Pairs that probe a leaf with no rows on this shard (empty partition, or a partition owned by another
 // GPU) produce no work item; their candidate count stays 0.
-__global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K,
+//
+// Pairs come in two classes: A = the query's closest leaf (rank 0), B = the rest.  Class-A items are laid out (and
+// scanned) first: the closest leaf almost always yields the smallest "R-th best" distance, so the batch-wide bound
+// tau_q is in place before the bulk of the work starts — and on a sharded index the class-A bounds of all shards can
+// be min-reduced between the two phases (scann_treeah_search_begin / _end).  A "virtual leaf" v = leaf + K * class.
+__device__ __forceinline__ uint32_t wl_virtual_leaf(uint32_t leaf, size_t p, uint32_t L, uint32_t K) {
+  return leaf + ((p % L) ? K : 0u);
+}
+
+__global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K, uint32_t L,
                                 const uint64_t* __restrict__ pt_off, uint32_t* __restrict__ leaf_cnt) {
   size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint32_t leaf = tokens[p];
-  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[leaf], 1u);
+  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[wl_virtual_leaf(leaf, p, L, K)], 1u);
 }
 
-// single block: exclusive scans of pair counts and item counts per leaf; also accumulates the
+// single block: exclusive scans of pair counts and item counts per virtual leaf; also accumulates the
 // algorithmic scan bytes of this batch (Σ pairs * leaf_size * bytes_per_point) for the roofline.
-// Leaves are laid out in `perm` order = descending leaf size (longest items first), so the persistent scan kernel's
-// atomic-counter schedule ends on the smallest items and the tail stays short.
+// Inside a class, leaves are laid out in `perm` order = descending leaf size (longest items first), so the persistent
+// scan kernel's atomic-counter schedule ends on the smallest items and the tail stays short.
 __global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
                                                        const uint32_t* __restrict__ perm,
                                                        const uint64_t* __restrict__ pt_off, uint32_t bpp,
                                                        uint32_t* __restrict__ pair_start,
                                                        uint32_t* __restrict__ item_start,
-                                                       uint32_t* __restrict__ counters /* [0]=total items,[1]=next */,
+                                                       uint32_t* __restrict__ counters /* [0]=items,[1]=next,[2]=class-A items */,
                                                        unsigned long long* __restrict__ stats) {
   __shared__ uint32_t s_pair[1024], s_item[1024];
   __shared__ unsigned long long s_bytes[1024];
-  const uint32_t per = (K + 1023) / 1024;
-  const uint32_t b = threadIdx.x * per, e = min(K, b + per);
+  const uint32_t K2 = 2 * K;
+  const uint32_t per = (K2 + 1023) / 1024;
+  const uint32_t b = threadIdx.x * per, e = min(K2, b + per);
+  auto vleaf = [&](uint32_t i) { return i < K ? perm[i] : K + perm[i - K]; };
   uint32_t pc = 0, ic = 0;
   unsigned long long bytes = 0;
   for (uint32_t i = b; i < e; ++i) {
-    const uint32_t l = perm[i];
-    uint32_t c = leaf_cnt[l];
+    const uint32_t v = vleaf(i), l = v >= K ? v - K : v;
+    uint32_t c = leaf_cnt[v];
     pc += c;
     ic += (c + G - 1) / G;
     bytes += static_cast<unsigned long long>(c) * (pt_off[l + 1] - pt_off[l]) * bpp;
@@ -115,42 +126,59 @@ __global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restric
   }
   uint32_t pbase = s_pair[threadIdx.x] - pc, ibase = s_item[threadIdx.x] - ic;
   for (uint32_t i = b; i < e; ++i) {
-    const uint32_t l = perm[i];
-    uint32_t c = leaf_cnt[l];
-    pair_start[l] = pbase;
-    item_start[l] = ibase;
+    const uint32_t v = vleaf(i);
+    uint32_t c = leaf_cnt[v];
+    pair_start[v] = pbase;
+    item_start[v] = ibase;
     pbase += c;
     ibase += (c + G - 1) / G;
   }
+  __syncthreads();
   if (threadIdx.x == 1023) {
-    pair_start[K] = s_pair[1023];
-    item_start[K] = s_item[1023];
     counters[0] = s_item[1023];
     counters[1] = 0;
+    counters[2] = item_start[K + perm[0]];  // first class-B item = number of class-A items
     atomicAdd(&stats[0], s_bytes[1023]);
     atomicAdd(&stats[1], static_cast<unsigned long long>(s_pair[1023]));
   }
 }
 
-__global__ void wl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K,
+__global__ void wl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K, uint32_t L,
                                   const uint64_t* __restrict__ pt_off, const uint32_t* __restrict__ pair_start,
                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted_pairs) {
   size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint32_t leaf = tokens[p];
   if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) {
-    uint32_t slot = atomicAdd(&cursor[leaf], 1u);
-    sorted_pairs[pair_start[leaf] + slot] = static_cast<uint32_t>(p);
+    const uint32_t v = wl_virtual_leaf(leaf, p, L, K);
+    uint32_t slot = atomicAdd(&cursor[v], 1u);
+    sorted_pairs[pair_start[v] + slot] = static_cast<uint32_t>(p);
   }
 }
 
 __global__ void wl_items_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
                                 const uint32_t* __restrict__ pair_start, const uint32_t* __restrict__ item_start,
                                 uint4* __restrict__ items) {
-  uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= K) return;
-  uint32_t c = leaf_cnt[l], pb = pair_start[l], ib = item_start[l];
+  uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= 2 * K) return;
+  const uint32_t l = v >= K ? v - K : v;
+  uint32_t c = leaf_cnt[v], pb = pair_start[v], ib = item_start[v];
   for (uint32_t g = 0; g * G < c; ++g) items[ib + g] = make_uint4(l, pb + g * G, min(static_cast<uint32_t>(G), c - g * G), 0u);
+}
+
+// qthr <-> caller-visible f32 bounds (scann_treeah_search_begin / _end)
+__global__ void tau_in_kernel(const float* __restrict__ tau, size_t nq, uint32_t* __restrict__ qthr) {
+  size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const float t = tau[q];
+  const uint32_t k = (t == t && t < __int_as_float(0x7F800000)) ? f32_key(t) : 0xFFFFFFFFu;
+  qthr[q] = min(qthr[q], k);
+}
+__global__ void tau_out_kernel(const uint32_t* __restrict__ qthr, size_t nq, float* __restrict__ tau) {
+  size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const uint32_t k = qthr[q];
+  tau[q] = k == 0xFFFFFFFFu ? __int_as_float(0x7F800000) : key_f32(k);
 }
 
 // --------------------------------------------------------------------------- merge + exact reorder
@@ -288,17 +316,41 @@ struct scann_treeah {
   std::mutex mu;
   cudaStream_t stream = nullptr;
   int sms = 148;
-  // optional live profiling: 5 events per chunk bracket the 4 stages
+  // the chunk being searched, between its two phases (treeah_phase1 / treeah_phase2)
+  struct Chunk {
+    const float* dq = nullptr;
+    size_t nq = 0, L = 0, R = 0, k = 0;
+    int G = 8;
+    uint32_t *tokens = nullptr, *counters = nullptr, *cand_cnt = nullptr, *qthr = nullptr;
+    uint2* cand = nullptr;
+    scann::ScanArgs a;
+  } ck;
+  bool split_active = false;  // between scann_treeah_search_begin and _end (mu stays locked)
+  // optional live profiling: (stage, start, end) CUDA-event spans; stages 0 partition, 1 worklist, 2 scan, 3 merge
   bool profiling = false;
-  std::vector<cudaEvent_t> prof_events;
+  struct Span {
+    int stage;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Span> prof_spans;
   uint64_t prof_launches = 0;
-  void mark(cudaStream_t s) {
+  void span_begin(int stage, cudaStream_t s) {
     if (!profiling) return;
-    cudaEvent_t e;
-    if (cudaEventCreate(&e) == cudaSuccess) {
-      cudaEventRecord(e, s);
-      prof_events.push_back(e);
+    Span sp{stage, nullptr, nullptr};
+    if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess) return;
+    cudaEventRecord(sp.e0, s);
+    prof_spans.push_back(sp);
+  }
+  void span_end(cudaStream_t s) {
+    if (!profiling || prof_spans.empty()) return;
+    cudaEventRecord(prof_spans.back().e1, s);
+  }
+  void clear_spans() {
+    for (Span& sp : prof_spans) {
+      if (sp.e0) cudaEventDestroy(sp.e0);
+      if (sp.e1) cudaEventDestroy(sp.e1);
     }
+    prof_spans.clear();
   }
 };
 
@@ -346,22 +398,32 @@ static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
   }
 }
 
-static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
-                                        uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cand_ids,
-                                        float* d_cand_dists, uint32_t* d_cand_counts, cudaStream_t s) {
+static scann_status launch_scan_g(int G, const ScanArgs& a, int sms, cudaStream_t s) {
+  switch (G) {
+    case 8: return launch_scan<8>(a, sms, s);
+    case 4: return launch_scan<4>(a, sms, s);
+    case 2: return launch_scan<2>(a, sms, s);
+    default: return launch_scan<1>(a, sms, s);
+  }
+}
+
+// Phase 1 of a chunk: partition -> worklist -> (two_phase: scan of the class-A items, i.e. every query's closest leaf
+// on this shard; tau_out receives the bounds they prove).  State for phase 2 stays in h->ck / the workspace.
+static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
+                                  bool two_phase, float* tau_out, cudaStream_t s) {
   const size_t K = h->K, P = nq * L;
   // group size: how many queries share a leaf on average
   double avg = static_cast<double>(P) / static_cast<double>(std::min<size_t>(K, P));
   int G = avg >= 6.0 ? 8 : (avg >= 3.0 ? 4 : (avg >= 1.5 ? 2 : 1));
-  size_t max_items = P / G + std::min<size_t>(K, P) + 1;
+  size_t max_items = P / G + 2 * std::min<size_t>(K, P) + 1;
 
   float* scratch = reinterpret_cast<float*>(h->ws.take<uint8_t>(
       std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0))));
   uint32_t* tokens = h->ws.take<uint32_t>(P);
-  uint32_t* leaf_cnt = h->ws.take<uint32_t>(2 * K);  // counts + cursors
-  uint32_t* cursor = leaf_cnt + K;
-  uint32_t* pair_start = h->ws.take<uint32_t>(K + 1);
-  uint32_t* item_start = h->ws.take<uint32_t>(K + 1);
+  uint32_t* leaf_cnt = h->ws.take<uint32_t>(4 * K);  // counts + cursors of the 2K virtual leaves
+  uint32_t* cursor = leaf_cnt + 2 * K;
+  uint32_t* pair_start = h->ws.take<uint32_t>(2 * K + 1);
+  uint32_t* item_start = h->ws.take<uint32_t>(2 * K + 1);
   uint32_t* counters = h->ws.take<uint32_t>(4);
   uint32_t* sorted_pairs = h->ws.take<uint32_t>(P);
   uint4* items = h->ws.take<uint4>(max_items);
@@ -370,29 +432,30 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   uint32_t* qthr = h->ws.take<uint32_t>(nq);
 
   // 1. partition (K == 1 still goes through it: one centre, token 0)
-  h->mark(s);
+  h->span_begin(0, s);
   if (h->ptc.ready)
     SCANN_TRY(launch_partition_tc(h->ptc, h->centers.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, h->sms, s));
   else
     SCANN_TRY(launch_partition(h->centersT.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, s));
-  h->mark(s);
+  h->span_end(s);
   // 2. worklist
-  SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 2 * K * sizeof(uint32_t), s));
+  h->span_begin(1, s);
+  SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 4 * K * sizeof(uint32_t), s));
   SCANN_CUDA(cudaMemsetAsync(cand_cnt, 0, P * sizeof(uint32_t), s));
   SCANN_CUDA(cudaMemsetAsync(qthr, 0xFF, nq * sizeof(uint32_t), s));
   unsigned pb = static_cast<unsigned>((P + 255) / 256);
-  wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), h->pt_off.p, leaf_cnt);
+  wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), h->pt_off.p,
+                                     leaf_cnt);
   wl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p,
                                     static_cast<uint32_t>((h->S + 1) / 2), pair_start, item_start, counters,
                                     h->stats.p);
-  wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), h->pt_off.p, pair_start, cursor,
-                                       sorted_pairs);
-  wl_items_kernel<<<static_cast<unsigned>((K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
-                                                                        pair_start, item_start, items);
+  wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), h->pt_off.p,
+                                       pair_start, cursor, sorted_pairs);
+  wl_items_kernel<<<static_cast<unsigned>((2 * K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
+                                                                            pair_start, item_start, items);
   SCANN_CUDA(cudaGetLastError());
-  h->mark(s);
-  // 3. scan
-  ScanArgs a;
+  h->span_end(s);
+  ScanArgs& a = h->ck.a;
   a.codes = reinterpret_cast<const uint4*>(h->codes.p);
   a.blk_off = h->blk_off.p;
   a.pt_off = h->pt_off.p;
@@ -402,6 +465,7 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   a.items = items;
   a.sorted_pairs = sorted_pairs;
   a.counters = counters;
+  a.end_idx = 0;
   a.cand = cand;
   a.cand_cnt = cand_cnt;
   a.qthr = qthr;
@@ -417,23 +481,58 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   a.cap = 0;  // set per CTA shape in launch_scan_mode
   a.pos_bits = h->pos_bits;
   a.use_residuals = h->use_residuals;
-  switch (G) {
-    case 8: SCANN_TRY(launch_scan<8>(a, h->sms, s)); break;
-    case 4: SCANN_TRY(launch_scan<4>(a, h->sms, s)); break;
-    case 2: SCANN_TRY(launch_scan<2>(a, h->sms, s)); break;
-    default: SCANN_TRY(launch_scan<1>(a, h->sms, s)); break;
+  h->ck.dq = dq;
+  h->ck.nq = nq;
+  h->ck.L = L;
+  h->ck.R = R;
+  h->ck.k = k;
+  h->ck.G = G;
+  h->ck.tokens = tokens;
+  h->ck.counters = counters;
+  h->ck.cand = cand;
+  h->ck.cand_cnt = cand_cnt;
+  h->ck.qthr = qthr;
+  h->prof_launches += h->ptc.ready ? 7 : 6;  // partition (2 or 3 kernels) + 4 worklist kernels
+  if (two_phase) {
+    // 3a. scan of the class-A items only
+    h->span_begin(2, s);
+    a.end_idx = 2;
+    SCANN_TRY(launch_scan_g(h->ck.G, a, h->sms, s));
+    if (tau_out) tau_out_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(qthr, nq, tau_out);
+    SCANN_CUDA(cudaGetLastError());
+    h->span_end(s);
+    h->prof_launches += 2;
   }
-  h->mark(s);
+  return SCANN_OK;
+}
+
+// Phase 2: scan of the remaining items (all of them when phase 1 did not scan) with the optional global bounds
+// tau_in (device [nq]), then merge + exact reorder.
+static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* tau_in, uint32_t* d_ids, float* d_dists,
+                                  uint32_t* d_counts, uint32_t* d_cand_ids, float* d_cand_dists,
+                                  uint32_t* d_cand_counts, cudaStream_t s) {
+  const size_t K = h->K, nq = h->ck.nq, L = h->ck.L, R = h->ck.R, k = h->ck.k;
+  ScanArgs& a = h->ck.a;
+  h->span_begin(2, s);
+  if (two_phase) {
+    // the item counter overshot the class-A range by one fetch per CTA: restart it at the first class-B item
+    SCANN_CUDA(cudaMemcpyAsync(h->ck.counters + 1, h->ck.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    if (tau_in) tau_in_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(tau_in, nq, h->ck.qthr);
+  }
+  a.end_idx = 0;
+  SCANN_TRY(launch_scan_g(h->ck.G, a, h->sms, s));
+  h->span_end(s);
   // 4. merge + reorder
+  h->span_begin(3, s);
   MergeArgs m;
-  m.cand = cand;
-  m.cand_cnt = cand_cnt;
-  m.tokens = tokens;
+  m.cand = h->ck.cand;
+  m.cand_cnt = h->ck.cand_cnt;
+  m.tokens = h->ck.tokens;
   m.pt_off = h->pt_off.p;
   m.ids = h->ids.p;
   m.raw = h->raw.p;
   m.stride = h->stride;
-  m.queries = dq;
+  m.queries = h->ck.dq;
   m.dim = static_cast<int>(h->dim);
   m.L = static_cast<int>(L);
   m.R = static_cast<int>(R);
@@ -451,11 +550,16 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
                                   static_cast<int>(msm)));
   merge_reorder_kernel<<<static_cast<unsigned>(nq), 256, msm, s>>>(m);
   SCANN_CUDA(cudaGetLastError());
-  h->mark(s);
-  // center_dist, part_select (or tc_prep_queries, tc_score, part_tc_select), wl_count, wl_scan, wl_scatter, wl_items,
-  // lut16_scan, merge_reorder
-  h->prof_launches += h->ptc.ready ? 9 : 8;
+  h->span_end(s);
+  h->prof_launches += two_phase && tau_in ? 3 : 2;  // (tau_in) + lut16_scan + merge_reorder
   return SCANN_OK;
+}
+
+static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
+                                        uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cand_ids,
+                                        float* d_cand_dists, uint32_t* d_cand_counts, cudaStream_t s) {
+  SCANN_TRY(treeah_phase1(h, dq, nq, L, R, k, false, nullptr, s));
+  return treeah_phase2(h, false, nullptr, d_ids, d_dists, d_counts, d_cand_ids, d_cand_dists, d_cand_counts, s);
 }
 
 static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, size_t R, size_t k, bool host) {
@@ -464,12 +568,12 @@ static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, siz
   auto add = [&](size_t bytes) { b += Workspace::padded(bytes); };
   add(std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0)));
   add(P * 4);
-  add(2 * K * 4);
-  add((K + 1) * 4);
-  add((K + 1) * 4);
+  add(4 * K * 4);
+  add((2 * K + 1) * 4);
+  add((2 * K + 1) * 4);
   add(16);
   add(P * 4);
-  add((P + K + 2) * 16);
+  add((P + 2 * K + 2) * 16);
   add(P * R * 8);
   add(P * 4);
   add(nq * 4);
@@ -691,14 +795,64 @@ scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint
   return SCANN_OK;
 }
 
+// ---- split search for a sharded index: begin = partition + worklist + scan of every query's closest
+// leaf on this shard -> tau_out; the caller min-reduces tau over the shards; end = scan of the rest under the global
+// bounds + merge + exact reorder.  Device pointers only; one chunk (the whole batch) per begin/end pair.
+scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L,
+                                       size_t R, size_t k, float* tau_out, void* stream) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "scann_treeah_search_begin called twice without _end");
+  SCANN_REQUIRE(queries && tau_out && nq >= 1, SCANN_INVALID_ARGUMENT, "NULL buffer or empty batch");
+  SCANN_REQUIRE(qdim == h->dim, SCANN_INVALID_ARGUMENT, "Query dimensionality mismatch");
+  SCANN_REQUIRE(L >= 1 && L <= 1024, SCANN_INVALID_ARGUMENT, "partitions_to_search %zu outside 1..1024", L);
+  SCANN_REQUIRE(R >= 1 && R <= 2048, SCANN_INVALID_ARGUMENT, "pre_reorder_k %zu outside 1..2048", R);
+  SCANN_REQUIRE(k >= 1, SCANN_INVALID_ARGUMENT, "k must be >= 1");
+  if (L > h->K) L = h->K;
+  SCANN_REQUIRE(nq * L * R * 8 <= (size_t(1) << 30) && nq * h->K * 4 <= (size_t(512) << 20), SCANN_INVALID_ARGUMENT,
+                "batch of %zu queries is too large for the split search (split it)", nq);
+  h->mu.lock();
+  DeviceGuard g(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  scann_status st = h->ws.reserve(treeah_chunk_bytes(h, nq, L, R, k, false));
+  if (st == SCANN_OK) {
+    cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s);
+    h->ws.reset();
+    st = treeah_phase1(h, queries, nq, L, R, k, true, tau_out, s);
+  }
+  if (st != SCANN_OK) {
+    h->mu.unlock();
+    return st;
+  }
+  h->split_active = true;  // mu stays locked until _end
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint32_t* ids, float* dists,
+                                     uint32_t* counts, void* stream) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  SCANN_REQUIRE(h->split_active, SCANN_FAILED_PRECONDITION, "scann_treeah_search_end without _begin");
+  scann_status st = SCANN_OK;
+  if (!(ids && dists && counts)) {
+    set_error("NULL buffer");
+    st = SCANN_INVALID_ARGUMENT;
+  } else {
+    DeviceGuard g(h->device);
+    st = treeah_phase2(h, true, tau_in, ids, dists, counts, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  }
+  h->split_active = false;
+  h->mu.unlock();
+  return st;
+}
+
 scann_status scann_treeah_set_profiling(scann_treeah* h, int enable) {
   using namespace scann;
   SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
-  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-  h->prof_events.clear();
+  h->clear_spans();
   h->prof_launches = 0;
   h->profiling = enable != 0;
   return SCANN_OK;
@@ -711,13 +865,11 @@ scann_status scann_treeah_get_profile(scann_treeah* h, double* ms4, uint64_t* ke
   DeviceGuard g(h->device);
   SCANN_CUDA(cudaDeviceSynchronize());
   for (int i = 0; i < 4; ++i) ms4[i] = 0.0;
-  for (size_t c = 0; c + 5 <= h->prof_events.size(); c += 5)
-    for (int i = 0; i < 4; ++i) {
-      float ms = 0.0f;
-      if (cudaEventElapsedTime(&ms, h->prof_events[c + i], h->prof_events[c + i + 1]) == cudaSuccess) ms4[i] += ms;
-    }
-  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-  h->prof_events.clear();
+  for (const scann_treeah::Span& sp : h->prof_spans) {
+    float ms = 0.0f;
+    if (sp.stage >= 0 && sp.stage < 4 && cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) ms4[sp.stage] += ms;
+  }
+  h->clear_spans();
   if (kernel_launches) *kernel_launches = h->prof_launches;
   h->prof_launches = 0;
   return SCANN_OK;

@@ -28,8 +28,15 @@ def sharded_search(searcher, queries, k: int, group=None, **kw):
 
     from . import searchers
 
-    ids, dists, counts = searcher.search_batched(queries, k, **kw)
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return ids, dists, counts
+        return searcher.search_batched(queries, k, **kw)
+    if hasattr(searcher, "search_begin") and getattr(queries, "is_cuda", False):
+        # Tree-AH on a sharded index: every shard scans the queries' closest leaves first, the bounds they prove are
+        # min-reduced over the shards (4 B per query), and the bulk of the scan runs under the global bounds
+        tau = searcher.search_begin(queries, k, **kw)
+        dist.all_reduce(tau, op=dist.ReduceOp.MIN, group=group)
+        ids, dists, counts = searcher.search_end(tau)
+    else:
+        ids, dists, counts = searcher.search_batched(queries, k, **kw)
     gi, gd = all_gather_results(ids, dists, group)
     return searchers.merge_topk(gi, gd, ids.device.index or 0)

@@ -412,6 +412,34 @@ class TreeXHybridSearcher(_Handle):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
 
+    def search_begin(self, queries, k: int, partitions_to_search: Optional[int] = None,
+                     pre_reorder_k: Optional[int] = None):
+        """First half of the split search for a sharded index (scann_treeah_search_begin): torch CUDA queries →
+        tau [nq] f32 CUDA tensor, the bounds proved by every query's closest leaf on this shard (+inf when it lives
+        elsewhere).  Min-reduce tau over the shards and pass it to search_end()."""
+        if not (self._h and self._h.value):
+            raise ScannError(capi.FAILED_PRECONDITION, "searcher not built")
+        b = _Batch(queries, self.device)
+        if not b.device or b.nq == 0:
+            raise ScannError(capi.INVALID_ARGUMENT, "the split search takes a non-empty batch of CUDA queries")
+        torch = _torch()
+        L = int(partitions_to_search if partitions_to_search is not None else self.config.partitions_to_search)
+        R = int(pre_reorder_k if pre_reorder_k is not None else self.config.pre_reorder_k(k))
+        tau = torch.empty((b.nq,), dtype=torch.float32, device=b.arr.device)
+        capi.check(capi.load().scann_treeah_search_begin(self._h, b.ptr, b.nq, b.dim, L, R, k,
+                                                         C.c_void_p(tau.data_ptr()), b.stream))
+        self._split = (b, k)  # keeps the query tensor alive until search_end
+        return tau
+
+    def search_end(self, tau=None):
+        """Second half (scann_treeah_search_end) → (ids, dists, counts) torch CUDA tensors."""
+        b, k = self._split
+        self._split = None
+        ids, dists, counts, pi, pd, pc = b.outputs(k)
+        pt = C.c_void_p(tau.data_ptr()) if tau is not None else None
+        capi.check(capi.load().scann_treeah_search_end(self._h, pt, pi, pd, pc, b.stream))
+        return ids, dists, counts
+
     def set_profiling(self, enable: bool):
         capi.check(capi.load().scann_treeah_set_profiling(self._h, int(enable)))
 

@@ -1,0 +1,113 @@
+"""GPU tests of the two-phase (split) Tree-AH search for a sharded index: scann_treeah_search_begin scans every
+query's closest leaf and returns the bounds it proves; after a min-reduction over the shards,
+scann_treeah_search_end scans the rest under the global bounds.  Two shards are emulated on one GPU (sequentially —
+no kernel waits on another)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _index(oracle, n=60_000, dim=32, K=48, S=16, seed=3):
+    x, _ = helpers.clustered(n, dim, 64, 0.35, seed)
+    return x, helpers.build_index(oracle, x, K, S)
+
+
+def _searcher(pkg, idx, x, L, part_offsets=None, ids=None, packed=None):
+    s = pkg.TreeXHybridSearcher(pkg.TreeXHybridConfig(num_partitions=len(idx["centers"]), partitions_to_search=L))
+    s.build_from_index(idx["centers"], idx["codebook"], packed if packed is not None else idx["packed"],
+                       ids if ids is not None else idx["ids"],
+                       part_offsets if part_offsets is not None else idx["part_offsets"], x)
+    return s
+
+
+def test_split_search_single_shard_equals_plain_search(gpu_lib, oracle):
+    x, idx = _index(oracle)
+    q = torch.tensor(x[:500] + 0.01).cuda()
+    s = _searcher(gpu_lib, idx, x, 8)
+    ids, dists, counts = s.search_batched(q, 10, pre_reorder_k=60)
+    tau = s.search_begin(q, 10, pre_reorder_k=60)
+    assert tau.shape == (500,) and bool(torch.isfinite(tau).all())
+    ids2, dists2, counts2 = s.search_end(tau)
+    torch.cuda.synchronize()
+    assert (ids.cpu() == ids2.cpu()).all() and (dists.cpu() == dists2.cpu()).all() and (counts.cpu() == counts2.cpu()).all()
+    # no bounds at all (tau = None) is also the plain search
+    s.search_begin(q, 10, pre_reorder_k=60)
+    ids3, dists3, _ = s.search_end(None)
+    assert (ids.cpu() == ids3.cpu()).all()
+    # tau is a valid bound: at least R candidates of the full search lie at or below it
+    _, _, _, (ci, cd, cc) = s.search_batched(q, 10, pre_reorder_k=60, want_candidates=True)
+    cd, cc, tau = cd.cpu().numpy(), cc.cpu().numpy(), tau.cpu().numpy()
+    for i in range(500):
+        if cc[i] == 60:
+            assert cd[i, 59] <= tau[i]
+
+
+def test_split_search_protocol_errors(gpu_lib, oracle):
+    x, idx = _index(oracle, n=5000, K=8, S=8)
+    s = _searcher(gpu_lib, idx, x, 4)
+    q = torch.tensor(x[:16]).cuda()
+    with pytest.raises(gpu_lib.ScannError) as e:
+        gpu_lib.capi.check(gpu_lib.capi.load().scann_treeah_search_end(s._h, None, None, None, None, None))
+    assert e.value.code == gpu_lib.capi.FAILED_PRECONDITION
+    s.search_begin(q, 5)
+    with pytest.raises(gpu_lib.ScannError) as e:
+        s.search_begin(q, 5)
+    assert e.value.code == gpu_lib.capi.FAILED_PRECONDITION
+    ids, dists, counts = s.search_end(None)
+    assert ids.shape == (16, 5)
+    with pytest.raises(gpu_lib.ScannError):
+        s.search_begin(x[:16], 5)  # host queries are not accepted by the split path
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_two_phase_sharded_search_is_deterministic_superset(gpu_lib, oracle, world):
+    x, idx = _index(oracle)
+    K = len(idx["centers"])
+    L, R, k = 12, 80, 10
+    qn = (x[1000:1600] + 0.01).astype(np.float32)
+    q = torch.tensor(qn).cuda()
+    full = _searcher(gpu_lib, idx, x, L)
+    fi, fd, fc, (ci, cd, cc) = full.search_batched(q, k, pre_reorder_k=R, want_candidates=True)
+    # whole partitions per shard (bench.py --shard partition)
+    off = idx["part_offsets"].astype(np.int64)
+    shards = []
+    for r in range(world):
+        keep = np.zeros(len(idx["ids"]), bool)
+        cnt = np.zeros(K, np.int64)
+        for leaf in range(K):
+            if leaf % world == r:
+                keep[off[leaf]:off[leaf + 1]] = True
+                cnt[leaf] = off[leaf + 1] - off[leaf]
+        po = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+        shards.append(_searcher(gpu_lib, idx, x, L, po, np.ascontiguousarray(idx["ids"][keep]),
+                                np.ascontiguousarray(idx["packed"][keep])))
+
+    def run():
+        taus = [s.search_begin(q, k, pre_reorder_k=R) for s in shards]
+        tau = torch.stack(taus).min(0).values  # = all_reduce(MIN)
+        outs = [s.search_end(tau) for s in shards]
+        gi = torch.stack([o[0] for o in outs])
+        gd = torch.stack([o[1] for o in outs])
+        mi, md, mc = gpu_lib.merge_topk(gi, gd)
+        torch.cuda.synchronize()
+        return mi.cpu().numpy().view(np.uint32), md.cpu().numpy(), tau.cpu().numpy()
+
+    mi, md, tau = run()
+    mi2, md2, _ = run()
+    assert (mi == mi2).all() and (md.view(np.uint32) == md2.view(np.uint32)).all()  # deterministic
+    # the global bound is valid: the R-th best approximate distance of the unsharded search is <= tau
+    cdn, ccn = cd.cpu().numpy(), cc.cpu().numpy()
+    assert all(cdn[i, R - 1] <= tau[i] for i in range(len(qn)) if ccn[i] == R)
+    # superset: every exact distance of the merged sharded result is <= the unsharded one at the same rank
+    fdn = fd.cpu().numpy()
+    assert (md <= fdn + 0.0).all()
+    # and the plain (unsplit) sharded search gives the same merged result
+    outs = [s.search_batched(q, k, pre_reorder_k=R) for s in shards]
+    pi, pd, _ = gpu_lib.merge_topk(torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]))
+    assert (pd.cpu().numpy() <= fdn).all()
+    rc, gt, _, _ = oracle.bf_search(x, qn, k, oracle.SQL2, nthreads=8)
+    assert helpers.recall(mi, gt, k) >= helpers.recall(fi.cpu().numpy().view(np.uint32), gt, k) - 1e-9

@@ -79,6 +79,26 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, uint32_t a0, uint32_t on
         asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(lo32) : "r"(r), "r"(a0));
         asm volatile("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(hi32) : "r"(r), "r"(sh));
         w[i] = ((unsigned long long)hi32 << 32) | lo32;
+      } else if (MODE == 14) {  // scan mode 3 now: PRMT,PRMT,LOP3 + 2 IDP2A per 4 lookups
+        uint32_t lo, hi, r;
+        asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(x[i]), "r"(y[i]), "r"(sh));
+        asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(y[i]), "r"(x[i]), "r"(sh));
+        asm volatile("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(r) : "r"(one), "r"(lo), "r"(hi));
+        asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(a0), "r"(r));
+        asm volatile("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(y[i]) : "r"(a0), "r"(r));
+      } else if (MODE == 15) {  // candidate: PRMT,PRMT + 4 IDP2A with per-byte weights (no select LOP3)
+        uint32_t lo, hi;
+        asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(lo) : "r"(x[i]), "r"(y[i]), "r"(sh));
+        asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(y[i]), "r"(x[i]), "r"(sh));
+        uint32_t lo32 = (uint32_t)w[i], hi32 = (uint32_t)(w[i] >> 32);
+        asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(lo32) : "r"(a0), "r"(lo));
+        asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(lo32) : "r"(one), "r"(hi));
+        asm volatile("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(hi32) : "r"(a0), "r"(lo));
+        asm volatile("dp2a.hi.u32.u32 %0, %1, %2, %0;" : "+r"(hi32) : "r"(one), "r"(hi));
+        x[i] ^= lo; y[i] ^= hi;
+        w[i] = ((unsigned long long)hi32 << 32) | lo32;
+      } else if (MODE == 16) {  // IDP2A alone
+        asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(y[i]), "r"(one));
       }
     }
   }
@@ -127,6 +147,9 @@ int main() {
     run<12>("2PRMT+LOP3+LOP3+IMAD+IMAD.WIDE", 6, w);
     run<10>("2PRMT+LOP3+IMAD.WIDE+2IDP4A", 6, w);
     run<13>("2PRMT+LOP3+4IDP4A", 7, w);
+    run<16>("IDP2A", 1, w);
+    run<14>("scan mode 3: 2PRMT+LOP3+2IDP2A", 5, w);
+    run<15>("candidate: 2PRMT+4IDP2A(+2LOP3 xor)", 8, w);
   }
   return 0;
 }
