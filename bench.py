@@ -197,12 +197,18 @@ def main():
             leaf_sorted = assign.long()[order]
             if a.shard == "rows":  # round-robin inside each partition
                 keep = ((pos - off[leaf_sorted]) % sw) == sr
-            else:  # whole partitions per GPU, dealt largest-first in snake order so shard sizes balance
-                by_size = torch.argsort(counts, descending=True)
-                slot = torch.arange(K, device=dev) % (2 * sw)
-                owner_sorted = torch.where(slot < sw, slot, 2 * sw - 1 - slot)
-                owner = torch.empty(K, dtype=torch.int64, device=dev)
-                owner[by_size] = owner_sorted
+            else:
+                # whole partitions per GPU.  A leaf's scan load is ~ size (bytes per probe) x size (probes: queries
+                # come from the data distribution), so leaves are dealt largest-first to the shard with the least
+                # accumulated size^2 (greedy LPT) — balances the scanned bytes, not just the row counts
+                cnt_h = counts.cpu().numpy().astype(np.float64)
+                load = np.zeros(sw)
+                owner_h = np.zeros(K, np.int64)
+                for leaf in np.argsort(-cnt_h, kind="stable"):
+                    g = int(np.argmin(load))
+                    owner_h[leaf] = g
+                    load[g] += cnt_h[leaf] ** 2
+                owner = torch.from_numpy(owner_h).to(dev)
                 keep = owner[leaf_sorted] == sr
             order = order[keep]
             cnt = torch.bincount(leaf_sorted[keep], minlength=K)
@@ -275,19 +281,17 @@ def main():
     xchg_events = []  # (start, end) CUDA events around the all-gather + merge of the timed steps
 
     def step_device(qb, timed=False):
-        if world > 1 or a.split:
-            tau = searcher.search_begin(qb, a.k, pre_reorder_k=R)
-            if world > 1:
-                dist.all_reduce(tau, op=dist.ReduceOp.MIN)
-            ids, dists, cnt = searcher.search_end(tau)
+        if world > 1:
+            ids, dists, cnt = pkg.distributed.two_phase_search(searcher, qb, a.k, pre_reorder_k=R)
+        elif a.split:
+            ids, dists, cnt = searcher.search_end(searcher.search_begin(qb, a.k, pre_reorder_k=R))
         else:
             ids, dists, cnt = searcher.search_batched(qb, a.k, pre_reorder_k=R)
         if world > 1:
             if timed:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            gi, gd = pkg.distributed.all_gather_results(ids, dists)
-            ids, dists, cnt = pkg.merge_topk(gi, gd, local_rank)
+            ids, dists, cnt = pkg.distributed.exchange_and_merge(ids, dists)
             if timed:
                 ev[1].record()
                 xchg_events.append(ev)

@@ -144,18 +144,24 @@ scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t n
                                  float* cand_dists, uint32_t* cand_counts, int memspace, void* stream);
 void scann_treeah_destroy(scann_treeah* h);
 /* Split search for a SHARDED index (one process per GPU, every shard sees the whole query batch).
- *   scann_treeah_search_begin: partition -> worklist -> LUT16 scan of every query's CLOSEST leaf when this shard
- *       owns it.  tau_out[q] (device, nq floats) receives the bound that leaf proves: the R-th smallest approximate
- *       distance it holds (+inf when the leaf lives on another shard or has fewer than R points).
+ *   scann_treeah_search_begin: partition -> worklist -> LUT16 probe of every query's CLOSEST leaf when this shard
+ *       owns it (its first 4096 points: any R points prove a bound, and a bounded probe keeps this phase short).
+ *       tau_out[q] (device, nq floats) receives the R-th smallest approximate distance among them (+inf when the
+ *       leaf lives on another shard or the probe saw fewer than R points).
  *   the caller min-reduces tau over the shards (e.g. ncclAllReduce MIN, 4 B per query);
- *   scann_treeah_search_end: scans the remaining leaves under tau_in (device, nq floats, or NULL) — a point above
- *       tau_in[q] cannot be among the global top-R of query q because the closest leaf already holds R points at or
- *       below it — then merges and re-scores exactly as scann_treeah_search does.
+ *   scann_treeah_search_end: scans all probed leaves under tau_in (device, nq floats, or NULL) — a point above
+ *       tau_in[q] cannot be among the global top-R of query q because R points at or below it exist — then merges
+ *       and re-scores exactly as scann_treeah_search does.
  * The bounds are data-defined (not timing-defined), so results are deterministic and every shard's list is a
  * superset of the global top-R restricted to the shard.  Device pointers only; begin/end must be paired on one
  * thread (the handle stays locked in between); the batch must fit one chunk (nq*L*R*8 <= 1 GiB). */
+/* `tokens` (device, nq*L u32, or NULL): the partition stage's output when the caller ran it — e.g. each shard
+ * partitions nq/world queries with scann_treeah_partition and the shards all-gather the tokens, so the stage is
+ * not repeated on every GPU.  The array must stay valid until scann_treeah_search_end returns.  L must be <= K. */
+scann_status scann_treeah_partition(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L,
+                                    uint32_t* tokens, void* stream);
 scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L,
-                                       size_t R, size_t k, float* tau_out, void* stream);
+                                       size_t R, size_t k, const uint32_t* tokens, float* tau_out, void* stream);
 scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint32_t* ids, float* dists,
                                      uint32_t* counts, void* stream);
 /* introspection used by bench.py for the roofline arithmetic: algorithmic code bytes scanned by the
@@ -218,6 +224,10 @@ scann_status scann_pq_encode(const float* codebook, size_t S, size_t ds, const f
 scann_status scann_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
                               uint32_t* ids_out, float* dists_out, uint32_t* counts_out, int device, int memspace,
                               void* stream);
+/* The same merge over ONE gathered device buffer laid out [parts][2][nq][k] (32-bit words): each part is a rank's
+ * ids block followed by its distances block, i.e. the result of a single all-gather of a packed per-rank buffer. */
+scann_status scann_merge_topk_packed(const uint32_t* packed, size_t parts, size_t nq, size_t k, uint32_t* ids_out,
+                                     float* dists_out, uint32_t* counts_out, int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,5 +12,5 @@ from .capi import ScannError, device_count, load  # noqa: F401
 from .scann import Scann, ScannBuilder, ScannConfig, SearchMode  # noqa: F401
 from .searchers import (AsymmetricHasher, AsymmetricHasherConfig, BruteForceSearcher, DistanceMeasure,  # noqa: F401
                         ScalarQuantizedBruteForceSearcher, ScalarQuantizedConfig, TreePartitioner, TreeXHybridConfig,
-                        TreeXHybridSearcher, lut16_build, lut16_scan, merge_topk, pq_encode, results_to_lists,
+                        TreeXHybridSearcher, lut16_build, lut16_scan, merge_topk, merge_topk_packed, pq_encode, results_to_lists,
                         scalar_quantize, tc_scores)

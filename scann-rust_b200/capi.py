@@ -34,8 +34,8 @@ SYMBOLS = [
     "scann_sq8_quantize", "scann_sq8_create", "scann_sq8_search", "scann_sq8_destroy",
     "scann_part_create", "scann_part_select", "scann_part_destroy",
     "scann_treeah_create", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
-    "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end",
-    "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_tc_scores",
+    "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end", "scann_treeah_partition",
+    "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_merge_topk_packed", "scann_tc_scores",
 ]
 
 
@@ -90,7 +90,8 @@ def load():
     L.scann_treeah_destroy.argtypes = [vp]
     L.scann_treeah_destroy.restype = None
     L.scann_treeah_last_scan_bytes.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-    L.scann_treeah_search_begin.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp, vp]
+    L.scann_treeah_search_begin.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp, vp, vp]
+    L.scann_treeah_partition.argtypes = [vp, vp, sz, sz, sz, vp, vp]
     L.scann_treeah_search_end.argtypes = [vp, vp, vp, vp, vp, vp]
     L.scann_treeah_set_profiling.argtypes = [vp, i32]
     L.scann_treeah_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -98,6 +99,7 @@ def load():
     L.scann_lut16_scan.argtypes = [vp, sz, sz, vp, vp, i32, i32]
     L.scann_pq_encode.argtypes = [vp, sz, sz, vp, sz, sz, vp, vp, vp, i32, i32]
     L.scann_merge_topk.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, i32, i32, vp]
+    L.scann_merge_topk_packed.argtypes = [vp, sz, sz, sz, vp, vp, vp, i32, vp]
     L.scann_tc_scores.argtypes = [vp, sz, sz, vp, i32, sz, sz, f32, i32, vp, vp, vp, sz, vp, i32]
     for name in SYMBOLS:
         fn = getattr(L, name)

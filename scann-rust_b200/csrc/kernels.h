@@ -34,8 +34,10 @@ scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, 
 scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists, const uint32_t* cnt,
                                   size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
                                   uint32_t* counts, cudaStream_t s);
+//   part_stride: elements between two parts' blocks (0 = nq * k, the dense [parts][nq][k] layout)
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
-                               uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s);
+                               uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s,
+                               size_t part_stride = 0);
 
 // tc_gemm.cu — tcgen05/TMEM/TMA ranking contraction (bf16 operands, f32 accumulation).  See the file header.
 struct TcScoreParams {

@@ -34,6 +34,8 @@ struct ScanArgs {
   const uint32_t* sorted_pairs;
   uint32_t* counters;  // [0] total items, [1] next item, [2] class-A items (closest-leaf pairs, scanned first)
   int end_idx;         // this launch stops at counters[end_idx]: 0 = every item, 2 = the class-A items only
+  int max_blocks;      // > 0: probe launch — scan only the first max_blocks 256-point blocks of each leaf and publish
+                       // the bound they prove (any R points give a valid bound); candidates are not written
   uint32_t* qthr;      // [nq] f32_key of the best known bound on the R-th approx distance (0xFFFFFFFF = none)
   uint2* cand;         // [P][R] {approx distance bits, position in leaf}
   uint32_t* cand_cnt;  // [P]
@@ -91,8 +93,12 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const Scan
     const uint32_t leaf = it.x, pbeg = it.y;
     const int ng = static_cast<int>(it.z);
     const uint32_t blk0 = a.blk_off[leaf];
-    const int nblk = static_cast<int>(a.blk_off[leaf + 1] - blk0);
-    const uint32_t leaf_n = static_cast<uint32_t>(a.pt_off[leaf + 1] - a.pt_off[leaf]);
+    int nblk = static_cast<int>(a.blk_off[leaf + 1] - blk0);
+    uint32_t leaf_n = static_cast<uint32_t>(a.pt_off[leaf + 1] - a.pt_off[leaf]);
+    if (a.max_blocks > 0 && nblk > a.max_blocks) {
+      nblk = a.max_blocks;
+      leaf_n = static_cast<uint32_t>(nblk) * kBlockPts;
+    }
 
     // (1) query residuals: q - centroid (src/tree_x_hybrid/mod.rs:309-316)
     for (int idx = tid; idx < G * a.dim; idx += NW * 32) {
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const Scan
     }
 
     // (6) write this item's candidates: approx distance = sum*multiplier + bias*S (lut16_simd.rs:136-140)
+    if (a.max_blocks > 0) continue;  // probe launch: only the bounds matter
     for (int g = warp; g < ng; g += NW) {
       const int c = static_cast<int>(min(s_cnt[g], static_cast<uint32_t>(a.R)));
       const uint32_t pair = s_pair[g];

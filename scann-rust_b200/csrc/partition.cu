@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256) part_select_kernel(const float* __restric
 // ---- tensor-core centroid scoring (tc_gemm.cu) + exact top-L -------------------------------------------------------
 // The north-star shape of this stage: the query x centroid contraction runs on tcgen05 (bf16 operands, f32 TMEM
 // accumulators) and produces RANKING scores v = |c|^2/2 - q~.c~ = (|q - c|^2 - |q|^2)/2 + rounding.  One warp per query
-// then (1) radix-selects the L-th smallest score v_L, (2) keeps every centre with v <= v_L + 2*eps (eps = rigorous
+// then (1) bounds the L-th smallest score v_L from above with a 256-bucket histogram of the row (vU >= v_L),
+// (2) keeps every centre with v <= vU + 2*eps (eps = rigorous
 // bound on |v - exact|, as in brute_force.cu: any centre outside the set is beaten by L centres inside it), (3) scores
 // the ~L survivors exactly in the reference's sequential un-fused order (tree_partitioner.rs:175-192) and (4) sorts them
 // by (distance, id) = the reference's stable sort.  Tokens and distances are bit-identical to the exact kernel's.
@@ -134,17 +135,33 @@ __global__ void __launch_bounds__(kPtWarps * 32) part_tc_select_kernel(
   const int Leff = L < K ? L : K;
   const float inf = __int_as_float(0x7F800000);
 
-  // (1) L-th smallest ranking score: 4 x 8-bit radix passes over the row (L2-resident)
-  uint32_t prefix = 0, mask = 0, need = static_cast<uint32_t>(Leff);
-  for (int shift = 24; shift >= 0; shift -= 8) {
+  // (1) an upper bound vU of the L-th smallest ranking score from one 256-bucket linear histogram of the row
+  //     (min/max pass, histogram pass): the bucket that holds the L-th smallest score ends at vU >= v_L
+  float mn = inf, mx = -inf;
+  for (int i = lane; i < K; i += 32) {
+    const float v = row[i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
-    __syncwarp();
-    for (int i = lane; i < K; i += 32) {
-      const uint32_t k = f32_key(row[i]);
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-    }
-    __syncwarp();
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+  }
+  const float width = (mx - mn) * (1.0f / 256.0f);
+  const float scale = width > 0.0f ? 1.0f / width : 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
+  __syncwarp();
+  for (int i = lane; i < K; i += 32) {
+    const float v = row[i];
+    int b = 255;
+    if (v == v) b = min(255, max(0, static_cast<int>((v - mn) * scale)));
+    atomicAdd(&hist[b], 1u);
+  }
+  __syncwarp();
+  int bL = 255;
+  {
     uint32_t h[8], s = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -157,9 +174,9 @@ __global__ void __launch_bounds__(kPtWarps * 32) part_tc_select_kernel(
       const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
       if (lane >= o) incl += v;
     }
-    const uint32_t excl = incl - s;
+    const uint32_t excl = incl - s, need = static_cast<uint32_t>(Leff);
     const bool mine = (excl < need) && (need <= incl);
-    uint32_t dg = 0, below = 0;
+    int dg = 255;
     if (mine) {
       uint32_t run = excl;
       bool found = false;
@@ -167,27 +184,22 @@ __global__ void __launch_bounds__(kPtWarps * 32) part_tc_select_kernel(
       for (int j = 0; j < 8; ++j) {
         if (!found && run + h[j] >= need) {
           dg = lane * 8 + j;
-          below = run;
           found = true;
         }
         if (!found) run += h[j];
       }
     }
-    const uint32_t owner = __ffs(__ballot_sync(0xFFFFFFFFu, mine)) - 1;
-    dg = __shfl_sync(0xFFFFFFFFu, dg, owner);
-    below = __shfl_sync(0xFFFFFFFFu, below, owner);
-    need -= below;
-    prefix |= dg << shift;
-    mask |= 0xFFu << shift;
-    __syncwarp();
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
+    if (bal) bL = __shfl_sync(0xFFFFFFFFu, dg, __ffs(bal) - 1);
   }
+  // every score of buckets 0..bL is below this edge (the slack covers the rounding of the bucket arithmetic)
+  const float vU = mn + static_cast<float>(bL + 1) * width * 1.00001f + (fabsf(mn) + fabsf(mx)) * 1e-6f;
   // (2) certified threshold (same bound as bf_thr_kernel in brute_force.cu)
-  const float vL = key_f32(prefix);
   const float nqr = sqrtf(qn[q]), nx = sqrtf(cmax2);
   const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
-  float thr = vL + 2.0f * eps;
+  float thr = vU + 2.0f * eps;
   thr = thr + fabsf(thr) * 1e-6f;
-  if (!(thr == thr)) thr = inf;
+  if (!(thr == thr) || bL == 255) thr = inf;
 
   // (3) survivors
   int m = 0;

@@ -151,7 +151,7 @@ scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists
 // ---- multi-GPU merge: [parts][nq][k] -> [nq][k] by (distance, id) -----------------
 __global__ void __launch_bounds__(128) merge_topk_kernel(const uint32_t* __restrict__ ids_in,
                                                          const float* __restrict__ dists_in, int parts, size_t nq,
-                                                         int k, uint32_t* __restrict__ ids_out,
+                                                         size_t part_stride, int k, uint32_t* __restrict__ ids_out,
                                                          float* __restrict__ dists_out,
                                                          uint32_t* __restrict__ counts_out) {
   extern __shared__ __align__(16) uint8_t sm[];
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint32_t* __restr
     uint64_t key = ~0ull;
     if (i < total) {
       int part = i / k, j = i - part * k;
-      size_t src = (static_cast<size_t>(part) * nq + q) * k + j;
+      size_t src = static_cast<size_t>(part) * part_stride + q * k + j;
       uint32_t id = ids_in[src];
       if (id != 0xFFFFFFFFu) key = (static_cast<uint64_t>(f32_key(dists_in[src])) << 32) | id;
     }
@@ -187,7 +187,9 @@ __global__ void __launch_bounds__(128) merge_topk_kernel(const uint32_t* __restr
 }
 
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
-                               uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s) {
+                               uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s,
+                               size_t part_stride) {
+  if (part_stride == 0) part_stride = nq * k;
   if (nq == 0 || k == 0) return SCANN_OK;
   SCANN_REQUIRE(parts * k <= 8192, SCANN_INVALID_ARGUMENT, "parts*k = %zu too large for the merge kernel", parts * k);
   int p2 = next_pow2(static_cast<int>(parts * k));
@@ -196,7 +198,8 @@ scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, si
     SCANN_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
   merge_topk_kernel<<<static_cast<unsigned>(nq), 128, smem, s>>>(ids_in, dists_in, static_cast<int>(parts), nq,
-                                                                 static_cast<int>(k), ids_out, dists_out, counts_out);
+                                                                 part_stride, static_cast<int>(k), ids_out, dists_out,
+                                                                 counts_out);
   SCANN_CUDA(cudaGetLastError());
   return SCANN_OK;
 }
@@ -229,6 +232,18 @@ scann_status scann_merge_topk(const uint32_t* ids_in, const float* dists_in, siz
   if (counts_out) SCANN_CUDA(cudaMemcpyAsync(counts_out, d_c.p, nq * 4, cudaMemcpyDeviceToHost, s));
   SCANN_CUDA(cudaStreamSynchronize(s));
   return SCANN_OK;
+}
+
+
+scann_status scann_merge_topk_packed(const uint32_t* packed, size_t parts, size_t nq, size_t k, uint32_t* ids_out,
+                                     float* dists_out, uint32_t* counts_out, int device, void* stream) {
+  using namespace scann;
+  if (nq == 0 || k == 0) return SCANN_OK;
+  SCANN_REQUIRE(packed && ids_out && dists_out && parts >= 1, SCANN_INVALID_ARGUMENT, "NULL buffer");
+  SCANN_TRY(check_device(device));
+  DeviceGuard g(device);
+  return launch_merge_topk(packed, reinterpret_cast<const float*>(packed + nq * k), parts, nq, k, ids_out, dists_out,
+                           counts_out, static_cast<cudaStream_t>(stream), 2 * nq * k);
 }
 
 }  // extern "C"

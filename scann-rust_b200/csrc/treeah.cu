@@ -202,8 +202,10 @@ struct MergeArgs {
 };
 
 constexpr int kMergeChunk = 2048;
+constexpr int kMergeThreads = 128;
 
-__global__ void __launch_bounds__(256) merge_reorder_kernel(const MergeArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int p2 = next_pow2(a.R < 1 ? 1 : a.R);
   uint64_t* buf = reinterpret_cast<uint64_t*>(sm);              // [R + chunk]
@@ -215,15 +217,28 @@ __global__ void __launch_bounds__(256) merge_reorder_kernel(const MergeArgs a) {
   const int tid = threadIdx.x;
   const size_t q = blockIdx.x;
 
-  for (int r = tid; r < a.L; r += 256) {
+  for (int r = tid; r < a.L; r += NT) {
     uint32_t leaf = a.tokens[q * a.L + r];
     prefix[r + 1] = leaf < a.K ? a.cand_cnt[q * a.L + r] : 0u;
   }
-  for (int d = tid; d < a.dim; d += 256) qs[d] = a.queries[q * a.dim + d];
+  for (int d = tid; d < a.dim; d += NT) qs[d] = a.queries[q * a.dim + d];
   __syncthreads();
-  if (tid == 0) {
-    prefix[0] = 0;
-    for (int r = 0; r < a.L; ++r) prefix[r + 1] += prefix[r];
+  if (tid < 32) {  // inclusive scan of the per-leaf candidate counts by one warp
+    const int per = (a.L + 31) / 32, b = tid * per, e = min(a.L, b + per);
+    uint32_t sum = 0;
+    for (int r = b; r < e; ++r) sum += prefix[r + 1];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (tid >= o) incl += v;
+    }
+    uint32_t run = incl - sum;
+    for (int r = b; r < e; ++r) {
+      run += prefix[r + 1];
+      prefix[r + 1] = run;
+    }
+    if (tid == 0) prefix[0] = 0;
   }
   __syncthreads();
   const int total = static_cast<int>(prefix[a.L]);
@@ -238,10 +253,10 @@ __global__ void __launch_bounds__(256) merge_reorder_kernel(const MergeArgs a) {
     uint2 c = cq[static_cast<size_t>(lo) * a.R + (i - prefix[lo])];
     return (static_cast<uint64_t>(f32_key(__uint_as_float(c.x))) << 32) | (static_cast<uint64_t>(lo) << 22) | c.y;
   };
-  const int m = block_topr_sorted<256, kMergeChunk>(gen, total, a.R, buf, out, hist);
+  const int m = block_topr_sorted<NT, kMergeChunk>(gen, total, a.R, buf, out, hist);
 
   // the R approximate candidates, in (approx distance, leaf rank, position) order
-  for (int j = tid; j < p2; j += 256) {
+  for (int j = tid; j < p2; j += NT) {
     uint32_t id = 0xFFFFFFFFu;
     float ad = __int_as_float(0x7F800000);
     if (j < m) {
@@ -264,23 +279,23 @@ __global__ void __launch_bounds__(256) merge_reorder_kernel(const MergeArgs a) {
   if (a.raw != nullptr) {
     // exact distance of every candidate row, 8 lanes per row (src/tree_x_hybrid/mod.rs:342-364)
     const int grp = tid >> 3, sub = tid & 7;
-    for (int j0 = 0; j0 < m; j0 += 32) {
+    for (int j0 = 0; j0 < m; j0 += NT / 8) {
       int j = j0 + grp;
       bool valid = j < m;
       const float* row = a.raw + static_cast<size_t>(valid ? cid[j] : cid[0]) * a.stride;
       float d = exact_pair_distance<false>(qs, row, a.dim, a.measure, 0.0f, sub);
       if (valid && sub == 0) fin[j] = (static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(j);
     }
-    for (int j = m + tid; j < p2; j += 256) fin[j] = ~0ull;
+    for (int j = m + tid; j < p2; j += NT) fin[j] = ~0ull;
     __syncthreads();
-    block_bitonic_sort<256>(fin, p2);  // stable by construction: ties broken by approximate rank j
+    block_bitonic_sort<NT>(fin, p2);  // stable by construction: ties broken by approximate rank j
   } else {
-    for (int j = tid; j < p2; j += 256)
+    for (int j = tid; j < p2; j += NT)
       fin[j] = j < m ? ((out[j] & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>(j)) : ~0ull;
     __syncthreads();
   }
   const int kk = a.k < m ? a.k : m;
-  for (int j = tid; j < a.k; j += 256) {
+  for (int j = tid; j < a.k; j += NT) {
     if (j < kk) {
       uint64_t key = fin[j];
       a.out_ids[q * a.k + j] = cid[key & 0xFFFFFFFFu];
@@ -398,6 +413,8 @@ static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
   }
 }
 
+constexpr int kProbeBlocks = 16;  // 4096 points
+
 static scann_status launch_scan_g(int G, const ScanArgs& a, int sms, cudaStream_t s) {
   switch (G) {
     case 8: return launch_scan<8>(a, sms, s);
@@ -410,7 +427,7 @@ static scann_status launch_scan_g(int G, const ScanArgs& a, int sms, cudaStream_
 // Phase 1 of a chunk: partition -> worklist -> (two_phase: scan of the class-A items, i.e. every query's closest leaf
 // on this shard; tau_out receives the bounds they prove).  State for phase 2 stays in h->ck / the workspace.
 static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
-                                  bool two_phase, float* tau_out, cudaStream_t s) {
+                                  bool two_phase, float* tau_out, const uint32_t* tokens_in, cudaStream_t s) {
   const size_t K = h->K, P = nq * L;
   // group size: how many queries share a leaf on average
   double avg = static_cast<double>(P) / static_cast<double>(std::min<size_t>(K, P));
@@ -420,6 +437,7 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   float* scratch = reinterpret_cast<float*>(h->ws.take<uint8_t>(
       std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0))));
   uint32_t* tokens = h->ws.take<uint32_t>(P);
+  if (tokens_in) tokens = const_cast<uint32_t*>(tokens_in);  // the caller partitioned (and keeps the array alive)
   uint32_t* leaf_cnt = h->ws.take<uint32_t>(4 * K);  // counts + cursors of the 2K virtual leaves
   uint32_t* cursor = leaf_cnt + 2 * K;
   uint32_t* pair_start = h->ws.take<uint32_t>(2 * K + 1);
@@ -433,10 +451,12 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
 
   // 1. partition (K == 1 still goes through it: one centre, token 0)
   h->span_begin(0, s);
-  if (h->ptc.ready)
+  if (tokens_in) {
+  } else if (h->ptc.ready) {
     SCANN_TRY(launch_partition_tc(h->ptc, h->centers.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, h->sms, s));
-  else
+  } else {
     SCANN_TRY(launch_partition(h->centersT.p, K, h->dim, dq, nq, L, tokens, nullptr, scratch, s));
+  }
   h->span_end(s);
   // 2. worklist
   h->span_begin(1, s);
@@ -466,6 +486,7 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   a.sorted_pairs = sorted_pairs;
   a.counters = counters;
   a.end_idx = 0;
+  a.max_blocks = 0;
   a.cand = cand;
   a.cand_cnt = cand_cnt;
   a.qthr = qthr;
@@ -494,9 +515,11 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   h->ck.qthr = qthr;
   h->prof_launches += h->ptc.ready ? 7 : 6;  // partition (2 or 3 kernels) + 4 worklist kernels
   if (two_phase) {
-    // 3a. scan of the class-A items only
+    // 3a. probe of the class-A items: the first kProbeBlocks blocks of every query's closest leaf prove a bound in
+    // bounded time (a full scan of the largest leaves would serialise on a few CTAs); phase 2 scans them in full
     h->span_begin(2, s);
     a.end_idx = 2;
+    a.max_blocks = kProbeBlocks;
     SCANN_TRY(launch_scan_g(h->ck.G, a, h->sms, s));
     if (tau_out) tau_out_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(qthr, nq, tau_out);
     SCANN_CUDA(cudaGetLastError());
@@ -515,11 +538,11 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
   ScanArgs& a = h->ck.a;
   h->span_begin(2, s);
   if (two_phase) {
-    // the item counter overshot the class-A range by one fetch per CTA: restart it at the first class-B item
-    SCANN_CUDA(cudaMemcpyAsync(h->ck.counters + 1, h->ck.counters + 2, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    SCANN_CUDA(cudaMemsetAsync(h->ck.counters + 1, 0, sizeof(uint32_t), s));  // restart the item counter
     if (tau_in) tau_in_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(tau_in, nq, h->ck.qthr);
   }
   a.end_idx = 0;
+  a.max_blocks = 0;
   SCANN_TRY(launch_scan_g(h->ck.G, a, h->sms, s));
   h->span_end(s);
   // 4. merge + reorder
@@ -546,9 +569,10 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
   m.cand_dists = d_cand_dists;
   m.cand_counts = d_cand_counts;
   size_t msm = merge_smem_bytes(static_cast<int>(R), static_cast<int>(L), static_cast<int>(h->dim));
-  SCANN_CUDA(cudaFuncSetAttribute(merge_reorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  // candidates per query after pruning are few: 128 threads per query keep more queries in flight per SM
+  SCANN_CUDA(cudaFuncSetAttribute(merge_reorder_kernel<kMergeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(msm)));
-  merge_reorder_kernel<<<static_cast<unsigned>(nq), 256, msm, s>>>(m);
+  merge_reorder_kernel<kMergeThreads><<<static_cast<unsigned>(nq), kMergeThreads, msm, s>>>(m);
   SCANN_CUDA(cudaGetLastError());
   h->span_end(s);
   h->prof_launches += two_phase && tau_in ? 3 : 2;  // (tau_in) + lut16_scan + merge_reorder
@@ -558,7 +582,7 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
 static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
                                         uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cand_ids,
                                         float* d_cand_dists, uint32_t* d_cand_counts, cudaStream_t s) {
-  SCANN_TRY(treeah_phase1(h, dq, nq, L, R, k, false, nullptr, s));
+  SCANN_TRY(treeah_phase1(h, dq, nq, L, R, k, false, nullptr, nullptr, s));
   return treeah_phase2(h, false, nullptr, d_ids, d_dists, d_counts, d_cand_ids, d_cand_dists, d_cand_counts, s);
 }
 
@@ -798,8 +822,33 @@ scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint
 // ---- split search for a sharded index: begin = partition + worklist + scan of every query's closest
 // leaf on this shard -> tau_out; the caller min-reduces tau over the shards; end = scan of the rest under the global
 // bounds + merge + exact reorder.  Device pointers only; one chunk (the whole batch) per begin/end pair.
+// TreePartitioner::partition of the handle's own centres for a slice of the batch (device pointers): lets a sharded
+// deployment partition nq/world queries per GPU and all-gather the tokens instead of repeating the stage on every GPU.
+scann_status scann_treeah_partition(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L,
+                                    uint32_t* tokens, void* stream) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  if (nq == 0) return SCANN_OK;
+  SCANN_REQUIRE(queries && tokens, SCANN_INVALID_ARGUMENT, "NULL buffer");
+  SCANN_REQUIRE(qdim == h->dim, SCANN_INVALID_ARGUMENT, "Query dimensionality mismatch");
+  SCANN_REQUIRE(L >= 1 && L <= 1024, SCANN_INVALID_ARGUMENT, "partitions_to_search %zu outside 1..1024", L);
+  SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "a split search is in flight on this handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t K = h->K;
+  const size_t Leff = std::min(L, K);
+  SCANN_REQUIRE(Leff == L, SCANN_INVALID_ARGUMENT, "partitions_to_search %zu > %zu partitions", L, K);
+  const size_t need = std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0)) + 4096;
+  SCANN_TRY(h->ws.reserve(need));
+  float* scratch = reinterpret_cast<float*>(h->ws.take<uint8_t>(need - 4096));
+  if (h->ptc.ready)
+    return launch_partition_tc(h->ptc, h->centers.p, K, h->dim, queries, nq, L, tokens, nullptr, scratch, h->sms, s);
+  return launch_partition(h->centersT.p, K, h->dim, queries, nq, L, tokens, nullptr, scratch, s);
+}
+
 scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L,
-                                       size_t R, size_t k, float* tau_out, void* stream) {
+                                       size_t R, size_t k, const uint32_t* tokens, float* tau_out, void* stream) {
   using namespace scann;
   SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
   SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "scann_treeah_search_begin called twice without _end");
@@ -818,7 +867,7 @@ scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, si
   if (st == SCANN_OK) {
     cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s);
     h->ws.reset();
-    st = treeah_phase1(h, queries, nq, L, R, k, true, tau_out, s);
+    st = treeah_phase1(h, queries, nq, L, R, k, true, tau_out, tokens, s);
   }
   if (st != SCANN_OK) {
     h->mu.unlock();

@@ -85,8 +85,10 @@ class _Batch:
         if self.device:
             torch = _torch()
             dev = self.arr.device
-            ids = torch.empty((self.nq, k), dtype=torch.int32, device=dev)
-            dists = torch.empty((self.nq, k), dtype=torch.float32, device=dev)
+            # one buffer [2, nq, k]: ids block + distances block, so a sharded deployment exchanges results with a
+            # single all-gather (distributed.all_gather_packed)
+            packed = torch.empty((2, self.nq, k), dtype=torch.int32, device=dev)
+            ids, dists = packed[0], packed[1].view(torch.float32)
             counts = torch.empty((self.nq,), dtype=torch.int32, device=dev)
             return ids, dists, counts, C.c_void_p(ids.data_ptr()), C.c_void_p(dists.data_ptr()), \
                 C.c_void_p(counts.data_ptr())
@@ -412,8 +414,20 @@ class TreeXHybridSearcher(_Handle):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
 
+    def partition_tokens(self, queries, partitions_to_search: Optional[int] = None):
+        """The partition stage alone (scann_treeah_partition) for a slice of a batch: torch CUDA queries [m, dim] →
+        tokens [m, L] int32 CUDA tensor."""
+        b = _Batch(queries, self.device)
+        torch = _torch()
+        L = int(partitions_to_search if partitions_to_search is not None else self.config.partitions_to_search)
+        tok = torch.empty((b.nq, L), dtype=torch.int32, device=b.arr.device)
+        if b.nq:
+            capi.check(capi.load().scann_treeah_partition(self._h, b.ptr, b.nq, b.dim, L, C.c_void_p(tok.data_ptr()),
+                                                          b.stream))
+        return tok
+
     def search_begin(self, queries, k: int, partitions_to_search: Optional[int] = None,
-                     pre_reorder_k: Optional[int] = None):
+                     pre_reorder_k: Optional[int] = None, tokens=None):
         """First half of the split search for a sharded index (scann_treeah_search_begin): torch CUDA queries →
         tau [nq] f32 CUDA tensor, the bounds proved by every query's closest leaf on this shard (+inf when it lives
         elsewhere).  Min-reduce tau over the shards and pass it to search_end()."""
@@ -426,18 +440,23 @@ class TreeXHybridSearcher(_Handle):
         L = int(partitions_to_search if partitions_to_search is not None else self.config.partitions_to_search)
         R = int(pre_reorder_k if pre_reorder_k is not None else self.config.pre_reorder_k(k))
         tau = torch.empty((b.nq,), dtype=torch.float32, device=b.arr.device)
-        capi.check(capi.load().scann_treeah_search_begin(self._h, b.ptr, b.nq, b.dim, L, R, k,
+        ptok = None
+        if tokens is not None:
+            tokens = tokens.contiguous()
+            assert tuple(tokens.shape) == (b.nq, L) and tokens.dtype == torch.int32 and tokens.is_cuda
+            ptok = C.c_void_p(tokens.data_ptr())
+        capi.check(capi.load().scann_treeah_search_begin(self._h, b.ptr, b.nq, b.dim, L, R, k, ptok,
                                                          C.c_void_p(tau.data_ptr()), b.stream))
-        self._split = (b, k)  # keeps the query tensor alive until search_end
+        self._split = (b, k, tokens)  # keeps the query and token tensors alive until search_end
         return tau
 
     def search_end(self, tau=None):
         """Second half (scann_treeah_search_end) → (ids, dists, counts) torch CUDA tensors."""
-        b, k = self._split
-        self._split = None
+        b, k, _tokens = self._split
         ids, dists, counts, pi, pd, pc = b.outputs(k)
         pt = C.c_void_p(tau.data_ptr()) if tau is not None else None
         capi.check(capi.load().scann_treeah_search_end(self._h, pt, pi, pd, pc, b.stream))
+        self._split = None
         return ids, dists, counts
 
     def set_profiling(self, enable: bool):
@@ -516,6 +535,22 @@ def merge_topk(ids_parts, dists_parts, device: int = 0):
     oi, od, oc = np.empty((nq, k), np.uint32), np.empty((nq, k), np.float32), np.zeros(nq, np.uint32)
     capi.check(capi.load().scann_merge_topk(capi.np_ptr(ii), capi.np_ptr(dd), parts, nq, k, capi.np_ptr(oi),
                                             capi.np_ptr(od), capi.np_ptr(oc), device, capi.HOST, None))
+    return oi, od, oc
+
+
+def merge_topk_packed(gathered, device: int = 0):
+    """merge_topk over ONE gathered CUDA buffer [parts, 2, nq, k] int32 (ids block + distance bits block per part)."""
+    capi.require_gpu()
+    torch = _torch()
+    parts, two, nq, k = gathered.shape
+    assert two == 2 and gathered.is_cuda and gathered.dtype == torch.int32 and gathered.is_contiguous()
+    oi = torch.empty((nq, k), dtype=torch.int32, device=gathered.device)
+    od = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
+    oc = torch.empty((nq,), dtype=torch.int32, device=gathered.device)
+    dev = gathered.device.index or 0
+    capi.check(capi.load().scann_merge_topk_packed(C.c_void_p(gathered.data_ptr()), parts, nq, k,
+                                                   C.c_void_p(oi.data_ptr()), C.c_void_p(od.data_ptr()),
+                                                   C.c_void_p(oc.data_ptr()), dev, _stream_ptr(dev)))
     return oi, od, oc
 
 

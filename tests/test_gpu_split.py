@@ -46,12 +46,27 @@ def test_split_search_single_shard_equals_plain_search(gpu_lib, oracle):
             assert cd[i, 59] <= tau[i]
 
 
+def test_split_search_with_gathered_tokens(gpu_lib, oracle):
+    x, idx = _index(oracle)
+    q = torch.tensor(x[2000:2512] + 0.01).cuda()
+    s = _searcher(gpu_lib, idx, x, 8)
+    ids, dists, counts = s.search_batched(q, 10, pre_reorder_k=60)
+    # four "ranks" partition a quarter of the batch each; the concatenation is the all-gather
+    tokens = torch.cat([s.partition_tokens(q[r * 128:(r + 1) * 128], 8) for r in range(4)])
+    otok, _ = oracle.partition(idx["centers"], q.cpu().numpy(), 8)
+    assert (tokens.cpu().numpy().view(np.uint32) == otok).all()
+    tau = s.search_begin(q, 10, pre_reorder_k=60, tokens=tokens)
+    ids2, dists2, counts2 = s.search_end(tau)
+    torch.cuda.synchronize()
+    assert (ids.cpu() == ids2.cpu()).all() and (dists.cpu() == dists2.cpu()).all()
+
+
 def test_split_search_protocol_errors(gpu_lib, oracle):
     x, idx = _index(oracle, n=5000, K=8, S=8)
     s = _searcher(gpu_lib, idx, x, 4)
     q = torch.tensor(x[:16]).cuda()
     with pytest.raises(gpu_lib.ScannError) as e:
-        gpu_lib.capi.check(gpu_lib.capi.load().scann_treeah_search_end(s._h, None, None, None, None, None))
+        gpu_lib.capi.check(gpu_lib.capi.load().scann_treeah_search_end(s._h, None, None, None, None, None))  # no begin
     assert e.value.code == gpu_lib.capi.FAILED_PRECONDITION
     s.search_begin(q, 5)
     with pytest.raises(gpu_lib.ScannError) as e:

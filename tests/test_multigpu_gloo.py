@@ -76,3 +76,71 @@ def test_two_rank_sharded_search_and_merge():
     _, ids1, d1, _ = oracle.treex_search(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"], x,
                                          q, 4, 40, 10)
     assert (r0["dists"] <= d1 + 1e-7).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# two_phase_search plumbing (token slices all-gathered, bounds min-reduced) with a CPU stand-in for the GPU searcher
+class _StubSearcher:
+    """Implements the searcher protocol of distributed.two_phase_search on the CPU: tokens via the oracle's
+    partitioner, bounds = rank-dependent floats, results = what the oracle finds on this rank's shard."""
+
+    class config:
+        partitions_to_search = 4
+
+    def __init__(self, oracle, sh, x, rank):
+        self.oracle, self.sh, self.x, self.rank = oracle, sh, x, rank
+        self.seen = {}
+
+    def partition_tokens(self, queries, L):
+        tok, _ = self.oracle.partition(self.sh["centers"], queries.numpy(), L)
+        return torch.from_numpy(tok.view(np.int32).copy())
+
+    def search_begin(self, queries, k, partitions_to_search=None, pre_reorder_k=None, tokens=None):
+        self.seen["tokens"] = tokens.numpy().copy()
+        self.q, self.k, self.R = queries.numpy(), k, pre_reorder_k
+        nq = queries.shape[0]
+        return torch.arange(nq, dtype=torch.float32) + (100.0 if self.rank == 0 else -1.0) * (torch.arange(nq) % 2)
+
+    def search_end(self, tau):
+        self.seen["tau"] = tau.numpy().copy()
+        _, ids, dists, counts = self.oracle.treex_search(self.sh["centers"], self.sh["codebook"], self.sh["part_offsets"],
+                                                         self.sh["ids"], self.sh["packed"], self.x, self.q, 4, self.R, self.k)
+        return torch.from_numpy(ids.view(np.int32)), torch.from_numpy(dists), torch.from_numpy(counts.view(np.int32))
+
+
+def _worker2(rank, world, init_file, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    import oracle
+
+    pkg = importlib.import_module("scann-rust_b200")
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    x, _ = helpers.clustered(6000, 32, 16, 0.3, 2)
+    q = torch.from_numpy((x[:48] + 0.02).astype(np.float32))
+    idx = helpers.build_index(oracle, x, 12, 8)
+    stub = _StubSearcher(oracle, pkg.indexing.shard_index(idx, rank, world), x, rank)
+    ids, dists, counts = pkg.distributed.two_phase_search(stub, q, 10, pre_reorder_k=40)
+    np.savez(os.path.join(out_dir, f"tp{rank}.npz"), tokens=stub.seen["tokens"], tau=stub.seen["tau"], ids=ids.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_phase_plumbing_gloo():
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker2, args=(world, os.path.join(d, "init"), d), nprocs=world, join=True)
+        r0, r1 = np.load(os.path.join(d, "tp0.npz")), np.load(os.path.join(d, "tp1.npz"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    import oracle
+    x, _ = helpers.clustered(6000, 32, 16, 0.3, 2)
+    idx = helpers.build_index(oracle, x, 12, 8)
+    otok, _ = oracle.partition(idx["centers"], (x[:48] + 0.02).astype(np.float32), 4)
+    # every rank saw the tokens of the WHOLE batch (its own slice + the gathered ones), in query order
+    assert (r0["tokens"].view(np.uint32) == otok).all() and (r1["tokens"].view(np.uint32) == otok).all()
+    # and the element-wise minimum of the two ranks' bounds
+    n = np.arange(48, dtype=np.float32)
+    want = np.minimum(n + 100.0 * (np.arange(48) % 2), n - 1.0 * (np.arange(48) % 2))
+    assert (r0["tau"] == want).all() and (r1["tau"] == want).all()
