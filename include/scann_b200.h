@@ -64,6 +64,7 @@ typedef struct scann_bf scann_bf;         /* BruteForceSearcher<f32>            
 typedef struct scann_sq8 scann_sq8;       /* ScalarQuantizedBruteForceSearcher           */
 typedef struct scann_part scann_part;     /* TreePartitioner (query side)                */
 typedef struct scann_treeah scann_treeah; /* TreeXHybridSearcher / AsymmetricHasher LUT16 */
+typedef struct scann_ivf scann_ivf;       /* Scann façade tree modes: Partitioned, TreeAH variant B */
 
 const char* scann_last_error(void);
 int scann_version(void);
@@ -173,6 +174,30 @@ scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint
  * lut16 scan, merge+reorder} and the number of kernel launches, and resets the accumulators. */
 scann_status scann_treeah_set_profiling(scann_treeah* h, int enable);
 scann_status scann_treeah_get_profile(scann_treeah* h, double* ms4, uint64_t* kernel_launches);
+
+/* ---------------------------------------------------------------------------------------------
+ * The Scann façade's tree modes that score EVERY member of the probed leaves (src/scann.rs:175-294)
+ *   scann_ivf_create ← what Scann::with_config leaves behind for SearchMode::Partitioned / TreeAH (:70-137):
+ *       centers[K*dim]; ids[n] = TreePartitioner::partition_indices concatenated; part_offsets[K+1];
+ *       raw[num_raw*stride] (DenseDataset::raw_data, may be NULL for TreeAH without reorder);
+ *       codebook[S*C*ds] + codes_by_id[num_raw*S] = AsymmetricHasher's global (non-residual) codebook and
+ *       encoded_database (hashes/hasher.rs:109-160), C <= 256 codes per block, or both NULL.
+ *   scann_ivf_search, mode 0 ← Scann::search_partitioned (:215-253): partition → exact `measure` distance of every
+ *       member of the L leaves (single-pair AVX2 order, bit-identical) → stable sort → first k.
+ *   scann_ivf_search, mode 1 ← Scann::search_tree_ah (:256-294): partition → one f32 LookupTable of the query
+ *       (hashes/lut.rs:47-82) → sequential f32 sum per member → stable sort → first k.  K = 1, L = 1 is the scoring
+ *       of AsymmetricHasher::search (hashes/hasher.rs:162-185).
+ *   reorder_measure >= 0 ← ReorderingHelper::reorder (utils/reordering.rs:23-54) of the k results as
+ *       Scann::search_impl applies it (:198-209); -1 = off.
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_ivf_create(const float* centers, size_t K, size_t dim, const uint32_t* ids,
+                              const uint64_t* part_offsets, size_t n, const float* raw, size_t num_raw, size_t stride,
+                              const float* codebook, size_t S, size_t C, const uint8_t* codes_by_id, int device,
+                              int memspace, scann_ivf** out);
+scann_status scann_ivf_search(scann_ivf* h, int mode, const float* queries, size_t nq, size_t qdim, size_t L, size_t k,
+                              int measure, int reorder_measure, uint32_t* ids, float* dists, uint32_t* counts,
+                              int memspace, void* stream);
+void scann_ivf_destroy(scann_ivf* h);
 
 /* ---------------------------------------------------------------------------------------------
  * Parity taps for the LUT16 pieces (bit-exact targets of BASELINE.json)

@@ -36,6 +36,7 @@ SYMBOLS = [
     "scann_treeah_create", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
     "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end", "scann_treeah_partition",
     "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_merge_topk_packed", "scann_tc_scores",
+    "scann_ivf_create", "scann_ivf_search", "scann_ivf_destroy",
 ]
 
 
@@ -99,6 +100,10 @@ def load():
     L.scann_lut16_scan.argtypes = [vp, sz, sz, vp, vp, i32, i32]
     L.scann_pq_encode.argtypes = [vp, sz, sz, vp, sz, sz, vp, vp, vp, i32, i32]
     L.scann_merge_topk.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, i32, i32, vp]
+    L.scann_ivf_create.argtypes = [vp, sz, sz, vp, vp, sz, vp, sz, sz, vp, sz, sz, vp, i32, i32, C.POINTER(vp)]
+    L.scann_ivf_search.argtypes = [vp, i32, vp, sz, sz, sz, sz, i32, i32, vp, vp, vp, i32, vp]
+    L.scann_ivf_destroy.argtypes = [vp]
+    L.scann_ivf_destroy.restype = None
     L.scann_merge_topk_packed.argtypes = [vp, sz, sz, sz, vp, vp, vp, i32, vp]
     L.scann_tc_scores.argtypes = [vp, sz, sz, vp, i32, sz, sz, f32, i32, vp, vp, vp, sz, vp, i32]
     for name in SYMBOLS:

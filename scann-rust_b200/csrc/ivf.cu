@@ -27,15 +27,21 @@ constexpr int kIvfChunk = 2048;
 
 // x86.rs:72-96 (dot), :139-165 (sqL2), hsum :31-44 — single-thread restatement of the 8-lane kernel
 __device__ __forceinline__ float exact_pair_distance_1t(const float* __restrict__ q, const float* __restrict__ x,
-                                                        int dim, int measure) {
+                                                        int dim, int measure, bool vec) {
   float acc[8];
 #pragma unroll
   for (int l = 0; l < 8; ++l) acc[l] = 0.0f;
   const int chunks = dim >> 3;
   for (int i = 0; i < chunks; ++i) {
-    const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + i * 8));
-    const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + i * 8 + 4));
-    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float xv[8];
+    if (vec) {  // rows 16-byte aligned (stride % 4 == 0)
+      const float4 x0 = __ldg(reinterpret_cast<const float4*>(x + i * 8));
+      const float4 x1 = __ldg(reinterpret_cast<const float4*>(x + i * 8 + 4));
+      xv[0] = x0.x, xv[1] = x0.y, xv[2] = x0.z, xv[3] = x0.w, xv[4] = x1.x, xv[5] = x1.y, xv[6] = x1.z, xv[7] = x1.w;
+    } else {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) xv[l] = __ldg(x + i * 8 + l);
+    }
 #pragma unroll
     for (int l = 0; l < 8; ++l) {
       const float a = q[i * 8 + l];
@@ -116,6 +122,7 @@ __global__ void __launch_bounds__(256) ivf_topk_kernel(const IvfArgs a) {
   }
   __syncthreads();
   const int total = static_cast<int>(prefix[a.L]);
+  const bool vec = (a.stride & 3) == 0 && (reinterpret_cast<uintptr_t>(a.raw) & 15) == 0;
   auto member = [&](int i) -> uint32_t {
     int lo = 0, hi = a.L;  // largest r with prefix[r] <= i
     while (hi - lo > 1) {
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(256) ivf_topk_kernel(const IvfArgs a) {
       d = 0.0f;
       for (int s = 0; s < a.S; ++s) d = __fadd_rn(d, lut[s * a.C + c[s]]);
     } else {
-      d = exact_pair_distance_1t(qs, a.raw + static_cast<size_t>(id) * a.stride, a.dim, a.measure);
+      d = exact_pair_distance_1t(qs, a.raw + static_cast<size_t>(id) * a.stride, a.dim, a.measure, vec);
     }
     return (static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(i);
   };
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(256) ivf_topk_kernel(const IvfArgs a) {
       uint64_t key = ~0ull;
       if (j < m) {
         const uint32_t id = member(static_cast<int>(out[j] & 0xFFFFFFFFu));
-        const float d = exact_pair_distance_1t(qs, a.raw + static_cast<size_t>(id) * a.stride, a.dim, a.reorder_measure);
+        const float d = exact_pair_distance_1t(qs, a.raw + static_cast<size_t>(id) * a.stride, a.dim, a.reorder_measure, vec);
         key = (static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(j);  // ties keep the previous order
         buf[j] = id;
       }

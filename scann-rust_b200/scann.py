@@ -6,7 +6,7 @@ tree only → Partitioned; hash only → Hashed.  On the GPU:
   TreeAH      → TreeXHybridSearcher with the LUT16 scan + exact reorder (the north-star path; the
                 reference's own `search_tree_ah` is the weaker non-residual "variant B")
   Hashed      → flat AsymmetricHasher on the LUT16 path (16 codes per block)
-  Partitioned → SURVEY §8f-2 ("next"): not on the GPU yet → UNIMPLEMENTED, loudly.
+  Partitioned → LeafScanSearcher.search_partitioned: exact distances inside the L closest leaves (scann.rs:215-253)
 Both builder spellings exist: `.tree()/.hash()` (the code, scann.rs:395-411) and `.partitioned()/.hashed()`
 (README / BASELINE.json north_star).
 """
@@ -54,6 +54,7 @@ class Scann:
         self.dimensionality = int(dataset.shape[1])
         self._bf = None
         self._tree = None
+        self._leaf = None
         if config.brute_force:
             self.search_mode = SearchMode.BruteForce
         elif config.num_partitions is not None and config.hash_num_blocks is not None:
@@ -67,8 +68,7 @@ class Scann:
         if self.search_mode == SearchMode.BruteForce:
             self._bf = searchers.BruteForceSearcher(dataset, config.distance_measure, device)
         elif self.search_mode == SearchMode.Partitioned:
-            raise ScannError(capi.UNIMPLEMENTED, "Partitioned (exact-in-leaf) mode is not on the GPU path yet "
-                                                 "(SURVEY §8f-2)")
+            self._init_partitioned()
         else:
             self._init_tree_ah()
 
@@ -89,6 +89,19 @@ class Scann:
     @classmethod
     def hashed(cls, dataset, num_blocks: int, device: int = 0):
         return cls(dataset, ScannConfig(hash_num_blocks=num_blocks), device)
+
+    def _init_partitioned(self):
+        import torch
+        x = self._dataset
+        if not (type(x).__module__.startswith("torch") and x.is_cuda):
+            x = torch.as_tensor(np.ascontiguousarray(x, np.float32)).cuda(self.device)
+        K = min(int(self.config.num_partitions), self.size)
+        centers = indexing.kmeans(x, K, 20, 7)
+        assign = indexing.assign_partitions(x, centers, self.device)
+        order = torch.argsort(assign.long(), stable=True)
+        off = torch.zeros((centers.shape[0] + 1,), dtype=torch.int64, device=x.device)
+        off[1:] = torch.cumsum(torch.bincount(assign.long(), minlength=centers.shape[0]), 0)
+        self._leaf = searchers.LeafScanSearcher(centers, order.to(torch.int32), off, x, device=self.device)
 
     def _init_tree_ah(self):
         import torch
@@ -117,6 +130,9 @@ class Scann:
         k = int(k if k is not None else self.config.num_neighbors)
         if self.search_mode == SearchMode.BruteForce:
             return self._bf.search_batched(queries, k)
+        if self.search_mode == SearchMode.Partitioned:
+            return self._leaf.search_partitioned(queries, k, int(self.config.num_partitions_to_search),
+                                                 self.config.distance_measure)
         return self._tree.search_batched(queries, k, pre_reorder_k=max(self._pre_reorder, k))
 
     def search(self, query, k: Optional[int] = None):

@@ -513,6 +513,70 @@ class AsymmetricHasher(TreeXHybridSearcher):
         return TreeXHybridSearcher.search_batched(self, queries, k, 1, pre_reorder_k)
 
 
+class LeafScanSearcher(_Handle):
+    """The Scann façade's tree modes that score every member of the probed leaves (src/scann.rs:215-294) over
+    prebuilt index arrays (include/scann_b200.h scann_ivf_*):
+      search_partitioned ← Scann::search_partitioned: exact distances inside the L closest leaves;
+      search_tree_ah     ← Scann::search_tree_ah ("variant B"): one f32 LookupTable of the query over byte codes
+                           indexed by datapoint id; K = 1 is the scoring of AsymmetricHasher::search.
+    `reorder` re-scores the k results exactly (ReorderingHelper::reorder as Scann::search_impl applies it)."""
+    _destroy = "scann_ivf_destroy"
+
+    def __init__(self, centers, ids, part_offsets, dataset=None, codebook=None, codes_by_id=None, device: int = 0):
+        super().__init__()
+        capi.require_gpu()
+        self.device = device
+        on_gpu = any(_is_torch(a) and a.is_cuda for a in (centers, ids, part_offsets, dataset, codebook, codes_by_id)
+                     if a is not None)
+
+        def conv(a, dtype):
+            if a is None:
+                return None, None
+            if on_gpu:
+                torch = _torch()
+                tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.uint32: torch.int32, np.uint64: torch.int64}[dtype]
+                t = a if _is_torch(a) else torch.as_tensor(np.ascontiguousarray(a).view(
+                    {np.uint32: np.int32, np.uint64: np.int64}.get(dtype, dtype)))
+                t = t.to(device=f"cuda:{device}", dtype=tdt).contiguous()
+                return C.c_void_p(t.data_ptr()), t
+            arr = np.ascontiguousarray(a.cpu().numpy() if _is_torch(a) else a, dtype=dtype)
+            return capi.np_ptr(arr), arr
+
+        K, dim = int(centers.shape[0]), int(centers.shape[1])
+        n = int(ids.shape[0])
+        pc, k1 = conv(centers, np.float32)
+        pi, k2 = conv(ids, np.uint32)
+        po, k3 = conv(part_offsets, np.uint64)
+        pr, k4 = conv(dataset, np.float32)
+        pcb, k5 = conv(codebook, np.float32)
+        pcd, k6 = conv(codes_by_id, np.uint8)
+        num_raw = int(dataset.shape[0]) if dataset is not None else (int(codes_by_id.shape[0]) if codes_by_id is not None else 0)
+        stride = int(dataset.shape[1]) if dataset is not None else dim
+        S = int(codebook.shape[0]) if codebook is not None else 0
+        Cc = int(codebook.shape[1]) if codebook is not None else 0
+        if on_gpu:
+            _torch().cuda.current_stream(device).synchronize()
+        self.dimensionality, self.num_partitions, self.size = dim, K, n
+        capi.check(capi.load().scann_ivf_create(pc, K, dim, pi, po, n, pr, num_raw, stride, pcb, S, Cc, pcd, device,
+                                                capi.DEVICE if on_gpu else capi.HOST, C.byref(self._h)))
+
+    def _search(self, mode, queries, k, L, measure, reorder):
+        b = _Batch(queries, self.device)
+        ids, dists, counts, pi, pd, pc = b.outputs(k)
+        if b.nq:
+            capi.check(capi.load().scann_ivf_search(self._h, mode, b.ptr, b.nq, b.dim, int(L), int(k), int(measure),
+                                                    -1 if reorder is None else int(reorder), pi, pd, pc, b.memspace,
+                                                    b.stream))
+        return ids, dists, counts
+
+    def search_partitioned(self, queries, k: int, partitions_to_search: int,
+                           distance_measure=DistanceMeasure.SquaredL2, reorder=None):
+        return self._search(0, queries, k, partitions_to_search, DistanceMeasure(distance_measure), reorder)
+
+    def search_tree_ah(self, queries, k: int, partitions_to_search: int, reorder=None):
+        return self._search(1, queries, k, partitions_to_search, DistanceMeasure.SquaredL2, reorder)
+
+
 def merge_topk(ids_parts, dists_parts, device: int = 0):
     """k-way merge of per-shard results [parts, nq, k] by (distance, id)."""
     capi.require_gpu()
