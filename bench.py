@@ -236,7 +236,8 @@ def main():
                             "L2-normalised; seeds db 42 / queries 123+ / train 7",
               "l2_policy": "inputs larger than L2: 24 B/point codes of the probed leaves (7.7 MB/query, 240 MB index) "
                            "+ 3.84 GB raw rows; two alternating query batches",
-              "parallelism": (f"{a.shard}-sharded x{shard_world}, NCCL all-gather of (id, dist) top-k + merge kernel"
+              "parallelism": (f"index {a.shard}-sharded x{shard_world}; per batch: token slices all-gathered, closest-leaf "
+                              "bounds all-reduced (MIN), local top-k all-gathered + merge kernel (NCCL)"
                               if shard_world > 1 else "single GPU")}
 
     # ---------------- the CPU arm (oracle = C++ restatement of the reference algorithm) ----------------
@@ -415,7 +416,7 @@ def main():
         "data": "synthetic", "config": config, "recall_at_10": recall,
         "e2e": {"value": e2e_val, "unit": "queries/s", "h2d_bytes_per_step": a.nq * a.dim * 4,
                 "d2h_bytes_per_step": a.nq * (a.k * 8 + 4)},
-        "gpu_launches": int(launches) + (a.steps if world > 1 else 0),
+        "gpu_launches": int(launches) + (a.steps if world > 1 else 0),  # + merge_topk per step when sharded
         "roofline": {"bound": "hbm", "kernel": "lut16_scan_kernel", "achieved": achieved, "peak": peak_gbs,
                      "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                      "algorithmic_bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms_per_launch,

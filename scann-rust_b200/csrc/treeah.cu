@@ -513,7 +513,7 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   h->ck.cand = cand;
   h->ck.cand_cnt = cand_cnt;
   h->ck.qthr = qthr;
-  h->prof_launches += h->ptc.ready ? 7 : 6;  // partition (2 or 3 kernels) + 4 worklist kernels
+  h->prof_launches += (tokens_in ? 0 : (h->ptc.ready ? 3 : 2)) + 4;  // partition (2 or 3 kernels) + 4 worklist kernels
   if (two_phase) {
     // 3a. probe of the class-A items: the first kProbeBlocks blocks of every query's closest leaf prove a bound in
     // bounded time (a full scan of the largest leaves would serialise on a few CTAs); phase 2 scans them in full
@@ -842,6 +842,7 @@ scann_status scann_treeah_partition(scann_treeah* h, const float* queries, size_
   const size_t need = std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0)) + 4096;
   SCANN_TRY(h->ws.reserve(need));
   float* scratch = reinterpret_cast<float*>(h->ws.take<uint8_t>(need - 4096));
+  h->prof_launches += h->ptc.ready ? 3 : 2;
   if (h->ptc.ready)
     return launch_partition_tc(h->ptc, h->centers.p, K, h->dim, queries, nq, L, tokens, nullptr, scratch, h->sms, s);
   return launch_partition(h->centersT.p, K, h->dim, queries, nq, L, tokens, nullptr, scratch, s);
