@@ -198,18 +198,27 @@ def main():
             if a.shard == "rows":  # round-robin inside each partition
                 keep = ((pos - off[leaf_sorted]) % sw) == sr
             else:
-                # whole partitions per GPU.  A leaf's scan load is ~ size (bytes per probe) x size (probes: queries
-                # come from the data distribution), so leaves are dealt largest-first to the shard with the least
-                # accumulated size^2 (greedy LPT) — balances the scanned bytes, not just the row counts
+                # whole partitions per GPU, balanced by MEASURED probe load: a calibration batch of queries from the
+                # same generator (its own seed, never timed) is partitioned, load(leaf) = probes x leaf size, and the
+                # leaves are dealt heaviest-first to the least-loaded shard (greedy LPT).  Every rank computes the
+                # same assignment.
+                calib = make_points(torch, 10_000, a.dim, lat, a.spread, a.decay, 999, dev)
+                part = pkg.TreePartitioner(centers, local_rank)
+                tok, _ = part.partition(calib, min(a.leaves, K))
+                probes = torch.bincount(tok.long().flatten().clamp_(0, K - 1), minlength=K).cpu().numpy()
+                part.close()
                 cnt_h = counts.cpu().numpy().astype(np.float64)
+                load_leaf = (probes.astype(np.float64) + 1.0) * cnt_h
                 load = np.zeros(sw)
                 owner_h = np.zeros(K, np.int64)
-                for leaf in np.argsort(-cnt_h, kind="stable"):
+                for leaf in np.argsort(-load_leaf, kind="stable"):
                     g = int(np.argmin(load))
                     owner_h[leaf] = g
-                    load[g] += cnt_h[leaf] ** 2
+                    load[g] += load_leaf[leaf]
                 owner = torch.from_numpy(owner_h).to(dev)
                 keep = owner[leaf_sorted] == sr
+                if sr == 0:
+                    log(f"shard plan: calibrated probe load max/mean = {load.max() / load.mean():.4f}")
             order = order[keep]
             cnt = torch.bincount(leaf_sorted[keep], minlength=K)
             off = torch.zeros((K + 1,), dtype=torch.int64, device=dev)

@@ -237,6 +237,13 @@ def test_treeah_c3_shape_dot(gpu_lib, oracle, nq):
                  measure=gpu_lib.DistanceMeasure.DotProduct, seed=3, min_recall=0.998)
 
 
+def test_treeah_c4_shape_sql2_tensor_core_partition(gpu_lib, oracle):
+    # C4 geometry scaled down: D=128, S=64 (32 B/point), SqL2 reorder, K=300 (>= 256: the centroid scoring runs on
+    # tcgen05 and the survivors are re-scored exactly), R=100, k=10.
+    _treeah_case(gpu_lib, oracle, n=150_000, dim=128, K=300, S=64, nq=200, L=24, R=100, k=10,
+                 measure=gpu_lib.DistanceMeasure.SquaredL2, seed=8, min_recall=0.995)
+
+
 def test_treeah_device_pointers(gpu_lib, oracle):
     _treeah_case(gpu_lib, oracle, n=30_000, dim=64, K=20, S=16, nq=128, L=5, R=50, k=10,
                  measure=gpu_lib.DistanceMeasure.SquaredL2, seed=4, device_path=True, min_recall=0.97)
