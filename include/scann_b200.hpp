@@ -7,6 +7,7 @@
 //   scann::ScalarQuantizedBruteForceSearcher  src/brute_force/scalar_quantized.rs:82-348
 //   scann::TreePartitioner                    src/partitioning/tree_partitioner.rs:18-250
 //   scann::TreeXHybridSearcher (+Config)      src/tree_x_hybrid/mod.rs:23-380
+//   scann::LeafScanSearcher                   src/scann.rs:215-294 (Scann::search_partitioned / search_tree_ah)
 //   scann::Result<T> / ScannError / ErrorCode src/error.rs:10-147
 //
 // `Result<T>` carries {code, message} like `Result<T, ScannError>`; nothing throws across the ABI.
@@ -293,6 +294,60 @@ class TreeXHybridSearcher {
  private:
   TreeXHybridConfig cfg_;
   scann_treeah* h_ = nullptr;
+};
+
+// The Scann facade's tree modes that score every member of the probed leaves (src/scann.rs:215-294):
+//   search_partitioned <- Scann::search_partitioned (exact distances inside the L closest leaves)
+//   search_tree_ah     <- Scann::search_tree_ah ("variant B": one f32 LookupTable of the query over byte codes)
+class LeafScanSearcher {
+ public:
+  LeafScanSearcher() = default;
+  LeafScanSearcher(LeafScanSearcher&& o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  LeafScanSearcher(const LeafScanSearcher&) = delete;
+  ~LeafScanSearcher() { scann_ivf_destroy(h_); }
+
+  // centers [K*dim]; ids [n] grouped by partition; part_offsets [K+1]; raw [num_raw*stride] or null;
+  // codebook [S*C*ds] + codes_by_id [num_raw*S] or both null
+  ScannError build_from_index(const float* centers, size_t K, size_t dim, const uint32_t* ids,
+                              const uint64_t* part_offsets, size_t n, const float* raw, size_t num_raw, size_t stride,
+                              const float* codebook = nullptr, size_t S = 0, size_t C = 0,
+                              const uint8_t* codes_by_id = nullptr, int device = 0) {
+    scann_ivf_destroy(h_);
+    h_ = nullptr;
+    return make_error(scann_ivf_create(centers, K, dim, ids, part_offsets, n, raw, num_raw, stride, codebook, S, C,
+                                       codes_by_id, device, SCANN_HOST, &h_));
+  }
+  Result<std::vector<NNResultsVector>> search_partitioned(const std::vector<std::vector<float>>& queries, size_t k,
+                                                          size_t partitions_to_search,
+                                                          DistanceMeasure m = DistanceMeasure::SquaredL2) const {
+    return run(0, queries, k, partitions_to_search, m, -1);
+  }
+  // reorder >= 0: ReorderingHelper::reorder of the k results with that measure (scann.rs:198-209)
+  Result<std::vector<NNResultsVector>> search_tree_ah(const std::vector<std::vector<float>>& queries, size_t k,
+                                                      size_t partitions_to_search, int reorder = -1) const {
+    return run(1, queries, k, partitions_to_search, DistanceMeasure::SquaredL2, reorder);
+  }
+
+ private:
+  Result<std::vector<NNResultsVector>> run(int mode, const std::vector<std::vector<float>>& queries, size_t k, size_t L,
+                                           DistanceMeasure m, int reorder) const {
+    Result<std::vector<NNResultsVector>> r;
+    if (queries.empty()) return r;
+    std::vector<float> flat;
+    size_t dim;
+    if (!detail::flatten(queries, &flat, &dim)) {
+      r.error = {ErrorCode::InvalidArgument, "Query dimensionality mismatch"};
+      return r;
+    }
+    size_t nq = queries.size();
+    std::vector<uint32_t> ids(nq * k), counts(nq);
+    std::vector<float> dists(nq * k);
+    r.error = make_error(scann_ivf_search(h_, mode, flat.data(), nq, dim, L, k, static_cast<int>(m), reorder, ids.data(),
+                                          dists.data(), counts.data(), SCANN_HOST, nullptr));
+    if (r.ok()) r.value = detail::unflatten(ids, dists, counts, k);
+    return r;
+  }
+  scann_ivf* h_ = nullptr;
 };
 
 }  // namespace scann

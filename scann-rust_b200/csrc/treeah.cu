@@ -413,7 +413,12 @@ static scann_status launch_scan(const ScanArgs& a, int sms, cudaStream_t s) {
   }
 }
 
-constexpr int kProbeBlocks = 16;  // 4096 points
+// blocks of each closest leaf the probe launch scans (256 points each); SCANN_PROBE_BLOCKS overrides (tuning)
+static int probe_blocks() {
+  const char* e = getenv("SCANN_PROBE_BLOCKS");
+  const int v = e ? atoi(e) : 16;
+  return v >= 1 && v <= 4096 ? v : 16;
+}
 
 static scann_status launch_scan_g(int G, const ScanArgs& a, int sms, cudaStream_t s) {
   switch (G) {
@@ -515,11 +520,11 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   h->ck.qthr = qthr;
   h->prof_launches += (tokens_in ? 0 : (h->ptc.ready ? 3 : 2)) + 4;  // partition (2 or 3 kernels) + 4 worklist kernels
   if (two_phase) {
-    // 3a. probe of the class-A items: the first kProbeBlocks blocks of every query's closest leaf prove a bound in
+    // 3a. probe of the class-A items: the first probe_blocks() blocks of every query's closest leaf prove a bound in
     // bounded time (a full scan of the largest leaves would serialise on a few CTAs); phase 2 scans them in full
     h->span_begin(2, s);
     a.end_idx = 2;
-    a.max_blocks = kProbeBlocks;
+    a.max_blocks = probe_blocks();
     SCANN_TRY(launch_scan_g(h->ck.G, a, h->sms, s));
     if (tau_out) tau_out_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(qthr, nq, tau_out);
     SCANN_CUDA(cudaGetLastError());

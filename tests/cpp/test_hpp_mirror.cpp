@@ -56,6 +56,21 @@ int main() {
 
   TreeXHybridConfig cfg;
   CHECK(cfg.pre_reorder_k(10) == 30);
+
+  // Scann::search_partitioned through the mirror: 2 leaves, exact distances inside the closest one
+  const float lc[2 * 2] = {0, 0, 10, 10};
+  const float pts[6 * 2] = {0, 0, 1, 0, 0, 2, 10, 10, 11, 10, 9, 9};
+  const uint32_t lids[6] = {0, 1, 2, 3, 4, 5};
+  const uint64_t loff[3] = {0, 3, 6};
+  LeafScanSearcher leaf;
+  CHECK(leaf.build_from_index(lc, 2, 2, lids, loff, 6, pts, 6, 2).code == ErrorCode::Ok);
+  auto lp = leaf.search_partitioned({{0.2f, 0.f}}, 5, 1);
+  CHECK(lp.ok() && lp.value.size() == 1 && lp.value[0].size() == 3 && lp.value[0][0].first == 0 &&
+        lp.value[0][1].first == 1 && lp.value[0][2].first == 2);
+  auto lp2 = leaf.search_partitioned({{10.f, 10.f}}, 2, 2);
+  CHECK(lp2.ok() && lp2.value[0].size() == 2 && lp2.value[0][0].first == 3 && lp2.value[0][0].second == 0.0f);
+  auto lbad = leaf.search_tree_ah({{0.f, 0.f}}, 2, 1);  // no hasher in this index
+  CHECK(!lbad.ok() && lbad.error.code == ErrorCode::FailedPrecondition);
   std::puts("hpp mirror ok");
   return 0;
 }
