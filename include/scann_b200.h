@@ -144,6 +144,12 @@ scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t n
                                  size_t k, uint32_t* ids, float* dists, uint32_t* counts, uint32_t* cand_ids,
                                  float* cand_dists, uint32_t* cand_counts, int memspace, void* stream);
 void scann_treeah_destroy(scann_treeah* h);
+/* Restrict filter ← TreeXHybridSearcher::search_with_filter (tree_x_hybrid/mod.rs:245-250): RestrictFilter::is_allowed
+ * (restricts/mod.rs:17-31) as a bitmap over datapoint ids — bit i of byte i/8 (LSB first) set = datapoint i may be
+ * returned; ids >= num_ids are not allowed.  Applies to every following search on the handle (plain and split) until
+ * cleared with allow_by_id = NULL.  Filtered-out points are skipped inside the LUT16 scan exactly where the reference
+ * skips them (before the per-leaf top-R), so a leaf contributes its R best ALLOWED points. */
+scann_status scann_treeah_set_filter(scann_treeah* h, const uint8_t* allow_by_id, size_t num_ids, int memspace);
 /* Split search for a SHARDED index (one process per GPU, every shard sees the whole query batch).
  *   scann_treeah_search_begin: partition -> worklist -> LUT16 probe of every query's CLOSEST leaf when this shard
  *       owns it (its first 4096 points: any R points prove a bound, and a bounded probe keeps this phase short).

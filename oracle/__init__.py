@@ -339,8 +339,14 @@ def ah_search(cb, codes, q, k, lut16=False, raw=None, pre_k=0, nthreads=1):
 
 
 def treex_search(centers, cb, part_off, part_ids, codes, raw, q, L, R, k, lut16=True, use_residuals=True,
-                 reorder_measure=SQL2, nthreads=1, want_candidates=False):
+                 reorder_measure=SQL2, nthreads=1, want_candidates=False, allow=None):
+    """allow: optional RestrictFilter as a packed bitmap over datapoint ids (np.packbits(mask, bitorder='little'))
+    → TreeXHybridSearcher::search_with_filter (tree_x_hybrid/mod.rs:245-250)."""
     centers, cb, q = _f32(centers), _f32(cb), _f32(q)
+    allow_arr = None
+    if allow is not None:
+        allow_arr = np.ascontiguousarray(allow, np.uint8)
+        lib().orc_set_filter(_p(allow_arr), _sz(allow_arr.size * 8))
     rawc = _f32(raw) if raw is not None else None
     part_off = np.ascontiguousarray(part_off, np.uint64)
     part_ids = np.ascontiguousarray(part_ids, np.uint32)
@@ -358,6 +364,8 @@ def treex_search(centers, cb, part_off, part_ids, codes, raw, q, L, R, k, lut16=
                                 C.c_int(reorder_measure), _p(q), _sz(nq), _sz(qdim), _sz(L), _sz(R), _sz(k),
                                 _p(ids), _p(dists), _p(counts), _p(cand), _p(cand_d), _p(cand_n),
                                 C.c_int(nthreads))
+    if allow is not None:
+        lib().orc_set_filter(None, _sz(0))
     if want_candidates:
         return rc, ids, dists, counts, cand, cand_d, cand_n
     return rc, ids, dists, counts

@@ -838,6 +838,21 @@ int orc_ah_search(const float* cb, size_t S, size_t C, size_t ds, const uint8_t*
   return 0;
 }
 
+// RestrictFilter for orc_treex_search (TreeXHybridSearcher::search_with_filter, tree_x_hybrid/mod.rs:245-250,
+// 327-332: `if !f.is_allowed(idx) { continue; }` before the per-leaf top-k push).  allow = bitmap over datapoint
+// ids (bit i of byte i/8, LSB first), ids >= num_ids not allowed; NULL = no filter.  Test infrastructure: set, call,
+// clear (not thread-safe across concurrent oracle calls).
+static const uint8_t* g_allow = nullptr;
+static size_t g_allow_n = 0;
+extern "C" void orc_set_filter(const uint8_t* allow, size_t num_ids) {
+  g_allow = allow;
+  g_allow_n = num_ids;
+}
+static inline bool allowed(uint32_t id) {
+  if (!g_allow) return true;
+  return id < g_allow_n && ((g_allow[id >> 3] >> (id & 7)) & 1u);
+}
+
 // ---- a12: TreeXHybridSearcher::search (tree_x_hybrid/mod.rs:245-364)
 // Index arrays: centers[K*dim]; cb[S*C*ds]; part_off[K+1]; part_ids[n] grouped by partition;
 // codes grouped by partition: lut16=0 → bytes [n*S]; lut16=1 → packed nibbles [n*ceil(S/2)].
@@ -870,6 +885,7 @@ int orc_treex_search(const float* centers, size_t K, size_t dim, const float* cb
       if (!lut16) {
         lut_f32(cb, S, C, ds, qr.data(), lutf.data());
         for (size_t i = b; i < e; ++i) {
+          if (!allowed(part_ids[i])) continue;  // :327-332
           float s = 0.0f;
           for (size_t j = 0; j < S; ++j) s += lutf[j * C + codes[i * S + j]];
           top.push(part_ids[i], s);
@@ -878,8 +894,10 @@ int orc_treex_search(const float* centers, size_t K, size_t dim, const float* cb
         lut_f32(cb, S, 16, ds, qr.data(), lutf.data());
         float bias, mult;
         lut16_quantize(lutf.data(), S, l8.data(), &bias, &mult);
-        for (size_t i = b; i < e; ++i)
+        for (size_t i = b; i < e; ++i) {
+          if (!allowed(part_ids[i])) continue;  // :327-332
           top.push(part_ids[i], lut16_dequant(lut16_sum(codes + i * bpp, l8.data(), S), mult, bias, S));
+        }
       }
       auto r = top.results();
       all.insert(all.end(), r.begin(), r.end());

@@ -1,6 +1,6 @@
 // The Tree-AH hot kernel: persistent LUT16 scan over (leaf, <=G queries) work items.
 //
-// Per work item a CTA of NW warps (8 by default; treeah.cu scan_warps())
+// Per work item a CTA of NW = 8 warps
 //   (1) stages the G query residuals q - centroid(leaf) in shared memory,
 //   (2) builds the G residual LUT16 tables (warp g builds table g; bit-exact quantiser, lut16_device.cuh),
 //   (3) turns the batch-wide upper bound tau_q of every query (see below) into an integer score bound
@@ -34,6 +34,9 @@ struct ScanArgs {
   const uint32_t* sorted_pairs;
   uint32_t* counters;  // [0] total items, [1] next item, [2] class-A items (closest-leaf pairs, scanned first)
   int end_idx;         // this launch stops at counters[end_idx]: 0 = every item, 2 = the class-A items only
+  const uint8_t* allow;  // restrict filter (search_with_filter): [total blocks][32] bytes, bit i of byte (block, lane) =
+                         // point lane*8+i of that block is allowed; nullptr = no filter
+  uint32_t sentinel;     // 255*S + 1: the integer score given to filtered-out points (above every real score)
   int max_blocks;      // > 0: probe launch — scan only the first max_blocks 256-point blocks of each leaf and publish
                        // the bound they prove (any R points give a valid bound); candidates are not written
   uint32_t* qthr;      // [nq] f32_key of the best known bound on the R-th approx distance (0xFFFFFFFF = none)
@@ -63,7 +66,7 @@ __device__ __forceinline__ uint32_t key_bound_from_tau(float tau, float mult, fl
   return static_cast<uint32_t>(s + 1) << pos_bits;
 }
 
-template <int G, int MODE, int NW>
+template <int G, int MODE, int NW, bool FILT>
 __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const ScanArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int S4 = a.SG * 4;
@@ -152,6 +155,25 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const Scan
       if (b < nblk) {
         PackedSums ps[G];
         scan_block<G, MODE>(a.codes + (static_cast<size_t>(blk0) + b) * a.SG * 32, a.SG, lut, S4, lane, a.mul, ps);
+        if (FILT) {
+          // RestrictFilter::is_allowed (tree_x_hybrid/mod.rs:327-332): filtered-out points never enter a top-R; here
+          // their score becomes the sentinel, which sorts after every real score and is dropped at the output
+          const uint32_t am = a.allow[(static_cast<size_t>(blk0) + b) * 32 + lane];
+          if (am != 0xFFu) {
+            const uint32_t lo = 0x0000FFFFu, hi = 0xFFFF0000u, sl = a.sentinel, sh = a.sentinel << 16;
+            const uint32_t k_ea = ((am & 1u) ? lo : 0u) | ((am & 4u) ? hi : 0u), k_xa = ((am & 2u) ? lo : 0u) | ((am & 8u) ? hi : 0u);
+            const uint32_t k_eb = ((am & 16u) ? lo : 0u) | ((am & 64u) ? hi : 0u), k_xb = ((am & 32u) ? lo : 0u) | ((am & 128u) ? hi : 0u);
+            const uint32_t v_ea = ((am & 1u) ? 0u : sl) | ((am & 4u) ? 0u : sh), v_xa = ((am & 2u) ? 0u : sl) | ((am & 8u) ? 0u : sh);
+            const uint32_t v_eb = ((am & 16u) ? 0u : sl) | ((am & 64u) ? 0u : sh), v_xb = ((am & 32u) ? 0u : sl) | ((am & 128u) ? 0u : sh);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              ps[g].ea = (ps[g].ea & k_ea) | v_ea;
+              ps[g].xa = (ps[g].xa & k_xa) | v_xa;
+              ps[g].eb = (ps[g].eb & k_eb) | v_eb;
+              ps[g].xb = (ps[g].xb & k_xb) | v_xb;
+            }
+          }
+        }
         const uint32_t pos0 = static_cast<uint32_t>(b) * kBlockPts + lane * 8;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
@@ -193,9 +215,12 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const Scan
           c = a.R;
           if (lane == 0) {
             s_cnt[g] = static_cast<uint32_t>(a.R);
-            // this leaf alone holds R points at or below dist(thr): publish the bound
-            const float dR = lut16_dequant(thr >> a.pos_bits, s_mult[g], s_bias[g]);
-            atomicMin(a.qthr + q, f32_key(dR));
+            // this leaf alone holds R points at or below dist(thr): publish the bound (unless the R-th entry is a
+            // filtered-out point: then fewer than R allowed points were seen and nothing is proved)
+            if (!FILT || (thr >> a.pos_bits) < a.sentinel) {
+              const float dR = lut16_dequant(thr >> a.pos_bits, s_mult[g], s_bias[g]);
+              atomicMin(a.qthr + q, f32_key(dR));
+            }
           }
         }
         if (lane == 0 && t + 1 < ntiles) {
@@ -221,12 +246,28 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const Scan
       const float mult = s_mult[g], biasS = s_bias[g];
       const uint32_t* bg = buf + static_cast<size_t>(g) * a.cap;
       uint2* out = a.cand + static_cast<size_t>(pair) * a.R;
-      for (int i = lane; i < c; i += 32) {
-        uint32_t key = bg[i];
-        float dist = lut16_dequant(key >> a.pos_bits, mult, biasS);
-        out[i] = make_uint2(__float_as_uint(dist), key & pos_mask);
+      if (!FILT) {
+        for (int i = lane; i < c; i += 32) {
+          uint32_t key = bg[i];
+          float dist = lut16_dequant(key >> a.pos_bits, mult, biasS);
+          out[i] = make_uint2(__float_as_uint(dist), key & pos_mask);
+        }
+        if (lane == 0) a.cand_cnt[pair] = static_cast<uint32_t>(c);
+      } else {  // drop the filtered-out points that were kept only because the leaf has fewer than R allowed ones
+        int w = 0;
+        for (int base = 0; base < c; base += 32) {
+          const int i = base + lane;
+          const uint32_t key = i < c ? bg[i] : 0xFFFFFFFFu;
+          const bool ok = i < c && (key >> a.pos_bits) < a.sentinel;
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, ok);
+          if (ok) {
+            const float dist = lut16_dequant(key >> a.pos_bits, mult, biasS);
+            out[w + __popc(bal & lanemask_lt())] = make_uint2(__float_as_uint(dist), key & pos_mask);
+          }
+          w += __popc(bal);
+        }
+        if (lane == 0) a.cand_cnt[pair] = static_cast<uint32_t>(w);
       }
-      if (lane == 0) a.cand_cnt[pair] = static_cast<uint32_t>(c);
     }
   }
 }

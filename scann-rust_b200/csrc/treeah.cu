@@ -166,6 +166,26 @@ __global__ void wl_items_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t 
   for (uint32_t g = 0; g * G < c; ++g) items[ib + g] = make_uint4(l, pb + g * G, min(static_cast<uint32_t>(G), c - g * G), 0u);
 }
 
+// restrict filter: id-indexed allow bitmap (bit i of byte i/8, LSB first) -> one byte per (block, lane) in scan order
+__global__ void build_allow_kernel(const uint8_t* __restrict__ allow_by_id, size_t num_ids,
+                                   const uint32_t* __restrict__ blk_leaf, const uint32_t* __restrict__ blk_off,
+                                   const uint64_t* __restrict__ pt_off, const uint32_t* __restrict__ ids,
+                                   size_t total /* blocks * 32 */, uint8_t* __restrict__ out) {
+  size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const uint32_t gb = static_cast<uint32_t>(t >> 5), lane = static_cast<uint32_t>(t & 31);
+  const uint32_t leaf = blk_leaf[gb];
+  const uint64_t p0 = pt_off[leaf] + static_cast<uint64_t>(gb - blk_off[leaf]) * kBlockPts + lane * 8, pend = pt_off[leaf + 1];
+  uint32_t m = 0;
+  for (int i = 0; i < 8; ++i) {
+    if (p0 + i < pend) {
+      const uint32_t id = ids[p0 + i];
+      if (id < num_ids && ((allow_by_id[id >> 3] >> (id & 7)) & 1u)) m |= 1u << i;
+    }
+  }
+  out[t] = static_cast<uint8_t>(m);
+}
+
 // qthr <-> caller-visible f32 bounds (scann_treeah_search_begin / _end)
 __global__ void tau_in_kernel(const float* __restrict__ tau, size_t nq, uint32_t* __restrict__ qthr) {
   size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -324,6 +344,10 @@ struct scann_treeah {
   uint32_t max_leaf = 0;
   scann::DevBuf<float> centers, centersT, codebook, raw;
   scann::DevBuf<uint32_t> codes, ids, blk_off, leaf_perm;  // leaf_perm: leaves by descending size
+  scann::DevBuf<uint32_t> blk_leaf;                        // leaf of every 256-point block
+  scann::DevBuf<uint8_t> allow_blk;                        // restrict filter in block order (scann_treeah_set_filter)
+  bool filter_on = false;
+  size_t num_blocks = 0;
   scann::DevBuf<uint64_t> pt_off;
   scann::DevBuf<unsigned long long> stats;  // [0] algorithmic scan bytes, [1] pairs of the last search
   scann::PartTc ptc;                        // tensor-core centroid scoring operands (partition.cu)
@@ -371,36 +395,28 @@ struct scann_treeah {
 
 namespace scann {
 
-template <int G, int MODE, int NW>
+template <int G, int MODE, int NW, bool FILT>
 static scann_status launch_scan_mode(ScanArgs a, int sms, cudaStream_t s) {
   a.cap = (NW * kBlockPts + 2 * a.R + 31) / 32 * 32;  // one tile of unfiltered points + 2R carried
   size_t smem = scan_smem_bytes(G, a.SG * 4, a.dim, a.cap, NW);
   SCANN_REQUIRE(smem <= 227 * 1024, SCANN_RESOURCE_EXHAUSTED, "scan kernel needs %zu B of shared memory (R too large)",
                 smem);
-  SCANN_CUDA(cudaFuncSetAttribute(lut16_scan_kernel<G, MODE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SCANN_CUDA(cudaFuncSetAttribute(lut16_scan_kernel<G, MODE, NW, FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
   int occ = 0;
-  SCANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lut16_scan_kernel<G, MODE, NW>, NW * 32, smem));
+  SCANN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lut16_scan_kernel<G, MODE, NW, FILT>, NW * 32, smem));
   if (occ < 1) occ = 1;
-  lut16_scan_kernel<G, MODE, NW><<<sms * occ, NW * 32, smem, s>>>(a);
+  lut16_scan_kernel<G, MODE, NW, FILT><<<sms * occ, NW * 32, smem, s>>>(a);
   SCANN_CUDA(cudaGetLastError());
   return SCANN_OK;
 }
 
-// warps per scan CTA: default 8 (2 CTAs/SM), SCANN_SCAN_WARPS=4 selects 4 (4 CTAs/SM).  Measured on B200 at C3:
-// 8 warps 35.6 ms, 4 warps 35.8 ms, 2 warps 44.7 ms (profiles/r1_scan_kernel.md).
-static int scan_warps() {
-  const char* e = getenv("SCANN_SCAN_WARPS");
-  int w = e ? atoi(e) : 8;
-  return (w == 4 || w == 8) ? w : 8;
-}
-
+// 8 warps per scan CTA (2 CTAs/SM).  Measured on B200 at C3: 8 warps 35.6 ms, 4 warps 35.8 ms, 2 warps 44.7 ms
+// (profiles/r1_scan_kernel.md).  The restrict filter is a template flag so the unfiltered kernel carries none of it.
 template <int G, int MODE>
 static scann_status launch_scan_nw(const ScanArgs& a, int sms, cudaStream_t s) {
-  switch (scan_warps()) {
-    case 4: return launch_scan_mode<G, MODE, 4>(a, sms, s);
-    default: return launch_scan_mode<G, MODE, 8>(a, sms, s);
-  }
+  if (a.allow != nullptr) return launch_scan_mode<G, MODE, 8, true>(a, sms, s);
+  return launch_scan_mode<G, MODE, 8, false>(a, sms, s);
 }
 
 template <int G>
@@ -492,6 +508,8 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   a.counters = counters;
   a.end_idx = 0;
   a.max_blocks = 0;
+  a.allow = h->filter_on ? h->allow_blk.p : nullptr;
+  a.sentinel = 255u * static_cast<uint32_t>(h->S) + 1u;
   a.cand = cand;
   a.cand_cnt = cand_cnt;
   a.qthr = qthr;
@@ -655,7 +673,7 @@ scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, con
   h->reorder_measure = reorder_measure;
   h->sms = sm_count(device);
   int sum_bits = 1;
-  while ((1u << sum_bits) <= 255u * S) ++sum_bits;
+  while ((1u << sum_bits) <= 255u * S + 1u) ++sum_bits;  // scores 0..255*S plus the filter sentinel 255*S + 1
   h->pos_bits = 32 - sum_bits;
   if (h->pos_bits > 22) h->pos_bits = 22;
 
@@ -701,7 +719,8 @@ scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, con
       for (uint32_t b = blk_off[l]; b < blk_off[l + 1]; ++b) blk_leaf[b] = static_cast<uint32_t>(l);
 
     DevBuf<uint8_t> d_packed;
-    DevBuf<uint32_t> d_blk_leaf;
+    DevBuf<uint32_t>& d_blk_leaf = h->blk_leaf;
+    h->num_blocks = nb;
     size_t bpp = (S + 1) / 2;
     if ((st = h->centers.upload(centers, K * dim, memspace, s)) != SCANN_OK) break;
     if ((st = h->centersT.alloc(K * dim)) != SCANN_OK) break;
@@ -901,6 +920,38 @@ scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint3
   return st;
 }
 
+// RestrictFilter for the following searches (TreeXHybridSearcher::search_with_filter, tree_x_hybrid/mod.rs:245-250,
+// 327-332): allow_by_id = bitmap over datapoint ids (bit i of byte i/8, LSB first; ids >= num_ids are not allowed);
+// NULL clears the filter.
+scann_status scann_treeah_set_filter(scann_treeah* h, const uint8_t* allow_by_id, size_t num_ids, int memspace) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "a split search is in flight on this handle");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard g(h->device);
+  if (allow_by_id == nullptr) {
+    SCANN_CUDA(cudaDeviceSynchronize());
+    h->filter_on = false;
+    return SCANN_OK;
+  }
+  const size_t total = h->num_blocks * 32;
+  if (total == 0) return SCANN_OK;
+  DevBuf<uint8_t> tmp;
+  const uint8_t* src = allow_by_id;
+  if (memspace == SCANN_HOST) {
+    SCANN_TRY(tmp.upload(allow_by_id, (num_ids + 7) / 8, SCANN_HOST, h->stream));
+    src = tmp.p;
+  }
+  SCANN_CUDA(cudaDeviceSynchronize());  // no search may be reading the previous filter
+  if (h->allow_blk.n != total) SCANN_TRY(h->allow_blk.alloc(total));
+  build_allow_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, h->stream>>>(
+      src, num_ids, h->blk_leaf.p, h->blk_off.p, h->pt_off.p, h->ids.p, total, h->allow_blk.p);
+  SCANN_CUDA(cudaGetLastError());
+  SCANN_CUDA(cudaStreamSynchronize(h->stream));
+  h->filter_on = true;
+  return SCANN_OK;
+}
+
 scann_status scann_treeah_set_profiling(scann_treeah* h, int enable) {
   using namespace scann;
   SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
@@ -945,6 +996,8 @@ void scann_treeah_destroy(scann_treeah* h) {
     h->blk_off.free_();
     h->pt_off.free_();
     h->leaf_perm.free_();
+    h->blk_leaf.free_();
+    h->allow_blk.free_();
     h->ptc.cbf.free_();
     h->ptc.hx.free_();
     h->ptc.small.free_();

@@ -414,6 +414,25 @@ class TreeXHybridSearcher(_Handle):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
 
+    def set_filter(self, allowed=None):
+        """RestrictFilter for the following searches (scann_treeah_set_filter): `allowed` = boolean mask over datapoint
+        ids (numpy or torch, True = may be returned) or None to clear."""
+        if allowed is None:
+            capi.check(capi.load().scann_treeah_set_filter(self._h, None, 0, capi.HOST))
+            return
+        m = allowed.cpu().numpy() if _is_torch(allowed) else np.asarray(allowed)
+        bits = np.packbits(m.astype(bool), bitorder="little")
+        capi.check(capi.load().scann_treeah_set_filter(self._h, capi.np_ptr(bits), int(m.size), capi.HOST))
+
+    def search_with_filter(self, queries, k: int, allowed=None, **kw):
+        """search_with_filter (tree_x_hybrid/mod.rs:245-294): search_batched restricted to the allowed datapoints."""
+        self.set_filter(allowed)
+        try:
+            return self.search_batched(queries, k, **kw)
+        finally:
+            if allowed is not None:
+                self.set_filter(None)
+
     def partition_tokens(self, queries, partitions_to_search: Optional[int] = None):
         """The partition stage alone (scann_treeah_partition) for a slice of a batch: torch CUDA queries [m, dim] →
         tokens [m, L] int32 CUDA tensor."""

@@ -487,3 +487,33 @@ def test_scann_builder_brute_force_and_tree_ah(gpu_lib, oracle):
     assert helpers.recall(tids, gt, 10) > 0.8
     with pytest.raises(gpu_lib.ScannError):
         gpu_lib.Scann.brute_force(np.zeros((0, 4), np.float32))  # "Dataset cannot be empty"
+
+
+# ----------------------------------------------------------------------------- restrict filter in the scan
+@pytest.mark.parametrize("keep_frac,nq", [(0.5, 64), (0.02, 200), (0.999, 9)])
+def test_treeah_search_with_filter(gpu_lib, oracle, keep_frac, nq):
+    # TreeXHybridSearcher::search_with_filter (tree_x_hybrid/mod.rs:245-250, 327-332): filtered-out points are skipped
+    # before the per-leaf top-R, so sparse filters make leaves contribute fewer than R candidates.
+    n, dim, K, S, L, R, k = 60_000, 32, 40, 16, 8, 60, 10
+    x, _ = helpers.clustered(n, dim, 48, 0.35, 17)
+    qs, _ = helpers.clustered(nq, dim, 48, 0.35, 17)
+    qs = (qs + 0.05 * helpers.gaussian(nq, dim, 18)).astype(np.float32)
+    idx = helpers.build_index(oracle, x, K, S)
+    allowed = np.random.default_rng(5).random(n) < keep_frac
+    bits = np.packbits(allowed, bitorder="little")
+    rc, oids, odists, ocounts, ocand, ocd, ocn = oracle.treex_search(
+        idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"], x, qs, L, R, k, lut16=True,
+        nthreads=8, want_candidates=True, allow=bits)
+    s = gpu_lib.TreeXHybridSearcher(gpu_lib.TreeXHybridConfig(num_partitions=K, partitions_to_search=L))
+    s.build_from_index(idx["centers"], idx["codebook"], idx["packed"], idx["ids"], idx["part_offsets"], x)
+    ids, dists, counts, (ci, cd, cc) = s.search_with_filter(qs, k, allowed, pre_reorder_k=R, want_candidates=True)
+    valid = ids != 0xFFFFFFFF
+    assert allowed[ids[valid]].all(), "a filtered-out datapoint was returned"
+    rec = _check_stages(oracle, x, oracle.SQL2, qs, k, (ids, dists, counts, ci, cd, cc),
+                        (oids, odists, ocounts, ocand, ocd, ocn))
+    assert rec >= 0.99, rec
+    # the filter is cleared afterwards: the plain search is the unfiltered one again
+    ids2, _, _ = s.search_batched(qs, k, pre_reorder_k=R)
+    rc, pids, _, _ = oracle.treex_search(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"],
+                                         x, qs, L, R, k, lut16=True, nthreads=8)
+    assert helpers.recall(ids2, pids, k) >= 0.99
