@@ -14,8 +14,8 @@
 // The GEMM scores only rank candidates; every distance that is returned comes from step 3.
 //
 // Default path for dim <= 256 — tensor cores (tc_gemm.cu: tcgen05.mma bf16, TMEM accumulators, TMA operands):
-//   a. DENSE scores v = hx - q~.x~ of a strided sample of <= 16384 rows; per query the k-th smallest v_k (an
-//      upper bound of the k-th best over all rows).
+//   a. DENSE scores v = hx - q~.x~ of a strided sample of <= 16384 rows; per query an upper bound v_k of the k-th
+//      smallest sample score (hence of the k-th best over all rows), from a 256-bucket histogram of the row.
 //   b. thr[q] = v_k + 2*eps_q, eps_q = a rigorous bound on |v - exact| (bf16 operand rounding: 2^-8 |q| max|x|,
 //      plus f32 accumulation slack).  Any row with v > thr is beaten by the k sample rows whatever the
 //      rounding did, so it cannot be among the exact top-k.
@@ -210,22 +210,25 @@ __global__ void state_to_cand_kernel(const uint64_t* __restrict__ state, size_t 
 }
 
 
-// thr[q] = (k-th smallest sample score) + 2*eps_q (see the file header).  state: [nq][kc] ascending keys from
-// bf_select_kernel; qn = |q|^2; xmax2 = max_r |x_r|^2 of the values the exact kernels see.
-__global__ void bf_thr_kernel(const uint64_t* __restrict__ state, int kc, const float* __restrict__ qn, float xmax2,
-                              size_t nq, float* __restrict__ thr) {
-  const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+// Steps a+b fused, one warp per query: thr[q] = (upper bound of the k-th smallest sample score) + 2*eps_q.  The bound
+// comes from a 256-bucket histogram of the query's sample row (common.cuh warp_kth_upper_bound) — any value >= the
+// k-th smallest keeps the certification argument, and it is 4x cheaper than an exact select of the row.
+__global__ void __launch_bounds__(256) bf_bound_kernel(const float* __restrict__ dense, int ld, int ncols, int kk,
+                                                       const float* __restrict__ qn, float xmax2, size_t nq,
+                                                       float* __restrict__ thr) {
+  __shared__ uint32_t s_hist[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t q = static_cast<size_t>(blockIdx.x) * 8 + warp;
   if (q >= nq) return;
-  const uint64_t key = state[q * kc + (kc - 1)];
   const float inf = __int_as_float(0x7F800000);
-  float vk = key == ~0ull ? inf : key_f32(static_cast<uint32_t>(key >> 32));
+  const float vU = warp_kth_upper_bound(dense + q * ld, ncols, static_cast<uint32_t>(kk), s_hist[warp], lane);
   const float nqr = sqrtf(qn[q]), nx = sqrtf(xmax2);
   // bf16 RN: |q~.x~ - q.x| <= (2^-8 + 2^-18) sum|q_j x_j| <= 1.001 * 2^-8 |q||x|; the second term covers the f32
   // accumulation of the tensor core, of hx and of the reference's own AVX2 sum (all <= ~dim * 2^-23 relative)
   const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
-  float t = vk + 2.0f * eps;
+  float t = vU + 2.0f * eps;
   t = t + fabsf(t) * 1e-6f;
-  thr[q] = (t == t) ? t : inf;  // NaN anywhere -> keep everything (overflows into the exact legacy path)
+  if (lane == 0) thr[q] = (t == t) ? t : inf;
 }
 
 __global__ void bf_overflow_kernel(const uint32_t* __restrict__ cnt, size_t nq, uint32_t cap, uint32_t* flag) {
@@ -380,7 +383,7 @@ struct BfCore {
   size_t tc_need(size_t nqc, size_t kk) const {
     const size_t qpad = tc_queries_pad(nqc, dim);
     return Workspace::padded(qpad * tc_kpad(dim) * 2) + Workspace::padded(qpad * 4) +
-           Workspace::padded(nqc * tc_sample_tiles() * 128 * 4) + Workspace::padded(nqc * kk * 8) +
+           Workspace::padded(nqc * tc_sample_tiles() * 128 * 4) +
            Workspace::padded(nqc * 4) * 2 + Workspace::padded(nqc * kTcCap * 4);
   }
   scann_status tc_chunk(const float* qsrc, size_t nqc, size_t k, size_t kk, uint32_t* oid, float* od, uint32_t* oc,
@@ -390,7 +393,6 @@ struct BfCore {
     uint16_t* qbf = ws.take<uint16_t>(qpad * kpad);
     float* qn = ws.take<float>(qpad);
     float* dense = ws.take<float>(nqc * scols);
-    uint64_t* state = ws.take<uint64_t>(nqc * kk);
     float* thr = ws.take<float>(nqc);
     uint32_t* cnt = ws.take<uint32_t>(nqc);
     uint32_t* lists = ws.take<uint32_t>(nqc * kTcCap);
@@ -415,22 +417,16 @@ struct BfCore {
     p.cand_cnt = nullptr;
     p.sms = sm_count(device);
     SCANN_TRY(launch_tc_scores(p, s));  // a. sample scores
-    {
-      const int p2 = next_pow2(static_cast<int>(kk));
-      const size_t sel_smem = (kk + kBfChunk + p2) * 8 + 264 * 4;
-      SCANN_CUDA(cudaFuncSetAttribute(bf_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(sel_smem)));
-      bf_select_kernel<<<static_cast<unsigned>(nqc), 256, sel_smem, s>>>(dense, static_cast<int>(scols),
-                                                                         static_cast<int>(scols), 0u, state, 0,
-                                                                         static_cast<int>(kk));
-      bf_thr_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(state, static_cast<int>(kk), qn, xmax2,
-                                                                             nqc, thr);  // b. certified threshold
-    }
+    // b. certified threshold from the sample
+    bf_bound_kernel<<<static_cast<unsigned>((nqc + 7) / 8), 256, 0, s>>>(dense, static_cast<int>(scols),
+                                                                        static_cast<int>(scols), static_cast<int>(kk),
+                                                                        qn, xmax2, nqc, thr);
     SCANN_CUDA(cudaMemsetAsync(cnt, 0, nqc * 4, s));
     SCANN_CUDA(cudaMemsetAsync(flag, 0, 4, s));
     p.nrows = rpad;
     p.tile_stride = 1;
     p.filter = true;
+    p.hx_is_zero = measure == SCANN_DOT;
     p.dense = nullptr;
     p.thr = thr;
     p.cand = lists;

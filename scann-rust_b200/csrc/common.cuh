@@ -309,6 +309,74 @@ __device__ int block_topr_sorted(Gen gen, int n, int R, uint64_t* buf, uint64_t*
   return m;
 }
 
+
+// ---- warp-level upper bound of the need-th smallest of row[0..n) ----------------------------------------------------
+// One 256-bucket linear histogram over [min, max of the finite entries]: the bucket that holds the need-th smallest
+// value ends at the returned edge (>= that value; the slack covers the rounding of the bucket arithmetic).  Entries
+// that are NaN or +inf land in the last bucket; the result is +inf when the need-th smallest lies there.  Three passes
+// over the row (L1/L2 resident), one of them with shared-memory atomics.  hist: 256 u32 private to the warp.
+__device__ __forceinline__ float warp_kth_upper_bound(const float* __restrict__ row, int n, uint32_t need,
+                                                      uint32_t* hist, int lane) {
+  const float inf = __int_as_float(0x7F800000);
+  float mn = inf, mx = -inf;
+  for (int i = lane; i < n; i += 32) {
+    const float v = row[i];
+    mn = fminf(mn, v);
+    if (v < inf) mx = fmaxf(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+  }
+  if (!(mx >= mn)) return inf;  // no finite entry
+  const float width = (mx - mn) * (1.0f / 255.0f);  // finite entries use buckets 0..254 (max lands on 255: clamped)
+  const float scale = width > 0.0f ? 1.0f / width : 0.0f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const float v = row[i];
+    int b = 255;
+    if (v < inf) b = min(254, max(0, static_cast<int>((v - mn) * scale)));
+    atomicAdd(&hist[b], 1u);
+  }
+  __syncwarp();
+  uint32_t h[8], s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    h[j] = hist[lane * 8 + j];
+    s += h[j];
+  }
+  uint32_t incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const uint32_t excl = incl - s;
+  const bool mine = (excl < need) && (need <= incl);
+  int dg = 255;
+  if (mine) {
+    uint32_t run = excl;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (!found && run + h[j] >= need) {
+        dg = lane * 8 + j;
+        found = true;
+      }
+      if (!found) run += h[j];
+    }
+  }
+  const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
+  int bL = 255;
+  if (bal) bL = __shfl_sync(0xFFFFFFFFu, dg, __ffs(bal) - 1);
+  __syncwarp();
+  if (bL >= 255) return inf;
+  return mn + static_cast<float>(bL + 1) * width * 1.00001f + (fabsf(mn) + fabsf(mx)) * 1e-6f;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace scann

@@ -49,6 +49,7 @@ struct TcScoreParams {
   size_t row0, nrows;        // rows [row0, row0 + nrows) of this launch; row0 % 128 == 0
   size_t tile_stride = 1;    // > 1: a sample — the t-th 128-row tile starts at row0 + t * tile_stride * 128
   bool filter;               // false: dense scores, true: threshold filter into candidate lists
+  bool hx_is_zero = false;   // hx == 0 for every real row (Dot): the FILTER epilogue skips the hx loads
   float* dense;              // [nq][ld], column = t * 128 + (row inside tile t); whole tiles are written
   size_t ld;
   const float* thr;          // [nq]

@@ -135,71 +135,14 @@ __global__ void __launch_bounds__(kPtWarps * 32) part_tc_select_kernel(
   const int Leff = L < K ? L : K;
   const float inf = __int_as_float(0x7F800000);
 
-  // (1) an upper bound vU of the L-th smallest ranking score from one 256-bucket linear histogram of the row
-  //     (min/max pass, histogram pass): the bucket that holds the L-th smallest score ends at vU >= v_L
-  float mn = inf, mx = -inf;
-  for (int i = lane; i < K; i += 32) {
-    const float v = row[i];
-    mn = fminf(mn, v);
-    mx = fmaxf(mx, v);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
-    mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-  }
-  const float width = (mx - mn) * (1.0f / 256.0f);
-  const float scale = width > 0.0f ? 1.0f / width : 0.0f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
-  __syncwarp();
-  for (int i = lane; i < K; i += 32) {
-    const float v = row[i];
-    int b = 255;
-    if (v == v) b = min(255, max(0, static_cast<int>((v - mn) * scale)));
-    atomicAdd(&hist[b], 1u);
-  }
-  __syncwarp();
-  int bL = 255;
-  {
-    uint32_t h[8], s = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      h[j] = hist[lane * 8 + j];
-      s += h[j];
-    }
-    uint32_t incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const uint32_t excl = incl - s, need = static_cast<uint32_t>(Leff);
-    const bool mine = (excl < need) && (need <= incl);
-    int dg = 255;
-    if (mine) {
-      uint32_t run = excl;
-      bool found = false;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!found && run + h[j] >= need) {
-          dg = lane * 8 + j;
-          found = true;
-        }
-        if (!found) run += h[j];
-      }
-    }
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mine);
-    if (bal) bL = __shfl_sync(0xFFFFFFFFu, dg, __ffs(bal) - 1);
-  }
-  // every score of buckets 0..bL is below this edge (the slack covers the rounding of the bucket arithmetic)
-  const float vU = mn + static_cast<float>(bL + 1) * width * 1.00001f + (fabsf(mn) + fabsf(mx)) * 1e-6f;
-  // (2) certified threshold (same bound as bf_thr_kernel in brute_force.cu)
+  // (1) an upper bound vU >= v_L of the L-th smallest ranking score (256-bucket histogram of the row, common.cuh)
+  const float vU = warp_kth_upper_bound(row, K, static_cast<uint32_t>(Leff), hist, lane);
+  // (2) certified threshold (same bound as bf_bound_kernel in brute_force.cu)
   const float nqr = sqrtf(qn[q]), nx = sqrtf(cmax2);
   const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
   float thr = vU + 2.0f * eps;
   thr = thr + fabsf(thr) * 1e-6f;
-  if (!(thr == thr) || bL == 255) thr = inf;
+  if (!(thr == thr)) thr = inf;
 
   // (3) survivors
   int m = 0;

@@ -135,6 +135,8 @@ struct TcArgs {
   uint32_t* cand;           // FILTER: [nq][cap] row ids in arbitrary order
   uint32_t cap;
   uint32_t* cand_cnt;       // FILTER: [nq] appended (may exceed cap = overflow)
+  int no_hx;                // FILTER with hx == 0 for every real row (Dot): v = -acc, the hx loads and subtractions are
+                            // skipped (padding rows then score 0 and may enter a list: the re-score ignores ids >= n)
 };
 
 template <int MT, int KA, int STAGES>
@@ -304,26 +306,37 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const int cc = ch * 32;
           uint32_t vr[32];
           tc_ld32(taddr + cc, vr);
-          const float4* h4 = reinterpret_cast<const float4*>(a.hx + row_tile + cc);
-          float h[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = __ldg(h4 + j);
-            h[4 * j + 0] = x.x;
-            h[4 * j + 1] = x.y;
-            h[4 * j + 2] = x.z;
-            h[4 * j + 3] = x.w;
-          }
-          tc_wait_ld();
-          if (ch + 1 == nchunks) {
-            // the whole accumulator is in registers: hand it back to the MMA warp before the last chunk's work
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kTEmpty + as));
-          }
           float v[32];
+          if (a.no_hx) {
+            tc_wait_ld();
+            if (ch + 1 == nchunks) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(kTEmpty + as));
+            }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __fsub_rn(h[j], __uint_as_float(vr[j]));
+            for (int j = 0; j < 32; ++j) v[j] = -__uint_as_float(vr[j]);
+          } else {
+            const float4* h4 = reinterpret_cast<const float4*>(a.hx + row_tile + cc);
+            float h[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = __ldg(h4 + j);
+              h[4 * j + 0] = x.x;
+              h[4 * j + 1] = x.y;
+              h[4 * j + 2] = x.z;
+              h[4 * j + 3] = x.w;
+            }
+            tc_wait_ld();
+            if (ch + 1 == nchunks) {
+              // the whole accumulator is in registers: hand it back to the MMA warp before the last chunk's work
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(kTEmpty + as));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __fsub_rn(h[j], __uint_as_float(vr[j]));
+          }
           if (!a.filter) {
             if (qvalid) {
               float4* o = reinterpret_cast<float4*>(a.dense + static_cast<size_t>(q) * a.ld + col_tile + cc);
@@ -537,6 +550,7 @@ scann_status launch_tc_scores(const TcScoreParams& p, cudaStream_t s) {
   a.cand = p.cand;
   a.cap = static_cast<uint32_t>(p.cap);
   a.cand_cnt = p.cand_cnt;
+  a.no_hx = (p.filter && p.hx_is_zero) ? 1 : 0;
   if (mt == 2) {
     if (ka == 1) return launch_tc<2, 1>(tmA, tmB, a, p.sms, s);
     return launch_tc<2, 2>(tmA, tmB, a, p.sms, s);
