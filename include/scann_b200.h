@@ -83,6 +83,13 @@ scann_status scann_bf_create(const float* db, size_t n, size_t dim, size_t strid
                              int memspace, scann_bf** out);
 scann_status scann_bf_search(scann_bf* h, const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids,
                              float* dists, uint32_t* counts, int memspace, void* stream);
+/*   scann_bf_search_radius ← search_radius (:142-167) for a batch: every row with distance <= radius, ascending
+ *                      (distance, id); ids/dists are [nq*max_results], counts[q] = rows written.  When more than
+ *                      max_results rows qualify for some query the nearest max_results are written and the call
+ *                      returns SCANN_RESOURCE_EXHAUSTED.  max_results < 4096; needs dim <= 256. */
+scann_status scann_bf_search_radius(scann_bf* h, const float* queries, size_t nq, size_t qdim, float radius,
+                                    size_t max_results, uint32_t* ids, float* dists, uint32_t* counts, int memspace,
+                                    void* stream);
 void scann_bf_destroy(scann_bf* h);
 /* introspection: query chunks answered by the tensor-core ranking path (csrc/tc_gemm.cu + exact re-score)
  * and by the CUDA-core path (dim > 256, list overflow) since the handle was created */

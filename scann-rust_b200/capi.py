@@ -30,7 +30,7 @@ HOST, DEVICE = 0, 1
 # every symbol include/scann_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "scann_last_error", "scann_version", "scann_device_count",
-    "scann_bf_create", "scann_bf_search", "scann_bf_destroy", "scann_bf_path_stats", "scann_sq8_path_stats",
+    "scann_bf_create", "scann_bf_search", "scann_bf_search_radius", "scann_bf_destroy", "scann_bf_path_stats", "scann_sq8_path_stats",
     "scann_sq8_quantize", "scann_sq8_create", "scann_sq8_search", "scann_sq8_destroy",
     "scann_part_create", "scann_part_select", "scann_part_destroy",
     "scann_treeah_create", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
@@ -73,6 +73,7 @@ def load():
     L.scann_device_count.argtypes = [C.POINTER(i32)]
     L.scann_bf_create.argtypes = [vp, sz, sz, sz, i32, i32, i32, C.POINTER(vp)]
     L.scann_bf_search.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, i32, vp]
+    L.scann_bf_search_radius.argtypes = [vp, vp, sz, sz, f32, sz, vp, vp, vp, i32, vp]
     L.scann_bf_destroy.argtypes = [vp]
     L.scann_bf_path_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.scann_sq8_path_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]

@@ -231,6 +231,22 @@ __global__ void __launch_bounds__(256) bf_bound_kernel(const float* __restrict__
   if (lane == 0) thr[q] = (t == t) ? t : inf;
 }
 
+// radius search: thr[q] in score units so that every row whose exact distance can be <= radius passes the filter
+//   SqL2: d <= r  <=>  (d - |q|^2)/2 <= (r - |q|^2)/2;  L2: d <= r^2;  Dot: -q.x <= r
+__global__ void bf_radius_thr_kernel(const float* __restrict__ qn, float xmax2, float radius, int measure, size_t nq,
+                                     float* __restrict__ thr) {
+  const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const float nqr = sqrtf(qn[q]), nx = sqrtf(xmax2);
+  const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+  float t;
+  if (measure == SCANN_DOT) t = radius;
+  else if (measure == SCANN_L2) t = radius < 0.0f ? -1.0f - qn[q] : 0.5f * (radius * radius * 1.000001f - qn[q]);
+  else t = 0.5f * (radius - qn[q]);
+  t = t + eps + fabsf(t) * 1e-6f;
+  thr[q] = (t == t) ? t : __int_as_float(0x7F800000);
+}
+
 __global__ void bf_overflow_kernel(const uint32_t* __restrict__ cnt, size_t nq, uint32_t cap, uint32_t* flag) {
   const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q < nq && cnt[q] > cap) atomicOr(flag, 1u);
@@ -442,6 +458,97 @@ struct BfCore {
     return SCANN_OK;
   }
 
+  // BruteForceSearcher::search_radius (searcher.rs:142-167) for a batch: every row with distance <= radius, ascending
+  // (distance, id), at most max_results per query.  Tensor-core path only (dim <= 256).
+  scann_status search_radius(const float* queries, size_t nq, size_t qdim, float radius, size_t max_results,
+                             uint32_t* ids, float* dists, uint32_t* counts, int memspace, void* user_stream) {
+    if (nq == 0) return SCANN_OK;
+    SCANN_REQUIRE(queries && counts, SCANN_INVALID_ARGUMENT, "NULL buffer");
+    std::lock_guard<std::mutex> lock(mu);
+    DeviceGuard g(device);
+    cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(user_stream)
+                                               : (user_stream ? static_cast<cudaStream_t>(user_stream) : stream);
+    const bool host = memspace == SCANN_HOST;
+    if (n == 0) {
+      if (host) memset(counts, 0, nq * sizeof(uint32_t));
+      else SCANN_CUDA(cudaMemsetAsync(counts, 0, nq * sizeof(uint32_t), s));
+      return SCANN_OK;
+    }
+    SCANN_REQUIRE(qdim == dim, SCANN_INVALID_ARGUMENT, "Query dimensionality does not match dataset");
+    SCANN_REQUIRE(ids && dists && max_results >= 1 && max_results < kTcCap, SCANN_INVALID_ARGUMENT,
+                  "max_results must be in 1..%zu", kTcCap - 1);
+    SCANN_REQUIRE(tc, SCANN_UNIMPLEMENTED, "radius search runs on the tensor-core path (dim <= 256)");
+    const size_t k = max_results;
+    const size_t chunk = std::min<size_t>(kTcQTile, nq);
+    const size_t kpad = tc_kpad(dim), rpad = tc_rows_pad(n);
+    size_t need = Workspace::padded(tc_queries_pad(chunk, dim) * kpad * 2) + Workspace::padded(tc_queries_pad(chunk, dim) * 4) +
+                  Workspace::padded(chunk * 4) * 2 + Workspace::padded(chunk * kTcCap * 4) + 4096;
+    if (host) need += Workspace::padded(chunk * dim * 4) + 2 * Workspace::padded(chunk * k * 4) + Workspace::padded(chunk * 4);
+    SCANN_TRY(ws.reserve(need));
+    uint16_t* qbf = ws.take<uint16_t>(tc_queries_pad(chunk, dim) * kpad);
+    float* qn = ws.take<float>(tc_queries_pad(chunk, dim));
+    float* thr = ws.take<float>(chunk);
+    uint32_t* cnt = ws.take<uint32_t>(chunk);
+    uint32_t* lists = ws.take<uint32_t>(chunk * kTcCap);
+    float* hq = nullptr;
+    uint32_t *hids = nullptr, *hcounts = nullptr;
+    float* hd = nullptr;
+    if (host) {
+      hq = ws.take<float>(chunk * dim);
+      hids = ws.take<uint32_t>(chunk * k);
+      hd = ws.take<float>(chunk * k);
+      hcounts = ws.take<uint32_t>(chunk);
+    }
+    uint32_t* flag = reinterpret_cast<uint32_t*>(d_small.p + 1);
+    for (size_t q0 = 0; q0 < nq; q0 += chunk) {
+      const size_t nqc = std::min(chunk, nq - q0);
+      const float* qsrc = queries + q0 * dim;
+      if (host) {
+        SCANN_CUDA(cudaMemcpyAsync(hq, qsrc, nqc * dim * 4, cudaMemcpyHostToDevice, s));
+        qsrc = hq;
+      }
+      SCANN_TRY(tc_prepare_queries(qsrc, nqc, dim, i8 ? scale : 1.0f, qbf, qn, s));
+      bf_radius_thr_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(qn, xmax2, radius, measure, nqc, thr);
+      SCANN_CUDA(cudaMemsetAsync(cnt, 0, nqc * 4, s));
+      SCANN_CUDA(cudaMemsetAsync(flag, 0, 4, s));
+      TcScoreParams p;
+      p.q_bf16 = qbf;
+      p.nq = nqc;
+      p.dim = dim;
+      p.rows_bf16 = rows_bf.p;
+      p.rows_pad_total = rpad;
+      p.hx = hx.p;
+      p.row0 = 0;
+      p.nrows = rpad;
+      p.filter = true;
+      p.hx_is_zero = measure == SCANN_DOT;
+      p.dense = nullptr;
+      p.ld = 0;
+      p.thr = thr;
+      p.cand = lists;
+      p.cap = kTcCap;
+      p.cand_cnt = cnt;
+      p.sms = sm_count(device);
+      SCANN_TRY(launch_tc_scores(p, s));
+      bf_overflow_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(cnt, nqc, kTcCap, flag);
+      uint32_t* oid = host ? hids : ids + q0 * k;
+      float* od = host ? hd : dists + q0 * k;
+      uint32_t* oc = host ? hcounts : counts + q0;
+      SCANN_TRY(launch_rescore_lists(rescore_params(qsrc), lists, cnt, nqc, kTcCap, k, n, oid, od, oc, s, radius, flag));
+      SCANN_CUDA(cudaMemcpyAsync(h_flag, flag, 4, cudaMemcpyDeviceToHost, s));
+      if (host) {
+        SCANN_CUDA(cudaMemcpyAsync(ids + q0 * k, hids, nqc * k * 4, cudaMemcpyDeviceToHost, s));
+        SCANN_CUDA(cudaMemcpyAsync(dists + q0 * k, hd, nqc * k * 4, cudaMemcpyDeviceToHost, s));
+        SCANN_CUDA(cudaMemcpyAsync(counts + q0, hcounts, nqc * 4, cudaMemcpyDeviceToHost, s));
+      }
+      SCANN_CUDA(cudaStreamSynchronize(s));
+      SCANN_REQUIRE(*h_flag == 0, SCANN_RESOURCE_EXHAUSTED,
+                    "more than max_results = %zu points lie within the radius for some query (results are truncated "
+                    "to the nearest ones)", max_results);
+    }
+    return SCANN_OK;
+  }
+
   scann_status search(const float* queries, size_t nq, size_t qdim, size_t k, uint32_t* ids, float* dists,
                       uint32_t* counts, int memspace, void* user_stream) {
     if (nq == 0) return SCANN_OK;  // searcher.rs:175-177
@@ -628,6 +735,13 @@ scann_status scann_bf_search(scann_bf* h, const float* queries, size_t nq, size_
                              float* dists, uint32_t* counts, int memspace, void* stream) {
   SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
   return h->core.search(queries, nq, qdim, k, ids, dists, counts, memspace, stream);
+}
+
+scann_status scann_bf_search_radius(scann_bf* h, const float* queries, size_t nq, size_t qdim, float radius,
+                                    size_t max_results, uint32_t* ids, float* dists, uint32_t* counts, int memspace,
+                                    void* stream) {
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  return h->core.search_radius(queries, nq, qdim, radius, max_results, ids, dists, counts, memspace, stream);
 }
 
 scann_status scann_bf_path_stats(scann_bf* h, uint64_t* tc_chunks, uint64_t* legacy_chunks) {

@@ -33,7 +33,8 @@ scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, 
 //   lists: [nq][cap] row ids, cnt [nq] entries appended (clamped to cap); rows >= n_rows ignored
 scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists, const uint32_t* cnt,
                                   size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
-                                  uint32_t* counts, cudaStream_t s);
+                                  uint32_t* counts, cudaStream_t s, float radius = __builtin_huge_valf(),
+                                  uint32_t* flag = nullptr);  // radius: keep d <= radius; flag |= 2 when > k qualify
 //   part_stride: elements between two parts' blocks (0 = nq * k, the dense [parts][nq][k] layout)
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
                                uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s,

@@ -84,8 +84,8 @@ template <bool I8>
 __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams rp,
                                                             const uint32_t* __restrict__ lists,
                                                             const uint32_t* __restrict__ cnt, int cap, int k,
-                                                            uint32_t n_rows, uint32_t* __restrict__ ids,
-                                                            float* __restrict__ dists,
+                                                            uint32_t n_rows, float radius, uint32_t* __restrict__ flag,
+                                                            uint32_t* __restrict__ ids, float* __restrict__ dists,
                                                             uint32_t* __restrict__ counts) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int tid = threadIdx.x;
@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams 
     const void* row = I8 ? static_cast<const void*>(rp.raw_i8 + static_cast<size_t>(id) * rp.stride)
                          : static_cast<const void*>(rp.raw + static_cast<size_t>(id) * rp.stride);
     const float d = exact_pair_distance<I8>(qs, row, dim, rp.measure, rp.scale, sub);
-    if (valid && sub == 0) keys[j] = (static_cast<uint64_t>(f32_key(d)) << 32) | id;
+    // radius search (searcher.rs:142-167): keep d <= radius only (radius = +inf for the top-k searches)
+    const bool in_radius = radius == __int_as_float(0x7F800000) ? true : d <= radius;
+    if (valid && sub == 0 && in_radius) keys[j] = (static_cast<uint64_t>(f32_key(d)) << 32) | id;
   }
   __syncthreads();
   block_bitonic_sort<256>(keys, p2);
@@ -124,12 +126,13 @@ __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams 
     for (int j = 0; j < lim; ++j)
       if (keys[j] != ~0ull) ++m;
     counts[q] = static_cast<uint32_t>(m);
+    if (flag && k < p2 && keys[k] != ~0ull) atomicOr(flag, 2u);  // more than k entries qualify (radius search)
   }
 }
 
 scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists, const uint32_t* cnt,
                                   size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
-                                  uint32_t* counts, cudaStream_t s) {
+                                  uint32_t* counts, cudaStream_t s, float radius, uint32_t* flag) {
   if (nq == 0) return SCANN_OK;
   SCANN_REQUIRE(cap >= 1 && cap <= 8192, SCANN_INVALID_ARGUMENT, "candidate list capacity %zu out of range", cap);
   const size_t smem = static_cast<size_t>(next_pow2(static_cast<int>(cap))) * 8 + rp.dim * 4 + 16;
@@ -137,12 +140,14 @@ scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists
     SCANN_CUDA(cudaFuncSetAttribute(rescore_lists_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
     rescore_lists_kernel<true><<<static_cast<unsigned>(nq), 256, smem, s>>>(
-        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), ids, dists, counts);
+        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), radius, flag, ids, dists,
+        counts);
   } else {
     SCANN_CUDA(cudaFuncSetAttribute(rescore_lists_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
     rescore_lists_kernel<false><<<static_cast<unsigned>(nq), 256, smem, s>>>(
-        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), ids, dists, counts);
+        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), radius, flag, ids, dists,
+        counts);
   }
   SCANN_CUDA(cudaGetLastError());
   return SCANN_OK;

@@ -173,6 +173,19 @@ class BruteForceSearcher(_Handle):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
 
+    def search_radius_batched(self, queries, radius: float, max_results: int = 1024):
+        """search_radius (searcher.rs:142-167) for a batch → (ids [nq, max_results], dists, counts)."""
+        b = _Batch(queries, self.device)
+        ids, dists, counts, pi, pd, pc = b.outputs(max_results)
+        if b.nq:
+            capi.check(capi.load().scann_bf_search_radius(self._h, b.ptr, b.nq, b.dim, float(radius), max_results, pi, pd,
+                                                          pc, b.memspace, b.stream))
+        return ids, dists, counts
+
+    def search_radius(self, query, radius: float, max_results: int = 1024):
+        ids, dists, counts = self.search_radius_batched(np.asarray(query, np.float32)[None, :], radius, max_results)
+        return results_to_lists(ids, dists, counts)[0]
+
     def path_stats(self):
         """(query chunks answered by the tcgen05 ranking path, by the CUDA-core path) since construction."""
         a, b = C.c_uint64(0), C.c_uint64(0)

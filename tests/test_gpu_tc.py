@@ -173,3 +173,35 @@ def test_partition_cuda_core_path_still_bit_exact(gpu_lib, oracle, monkeypatch):
     tokens, dists = gpu_lib.TreePartitioner(centers).partition(q, 64)
     otok, odist = oracle.partition(centers, q, 64)
     assert (tokens == otok).all() and (dists.view(np.uint32) == odist.view(np.uint32)).all()
+
+
+# ----------------------------------------------------------------------------- radius search
+@pytest.mark.parametrize("measure,radius", [("SquaredL2", 110.0), ("L2", 10.5), ("DotProduct", -25.0)])
+def test_bf_search_radius_matches_oracle(gpu_lib, oracle, measure, radius):
+    # BruteForceSearcher::search_radius (searcher.rs:142-167): every row with distance <= radius, ascending
+    db = helpers.gaussian(30_000, 96, 42)
+    q = helpers.gaussian(40, 96, 123)
+    om = {"SquaredL2": oracle.SQL2, "DotProduct": oracle.DOT, "L2": oracle.L2}[measure]
+    bf = gpu_lib.BruteForceSearcher(db, gpu_lib.DistanceMeasure[measure])
+    ids, dists, counts = bf.search_radius_batched(q, radius, max_results=2048)
+    total = 0
+    for i in range(len(q)):
+        oi, od = oracle.bf_search_radius(db, q[i], radius, om)
+        assert counts[i] == len(oi), (i, counts[i], len(oi))
+        assert (dists[i, :len(oi)].view(np.uint32) == od.view(np.uint32)).all()
+        assert (ids[i, :len(oi)] == oi).all() or len(set(od.tolist())) < len(od)
+        assert (ids[i, len(oi):] == 0xFFFFFFFF).all()
+        total += len(oi)
+    assert total > 50  # the radii above select a few rows per query on this data
+
+
+def test_bf_search_radius_reference_kat_and_truncation(gpu_lib):
+    # src/brute_force/searcher.rs:327-340 test_brute_force_radius_search: 4 of the 5 points lie within 1.5 of the origin
+    db = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 1]], np.float32)
+    bf = gpu_lib.BruteForceSearcher(db)
+    r = bf.search_radius([0, 0, 0], 1.5)
+    assert len(r) == 4 and all(d <= 1.5 for _, d in r) and r[0] == (0, 0.0)
+    with pytest.raises(gpu_lib.ScannError) as e:
+        bf.search_radius([0, 0, 0], 1.5, max_results=2)      # 4 rows qualify, only room for 2
+    assert e.value.code == gpu_lib.capi.RESOURCE_EXHAUSTED
+    assert bf.search_radius([9, 9, 9], 0.5) == []
