@@ -608,6 +608,15 @@ class LeafScanSearcher(_Handle):
     def search_tree_ah(self, queries, k: int, partitions_to_search: int, reorder=None):
         return self._search(1, queries, k, partitions_to_search, DistanceMeasure.SquaredL2, reorder)
 
+    def search_with_reordering(self, queries, k: int, pre_reorder_k: int, partitions_to_search: int = 1):
+        """AsymmetricHasher::search_with_reordering (hashes/hasher.rs:188-229) on a K = 1 index: the pre_reorder_k
+        best by the f32 LUT, exact SqL2 (hard-wired, :208) re-rank, first k."""
+        ids, dists, counts = self._search(1, queries, max(int(pre_reorder_k), 1), partitions_to_search,
+                                          DistanceMeasure.SquaredL2, DistanceMeasure.SquaredL2)
+        if _is_torch(counts):
+            return ids[:, :k].contiguous(), dists[:, :k].contiguous(), counts.clamp(max=k)
+        return np.ascontiguousarray(ids[:, :k]), np.ascontiguousarray(dists[:, :k]), np.minimum(counts, k)
+
 
 def merge_topk(ids_parts, dists_parts, device: int = 0):
     """k-way merge of per-shard results [parts, nq, k] by (distance, id)."""

@@ -73,6 +73,25 @@ def test_flat_asymmetric_hasher_f32_lut_scoring(gpu_lib, oracle):
     assert mism == 0
 
 
+def test_asymmetric_hasher_search_with_reordering(gpu_lib, oracle):
+    # hasher.rs:188-229: top pre_reorder_k by the f32 LUT -> exact SqL2 -> first k
+    n, dim, S, C, k, pre = 6000, 24, 6, 64, 10, 80
+    x = helpers.gaussian(n, dim, 31)
+    rng = np.random.default_rng(2)
+    cb = np.stack([x[rng.choice(n, C, replace=False)][:, s * 4:(s + 1) * 4] for s in range(S)]).astype(np.float32)
+    codes = oracle.pq_encode(cb, x)
+    q = helpers.gaussian(30, dim, 32)
+    s = gpu_lib.LeafScanSearcher(np.zeros((1, dim), np.float32), np.arange(n, dtype=np.uint32),
+                                 np.array([0, n], np.uint64), x, cb, codes)
+    ids, dists, counts = s.search_with_reordering(q, k, pre)
+    rc, oids, odists, ocounts = oracle.ah_search(cb, codes, q, k, lut16=False, raw=x, pre_k=pre, nthreads=8)
+    assert rc == 0 and (counts == ocounts).all()
+    compared, mism = helpers.ids_equal_away_from_ties(ids, dists, oids, odists, counts, rel_gap=0.0)
+    same = ids == oids
+    assert mism == 0 and same.mean() > 0.97            # candidate-set ties at the pre_reorder cut-off may differ
+    assert (dists[same].view(np.uint32) == odists[same].view(np.uint32)).all()
+
+
 def test_leafscan_errors_and_facade(gpu_lib, oracle):
     x, centers, order, off = _ivf_index(oracle, 2000, 8, 5, 13)
     s = gpu_lib.LeafScanSearcher(centers, order, off, x)
