@@ -57,6 +57,7 @@ def parse():
                    help="multi-GPU sharding: whole partitions per GPU (default) or rows round-robin inside partitions")
     p.add_argument("--emulate-shard", type=int, default=0,
                    help="single-GPU tuning aid: build and search only shard 0 of N (not a bench mode)")
+    p.add_argument("--phase-times", action="store_true", help="multi-GPU: log the per-phase device times of the step")
     p.add_argument("--split", action="store_true",
                    help="single-GPU tuning aid: use the two-phase search_begin/search_end path (no reduction)")
     p.add_argument("--sweep-leaves", default="", help="comma list: print recall/QPS for each L (stderr) and exit")
@@ -352,6 +353,8 @@ def main():
     if rank == 0:
         sampler.start()
     searcher.set_profiling(True)
+    if a.phase_times and world > 1:
+        pkg.distributed._PHASE_MARKS = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -362,6 +365,16 @@ def main():
     ms = e0.elapsed_time(e1)
     prof, launches = searcher.get_profile()
     searcher.set_profiling(False)
+    if a.phase_times and world > 1:
+        mk = pkg.distributed._PHASE_MARKS
+        pkg.distributed._PHASE_MARKS = None
+        per = len(mk) // a.steps
+        names = ["partition slice", "all-gather tokens", "search_begin", "all-reduce tau", "search_end"]
+        acc = [0.0] * (per - 1)
+        for st in range(a.steps):
+            for j in range(per - 1):
+                acc[j] += mk[st * per + j].elapsed_time(mk[st * per + j + 1])
+        log(f"[rank {rank}] phases: " + ", ".join(f"{nm} {v / a.steps:.3f}" for nm, v in zip(names, acc)))
     scan_bytes, pairs = searcher.last_scan_bytes()  # algorithmic bytes of one step (this rank's shard)
     xchg_ms = sum(e[0].elapsed_time(e[1]) for e in xchg_events) / max(1, len(xchg_events))
     log(f"[rank {rank}] {ms / a.steps:.3f} ms/step; all-gather+merge {xchg_ms:.3f}; stages " +

@@ -536,10 +536,14 @@ scann_status launch_tc_scores(const TcScoreParams& p, cudaStream_t s) {
   a.row0 = static_cast<uint32_t>(p.row0);
   a.n_tiles = static_cast<uint32_t>((p.nrows + kTcBN - 1) / kTcBN);
   a.tile_stride = static_cast<uint32_t>(p.tile_stride < 1 ? 1 : p.tile_stride);
-  // enough units to fill the machine a few times over, but runs long enough to amortise the A load
+  // enough units to fill the machine a few times over; runs of >= 8 tiles amortise the A load, but only while the
+  // machine stays full (small problems — a slice of a batch against a few thousand centroids — need the parallelism)
   uint32_t want_units = static_cast<uint32_t>(std::max(1, 4 * p.sms / static_cast<int>(a.q_tiles)));
   uint32_t tpu = (a.n_tiles + want_units - 1) / want_units;
-  if (tpu < 8) tpu = std::min<uint32_t>(8, a.n_tiles);
+  if (tpu < 8) {
+    const uint32_t t8 = std::min<uint32_t>(8, a.n_tiles);
+    if (a.q_tiles * ((a.n_tiles + t8 - 1) / t8) >= 2u * static_cast<uint32_t>(p.sms)) tpu = t8;
+  }
   a.tiles_per_unit = tpu;
   a.n_units = (a.n_tiles + tpu - 1) / tpu;
   a.hx = p.hx;

@@ -22,6 +22,9 @@ def all_gather_results(ids, dists, group=None):
     return gi.view(world, nq, k), gd.view(world, nq, k)
 
 
+_PHASE_MARKS = None  # set to a list to collect CUDA events: start, tokens, gathered, begin, reduced, end (per step)
+
+
 def exchange_and_merge(ids, dists, group=None):
     """This rank's [nq, k] results → merged (ids, dists, counts) on every rank.  When ids and dists are the two
     halves of one packed [2, nq, k] buffer (what the searchers return for CUDA queries) the exchange is ONE all-gather
@@ -56,16 +59,31 @@ def two_phase_search(searcher, queries, k: int, group=None, partitions_to_search
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     nq = int(queries.shape[0])
+    marks = _PHASE_MARKS  # optional CUDA-event marks between the phases (bench.py --phase-times)
+
+    def mark():
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
+
+    mark()
     tokens = None
     per = (nq + world - 1) // world
     if world > 1 and per * world == nq:  # equal slices only (all_gather_into_tensor); otherwise partition locally
         L = int(partitions_to_search if partitions_to_search is not None else searcher.config.partitions_to_search)
         mine = searcher.partition_tokens(queries[rank * per:(rank + 1) * per], L)
+        mark()
         tokens = torch.empty((nq, L), dtype=torch.int32, device=queries.device)
         dist.all_gather_into_tensor(tokens, mine, group=group)
+    mark()
     tau = searcher.search_begin(queries, k, partitions_to_search, pre_reorder_k, tokens=tokens)
+    mark()
     dist.all_reduce(tau, op=dist.ReduceOp.MIN, group=group)
-    return searcher.search_end(tau)
+    mark()
+    out = searcher.search_end(tau)
+    mark()
+    return out
 
 
 def sharded_search(searcher, queries, k: int, group=None, **kw):
