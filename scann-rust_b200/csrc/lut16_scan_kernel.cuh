@@ -154,7 +154,24 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) lut16_scan_kernel(const Scan
       const int b = t * NW + warp;
       if (b < nblk) {
         PackedSums ps[G];
-        scan_block<G, MODE>(a.codes + (static_cast<size_t>(blk0) + b) * a.SG * 32, a.SG, lut, S4, lane, a.mul, ps);
+        {
+          // remainder items carry fewer than G queries: the lookups of the unused tables are skipped by running the
+          // narrower instantiation (the code-only work is per block either way)
+          const uint4* cb = a.codes + (static_cast<size_t>(blk0) + b) * a.SG * 32;
+          if (G >= 8 && ng <= 2) {
+            PackedSums p2[2];
+            scan_block<2, MODE>(cb, a.SG, lut, S4, lane, a.mul, p2);
+            ps[0] = p2[0];
+            ps[1] = p2[1];
+          } else if (G >= 8 && ng <= 4) {
+            PackedSums p4[4];
+            scan_block<4, MODE>(cb, a.SG, lut, S4, lane, a.mul, p4);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ps[g] = p4[g];
+          } else {
+            scan_block<G, MODE>(cb, a.SG, lut, S4, lane, a.mul, ps);
+          }
+        }
         if (FILT) {
           // RestrictFilter::is_allowed (tree_x_hybrid/mod.rs:327-332): filtered-out points never enter a top-R; here
           // their score becomes the sentinel, which sorts after every real score and is dropped at the output

@@ -80,66 +80,143 @@ __global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, u
   if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[wl_virtual_leaf(leaf, p, L, K)], 1u);
 }
 
-// single block: exclusive scans of pair counts and item counts per virtual leaf; also accumulates the
-// algorithmic scan bytes of this batch (Σ pairs * leaf_size * bytes_per_point) for the roofline.
-// Inside a class, leaves are laid out in `perm` order = descending leaf size (longest items first), so the persistent
-// scan kernel's atomic-counter schedule ends on the smallest items and the tail stays short.
-__global__ void __launch_bounds__(1024) wl_scan_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
-                                                       const uint32_t* __restrict__ perm,
-                                                       const uint64_t* __restrict__ pt_off, uint32_t bpp,
-                                                       uint32_t* __restrict__ pair_start,
-                                                       uint32_t* __restrict__ item_start,
-                                                       uint32_t* __restrict__ counters /* [0]=items,[1]=next,[2]=class-A items */,
-                                                       unsigned long long* __restrict__ stats) {
-  __shared__ uint32_t s_pair[1024], s_item[1024];
-  __shared__ unsigned long long s_bytes[1024];
-  const uint32_t K2 = 2 * K;
-  const uint32_t per = (K2 + 1023) / 1024;
-  const uint32_t b = threadIdx.x * per, e = min(K2, b + per);
-  auto vleaf = [&](uint32_t i) { return i < K ? perm[i] : K + perm[i - K]; };
-  uint32_t pc = 0, ic = 0;
-  unsigned long long bytes = 0;
-  for (uint32_t i = b; i < e; ++i) {
-    const uint32_t v = vleaf(i), l = v >= K ? v - K : v;
-    uint32_t c = leaf_cnt[v];
-    pc += c;
-    ic += (c + G - 1) / G;
-    bytes += static_cast<unsigned long long>(c) * (pt_off[l + 1] - pt_off[l]) * bpp;
+// Exclusive scans of pair counts and item counts over the 2K virtual leaves (three small kernels so that K = 65,536
+// partitions do not serialise on one CTA), plus the algorithmic scan bytes of this batch (Σ pairs * leaf_size *
+// bytes_per_point) for the roofline.  Position i of the scan order is virtual leaf
+//   v(i) = perm[i] for i < K (class A), K + perm[i - K] otherwise (class B)
+// with perm = leaves by descending size (longest items first), so the persistent scan kernel's atomic-counter
+// schedule ends on the smallest items and the tail stays short.
+constexpr int kWlBlock = 256;
+
+__device__ __forceinline__ void wl_entry(uint32_t i, uint32_t K, int G, const uint32_t* __restrict__ perm,
+                                         const uint32_t* __restrict__ leaf_cnt, const uint64_t* __restrict__ pt_off,
+                                         uint32_t bpp, uint32_t& v, uint32_t& pc, uint32_t& ic,
+                                         unsigned long long& bytes) {
+  v = i < K ? perm[i] : K + perm[i - K];
+  const uint32_t l = v >= K ? v - K : v;
+  pc = leaf_cnt[v];
+  ic = (pc + G - 1) / G;
+  bytes = static_cast<unsigned long long>(pc) * (pt_off[l + 1] - pt_off[l]) * bpp;
+}
+
+// (1) per-block totals
+__global__ void __launch_bounds__(kWlBlock) wl_reduce_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
+                                                             const uint32_t* __restrict__ perm,
+                                                             const uint64_t* __restrict__ pt_off, uint32_t bpp,
+                                                             uint32_t* __restrict__ blk_pair,
+                                                             uint32_t* __restrict__ blk_item,
+                                                             unsigned long long* __restrict__ blk_bytes) {
+  __shared__ uint32_t s_p[kWlBlock], s_i[kWlBlock];
+  __shared__ unsigned long long s_b[kWlBlock];
+  const uint32_t i = blockIdx.x * kWlBlock + threadIdx.x;
+  uint32_t v, pc = 0, ic = 0;
+  unsigned long long by = 0;
+  if (i < 2 * K) wl_entry(i, K, G, perm, leaf_cnt, pt_off, bpp, v, pc, ic, by);
+  s_p[threadIdx.x] = pc;
+  s_i[threadIdx.x] = ic;
+  s_b[threadIdx.x] = by;
+  __syncthreads();
+  for (int o = kWlBlock / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_p[threadIdx.x] += s_p[threadIdx.x + o];
+      s_i[threadIdx.x] += s_i[threadIdx.x + o];
+      s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    }
+    __syncthreads();
   }
-  s_pair[threadIdx.x] = pc;
-  s_item[threadIdx.x] = ic;
-  s_bytes[threadIdx.x] = bytes;
+  if (threadIdx.x == 0) {
+    blk_pair[blockIdx.x] = s_p[0];
+    blk_item[blockIdx.x] = s_i[0];
+    blk_bytes[blockIdx.x] = s_b[0];
+  }
+}
+
+// (2) one CTA: exclusive scan of the block totals (in place), batch totals -> counters / stats
+__global__ void __launch_bounds__(1024) wl_scan_blocks_kernel(uint32_t* __restrict__ blk_pair,
+                                                              uint32_t* __restrict__ blk_item,
+                                                              const unsigned long long* __restrict__ blk_bytes,
+                                                              uint32_t nblocks,
+                                                              uint32_t* __restrict__ counters /* [0]=items,[1]=next */,
+                                                              unsigned long long* __restrict__ stats) {
+  __shared__ uint32_t s_p[1024], s_i[1024];
+  __shared__ unsigned long long s_b[1024];
+  const uint32_t per = (nblocks + 1023) / 1024;
+  const uint32_t b = threadIdx.x * per, e = min(nblocks, b + per);
+  uint32_t pc = 0, ic = 0;
+  unsigned long long by = 0;
+  for (uint32_t j = b; j < e; ++j) {
+    pc += blk_pair[j];
+    ic += blk_item[j];
+    by += blk_bytes[j];
+  }
+  s_p[threadIdx.x] = pc;
+  s_i[threadIdx.x] = ic;
+  s_b[threadIdx.x] = by;
   __syncthreads();
   for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
     uint32_t vp = 0, vi = 0;
     unsigned long long vb = 0;
     if (threadIdx.x >= o) {
-      vp = s_pair[threadIdx.x - o];
-      vi = s_item[threadIdx.x - o];
-      vb = s_bytes[threadIdx.x - o];
+      vp = s_p[threadIdx.x - o];
+      vi = s_i[threadIdx.x - o];
+      vb = s_b[threadIdx.x - o];
     }
     __syncthreads();
-    s_pair[threadIdx.x] += vp;
-    s_item[threadIdx.x] += vi;
-    s_bytes[threadIdx.x] += vb;
+    s_p[threadIdx.x] += vp;
+    s_i[threadIdx.x] += vi;
+    s_b[threadIdx.x] += vb;
     __syncthreads();
   }
-  uint32_t pbase = s_pair[threadIdx.x] - pc, ibase = s_item[threadIdx.x] - ic;
-  for (uint32_t i = b; i < e; ++i) {
-    const uint32_t v = vleaf(i);
-    uint32_t c = leaf_cnt[v];
-    pair_start[v] = pbase;
-    item_start[v] = ibase;
-    pbase += c;
-    ibase += (c + G - 1) / G;
+  uint32_t pbase = s_p[threadIdx.x] - pc, ibase = s_i[threadIdx.x] - ic;
+  for (uint32_t j = b; j < e; ++j) {
+    const uint32_t p = blk_pair[j], it = blk_item[j];
+    blk_pair[j] = pbase;
+    blk_item[j] = ibase;
+    pbase += p;
+    ibase += it;
   }
-  __syncthreads();
   if (threadIdx.x == 1023) {
-    counters[0] = s_item[1023];
+    counters[0] = s_i[1023];
     counters[1] = 0;
-    counters[2] = item_start[K + perm[0]];  // first class-B item = number of class-A items
-    atomicAdd(&stats[0], s_bytes[1023]);
-    atomicAdd(&stats[1], static_cast<unsigned long long>(s_pair[1023]));
+    atomicAdd(&stats[0], s_b[1023]);
+    atomicAdd(&stats[1], static_cast<unsigned long long>(s_p[1023]));
+  }
+}
+
+// (3) per-block exclusive scan + block offset -> pair_start / item_start of every virtual leaf; counters[2] = first
+// class-B item = number of class-A items
+__global__ void __launch_bounds__(kWlBlock) wl_offsets_kernel(const uint32_t* __restrict__ leaf_cnt, uint32_t K, int G,
+                                                              const uint32_t* __restrict__ perm,
+                                                              const uint64_t* __restrict__ pt_off, uint32_t bpp,
+                                                              const uint32_t* __restrict__ blk_pair,
+                                                              const uint32_t* __restrict__ blk_item,
+                                                              uint32_t* __restrict__ pair_start,
+                                                              uint32_t* __restrict__ item_start,
+                                                              uint32_t* __restrict__ counters) {
+  __shared__ uint32_t s_p[kWlBlock], s_i[kWlBlock];
+  const uint32_t i = blockIdx.x * kWlBlock + threadIdx.x;
+  uint32_t v = 0, pc = 0, ic = 0;
+  unsigned long long by = 0;
+  if (i < 2 * K) wl_entry(i, K, G, perm, leaf_cnt, pt_off, bpp, v, pc, ic, by);
+  s_p[threadIdx.x] = pc;
+  s_i[threadIdx.x] = ic;
+  __syncthreads();
+  for (int o = 1; o < kWlBlock; o <<= 1) {
+    uint32_t vp = 0, vi = 0;
+    if (threadIdx.x >= o) {
+      vp = s_p[threadIdx.x - o];
+      vi = s_i[threadIdx.x - o];
+    }
+    __syncthreads();
+    s_p[threadIdx.x] += vp;
+    s_i[threadIdx.x] += vi;
+    __syncthreads();
+  }
+  if (i < 2 * K) {
+    const uint32_t ps = blk_pair[blockIdx.x] + s_p[threadIdx.x] - pc, is = blk_item[blockIdx.x] + s_i[threadIdx.x] - ic;
+    pair_start[v] = ps;
+    item_start[v] = is;
+    if (i == K) counters[2] = is;
   }
 }
 
@@ -464,6 +541,10 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   uint32_t* pair_start = h->ws.take<uint32_t>(2 * K + 1);
   uint32_t* item_start = h->ws.take<uint32_t>(2 * K + 1);
   uint32_t* counters = h->ws.take<uint32_t>(4);
+  const size_t nwl = (2 * K + kWlBlock - 1) / kWlBlock;
+  uint32_t* wl_blk_pair = h->ws.take<uint32_t>(nwl);
+  uint32_t* wl_blk_item = h->ws.take<uint32_t>(nwl);
+  unsigned long long* wl_blk_bytes = h->ws.take<unsigned long long>(nwl);
   uint32_t* sorted_pairs = h->ws.take<uint32_t>(P);
   uint4* items = h->ws.take<uint4>(max_items);
   uint2* cand = h->ws.take<uint2>(P * R);
@@ -487,9 +568,14 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   unsigned pb = static_cast<unsigned>((P + 255) / 256);
   wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), h->pt_off.p,
                                      leaf_cnt);
-  wl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p,
-                                    static_cast<uint32_t>((h->S + 1) / 2), pair_start, item_start, counters,
-                                    h->stats.p);
+  {
+    const uint32_t nwb = static_cast<uint32_t>((2 * K + kWlBlock - 1) / kWlBlock), bpp32 = static_cast<uint32_t>((h->S + 1) / 2);
+    wl_reduce_kernel<<<nwb, kWlBlock, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p, bpp32,
+                                              wl_blk_pair, wl_blk_item, wl_blk_bytes);
+    wl_scan_blocks_kernel<<<1, 1024, 0, s>>>(wl_blk_pair, wl_blk_item, wl_blk_bytes, nwb, counters, h->stats.p);
+    wl_offsets_kernel<<<nwb, kWlBlock, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p, bpp32,
+                                               wl_blk_pair, wl_blk_item, pair_start, item_start, counters);
+  }
   wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), h->pt_off.p,
                                        pair_start, cursor, sorted_pairs);
   wl_items_kernel<<<static_cast<unsigned>((2 * K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
@@ -536,7 +622,7 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   h->ck.cand = cand;
   h->ck.cand_cnt = cand_cnt;
   h->ck.qthr = qthr;
-  h->prof_launches += (tokens_in ? 0 : (h->ptc.ready ? 3 : 2)) + 4;  // partition (2 or 3 kernels) + 4 worklist kernels
+  h->prof_launches += (tokens_in ? 0 : (h->ptc.ready ? 3 : 2)) + 6;  // partition (2 or 3 kernels) + 6 worklist kernels
   if (two_phase) {
     // 3a. probe of the class-A items: the first probe_blocks() blocks of every query's closest leaf prove a bound in
     // bounded time (a full scan of the largest leaves would serialise on a few CTAs); phase 2 scans them in full
@@ -619,6 +705,9 @@ static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, siz
   add((2 * K + 1) * 4);
   add((2 * K + 1) * 4);
   add(16);
+  add(((2 * K + 255) / 256) * 4);
+  add(((2 * K + 255) / 256) * 4);
+  add(((2 * K + 255) / 256) * 8);
   add(P * 4);
   add((P + 2 * K + 2) * 16);
   add(P * R * 8);
