@@ -13,9 +13,11 @@ A "step" = one search_batched pass of the hot path over one batch of --nq synthe
   cpu_baseline  the CPU oracle (C++ restatement of the reference algorithm, all host threads) on a bounded
            sample of the same workload
 --impl reference times that CPU arm alone (the reference crate is Rust and cannot be built here).
-Multi-GPU (torchrun, one rank per GPU): rows are sharded round-robin inside every partition, each rank
-returns its local top-k, shards merge with an NCCL all-gather of (id, distance) pairs + a k-way merge
-kernel; the dataset size is fixed, so scaling is "strong".
+Multi-GPU (torchrun, one rank per GPU): the index is sharded by whole partitions (shard plan balanced on the probe
+load of a calibration batch), every rank searches the whole batch on its shard with the two-phase protocol of
+scann-rust_b200/distributed.py (token slices all-gathered, closest-leaf bounds all-reduced, local top-k all-gathered
+and merged by a kernel); the dataset size is fixed, so scaling is "strong".  --shard rows selects SURVEY §8e's
+round-robin-inside-partitions alternative.
 """
 import argparse
 import importlib

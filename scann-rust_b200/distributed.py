@@ -1,7 +1,12 @@
-"""Multi-GPU plumbing: one process per GPU, the index row-sharded round-robin inside every
-partition (``indexing.shard_index``), every rank searches the whole query batch on its shard and returns its
-local top-k (exact distances, global ids); the shards are merged with ONE all-gather of (id, distance) pairs
-(80 B per query per rank at k = 10) and a k-way merge kernel ordered by (distance, id).
+"""Multi-GPU plumbing: one process per GPU, the index sharded (whole partitions per rank in bench.py;
+``indexing.shard_index`` implements the rows-round-robin-inside-partitions alternative), every rank searches the whole
+query batch on its shard and returns its local top-k (exact distances, global ids).
+
+  two_phase_search     the Tree-AH step on a sharded index: token slices all-gathered, closest-leaf bounds all-reduced
+                       (MIN), scan under the global bounds (include/scann_b200.h scann_treeah_search_begin/_end)
+  exchange_and_merge   ONE all-gather of the packed [2, nq, k] result buffer (80 B per query per rank at k = 10) and a
+                       k-way merge kernel ordered by (distance, id)
+  sharded_search       both, for any searcher (falls back to a plain local search + exchange)
 
 torch.distributed is only the transport (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
 from __future__ import annotations
