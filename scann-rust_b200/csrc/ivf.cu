@@ -133,13 +133,33 @@ __global__ void __launch_bounds__(256) ivf_topk_kernel(const IvfArgs a) {
     const uint32_t leaf = a.tokens[q * a.L + lo];
     return a.ids[a.pt_off[leaf] + (static_cast<uint32_t>(i) - prefix[lo])];
   };
+  int cur = 0;  // leaf rank of this thread's previous candidate: block_topr_sorted calls gen with increasing i
   auto gen = [&](int i) -> uint64_t {
-    const uint32_t id = member(i);
+    while (cur + 1 < a.L && prefix[cur + 1] <= static_cast<uint32_t>(i)) ++cur;
+    const uint32_t id = a.ids[a.pt_off[a.tokens[q * a.L + cur]] + (static_cast<uint32_t>(i) - prefix[cur])];
     float d;
     if (a.lut_mode) {
+      // LookupTable::compute_distance: sum += distances[s][code_s] for s = 0..S-1, in that order.  The code row is
+      // fetched with the widest aligned loads available (one byte load per subspace made the kernel LSU-bound).
       const uint8_t* c = a.codes + static_cast<size_t>(id) * a.S;
       d = 0.0f;
-      for (int s = 0; s < a.S; ++s) d = __fadd_rn(d, lut[s * a.C + c[s]]);
+      auto add4 = [&](uint32_t w, int s0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d = __fadd_rn(d, lut[(s0 + j) * a.C + ((w >> (8 * j)) & 0xFFu)]);
+      };
+      if ((a.S & 15) == 0) {
+        for (int s0 = 0; s0 < a.S; s0 += 16) {
+          const uint4 w = __ldg(reinterpret_cast<const uint4*>(c + s0));
+          add4(w.x, s0);
+          add4(w.y, s0 + 4);
+          add4(w.z, s0 + 8);
+          add4(w.w, s0 + 12);
+        }
+      } else if ((a.S & 3) == 0) {
+        for (int s0 = 0; s0 < a.S; s0 += 4) add4(__ldg(reinterpret_cast<const uint32_t*>(c + s0)), s0);
+      } else {
+        for (int s = 0; s < a.S; ++s) d = __fadd_rn(d, lut[s * a.C + c[s]]);
+      }
     } else {
       d = exact_pair_distance_1t(qs, a.raw + static_cast<size_t>(id) * a.stride, a.dim, a.measure, vec);
     }

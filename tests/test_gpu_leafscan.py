@@ -32,9 +32,9 @@ def test_search_partitioned_matches_oracle(gpu_lib, oracle, measure, n, dim, K, 
     assert (ids == oids).all()                                        # stable sort: ties keep candidate order
 
 
-@pytest.mark.parametrize("C", [16, 256])
-def test_search_tree_ah_variant_b_matches_oracle(gpu_lib, oracle, C):
-    n, dim, K, S, L, k = 15_000, 32, 24, 8, 5, 10
+@pytest.mark.parametrize("C,dim,S", [(16, 32, 8), (256, 32, 8), (16, 96, 48), (64, 30, 6)])
+def test_search_tree_ah_variant_b_matches_oracle(gpu_lib, oracle, C, dim, S):
+    n, K, L, k = 15_000, 24, 5, 10
     x, centers, order, off = _ivf_index(oracle, n, dim, K, 12)
     ds = dim // S
     rng = np.random.default_rng(C)
