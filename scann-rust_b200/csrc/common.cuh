@@ -310,6 +310,53 @@ __device__ int block_topr_sorted(Gen gen, int n, int R, uint64_t* buf, uint64_t*
 }
 
 
+// Grouped variant of block_topr_sorted: LANES adjacent lanes (a power of two <= 32) cooperate on one candidate.
+// gen(i, sub) is called by all lanes of a group with the same i (and by every lane of the warp at the same time, so
+// it may shuffle); the key it returns on sub == 0 is the one that is kept.  Same shared-memory needs and result.
+template <int NT, int CHUNK, int LANES, class Gen>
+__device__ int block_topr_sorted_grouped(Gen gen, int n, int R, uint64_t* buf, uint64_t* out, uint32_t* hist,
+                                         uint64_t thr_init = ~0ull) {
+  const int tid = threadIdx.x;
+  const int p2 = next_pow2(R < 1 ? 1 : R);
+  const int grp = tid / LANES, sub = tid % LANES;
+  if (tid == 0) hist[258] = 0;
+  __syncthreads();
+  uint64_t thr = thr_init;
+  for (int base = 0; base < n; base += CHUNK) {
+    const int end = base + CHUNK < n ? base + CHUNK : n;
+    for (int i0 = base; i0 < end; i0 += NT / LANES) {
+      const int i = i0 + grp;
+      const bool valid = i < end;
+      const uint64_t k = gen(valid ? i : end - 1, sub);
+      if (valid && sub == 0 && k < thr) {
+        uint32_t slot = atomicAdd(&hist[258], 1u);
+        buf[slot] = k;
+      }
+    }
+    __syncthreads();
+    int c = static_cast<int>(hist[258]);
+    if (c > R && R > 0) {
+      uint64_t T = block_radix_threshold<NT>(buf, c, R, hist);
+      if (tid == 0) hist[258] = 0;
+      __syncthreads();
+      for (int i = tid; i < c; i += NT) {
+        uint64_t k = buf[i];
+        if (k <= T) out[atomicAdd(&hist[258], 1u)] = k;
+      }
+      __syncthreads();
+      for (int i = tid; i < R; i += NT) buf[i] = out[i];
+      thr = T;
+      __syncthreads();
+    }
+  }
+  int m = static_cast<int>(hist[258]);
+  if (R <= 0) m = 0;
+  for (int i = tid; i < p2; i += NT) out[i] = i < m ? buf[i] : ~0ull;
+  __syncthreads();
+  block_bitonic_sort<NT>(out, p2);
+  return m;
+}
+
 // ---- warp-level upper bound of the need-th smallest of row[0..n) ----------------------------------------------------
 // One 256-bucket linear histogram over [min, max of the finite entries]: the bucket that holds the need-th smallest
 // value ends at the returned edge (>= that value; the slack covers the rounding of the bucket arithmetic).  Entries

@@ -165,7 +165,21 @@ __global__ void __launch_bounds__(256) ivf_topk_kernel(const IvfArgs a) {
     }
     return (static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(i);
   };
-  const int m = block_topr_sorted<256, kIvfChunk>(gen, total, a.k, buf, out, hist);
+  int m;
+  if (a.lut_mode) {
+    m = block_topr_sorted<256, kIvfChunk>(gen, total, a.k, buf, out, hist);
+  } else {
+    // exact mode: 8 lanes per member read its row as full 32-byte sectors (x86.rs lane order, common.cuh
+    // exact_pair_distance) — a thread per member touched twice as many sectors with a quarter of the loads in flight
+    int cur8 = 0;
+    auto gen8 = [&](int i, int sub) -> uint64_t {
+      while (cur8 + 1 < a.L && prefix[cur8 + 1] <= static_cast<uint32_t>(i)) ++cur8;
+      const uint32_t id = a.ids[a.pt_off[a.tokens[q * a.L + cur8]] + (static_cast<uint32_t>(i) - prefix[cur8])];
+      const float d = exact_pair_distance<false>(qs, a.raw + static_cast<size_t>(id) * a.stride, a.dim, a.measure, 0.0f, sub);
+      return (static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(i);
+    };
+    m = block_topr_sorted_grouped<256, kIvfChunk, 8>(gen8, total, a.k, buf, out, hist);
+  }
   // out[0..m): ascending (distance, candidate position) keys
   if (a.reorder_measure >= 0 && a.raw != nullptr) {
     for (int j = tid; j < p2; j += 256) {
