@@ -8,10 +8,13 @@
 //                                                     (src/hashes/hasher.rs:162-185)
 // plus ReorderingHelper::reorder (src/utils/reordering.rs:23-54) of the k results.
 //
-// One CTA per query streams the concatenated member lists of its leaves; a thread scores one member:
-//   exact mode: the reference's AVX2+FMA summation order restated by ONE thread (8 lane accumulators, the fixed
-//               hsum tree, un-fused scalar tail) so the value is bit-identical to x86.rs:72-165;
-//   LUT mode  : sequential f32 sum of S table entries, the table in shared memory.
+// One CTA per query streams the concatenated member lists of its leaves:
+//   exact mode: 8 adjacent lanes score one member in the reference's AVX2+FMA lane order (common.cuh
+//               exact_pair_distance: lane-wise FMA, the fixed hsum tree, un-fused scalar tail), so the value is
+//               bit-identical to x86.rs:72-165 and every load is a full 32-byte sector of the member's row;
+//   LUT mode  : a thread per member — 16-byte loads of its code row, sequential f32 sum of S table entries, the table
+//               in shared memory.
+// (exact_pair_distance_1t, the single-thread restatement of the same order, re-scores the k results for `reorder`.)
 // Keys (ordered distance << 32 | position in the concatenated candidate list) go through the block-wide streaming
 // top-k (common.cuh); ascending keys = the reference's stable sort by distance.
 // Bound: HBM (exact mode gathers D*4-byte rows: Σ|leaf| * D * 4 B per query; LUT mode S bytes per member).
