@@ -369,3 +369,28 @@ def test_treex_search_structural(oracle):
         # reordered distances are exact SqL2
         for i, d in zip(ids[0], dists[0]):
             assert d == np.float32(oracle.pair_distance(oracle.SQL2, q[0], x[i]))
+
+
+# ----------------------------------------------------------------------------- restrict filter (oracle side)
+def test_oracle_search_with_filter_properties(oracle):
+    """TreeXHybridSearcher::search_with_filter (tree_x_hybrid/mod.rs:245-250, 327-332) in the oracle: an all-allowed
+    filter is the plain search; a real filter only returns allowed datapoints and equals the plain search of an index
+    whose partitions contain only the allowed rows (the reference skips filtered-out rows before the per-leaf top-k)."""
+    import helpers
+    x, _ = helpers.clustered(4000, 16, 12, 0.35, 3)
+    q = (x[:20] + 0.03).astype(np.float32)
+    idx = helpers.build_index(oracle, x, 10, 4)
+    args = (idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"], x, q, 4, 30, 10)
+    rc, ids0, d0, c0 = oracle.treex_search(*args, lut16=True)
+    rc, ids1, d1, c1 = oracle.treex_search(*args, lut16=True, allow=np.packbits(np.ones(4000, bool), bitorder="little"))
+    assert (ids0 == ids1).all() and (d0.view(np.uint32) == d1.view(np.uint32)).all()
+    allowed = np.random.default_rng(1).random(4000) < 0.4
+    rc, ids2, d2, c2 = oracle.treex_search(*args, lut16=True, allow=np.packbits(allowed, bitorder="little"))
+    assert allowed[ids2[ids2 != 0xFFFFFFFF]].all()
+    keep = allowed[idx["ids"]]
+    off = idx["part_offsets"].astype(np.int64)
+    cnt = np.array([keep[off[i]:off[i + 1]].sum() for i in range(len(off) - 1)])
+    off2 = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+    rc, ids3, d3, c3 = oracle.treex_search(idx["centers"], idx["codebook"], off2, np.ascontiguousarray(idx["ids"][keep]),
+                                           np.ascontiguousarray(idx["packed"][keep]), x, q, 4, 30, 10, lut16=True)
+    assert (ids2 == ids3).all() and (d2.view(np.uint32) == d3.view(np.uint32)).all() and (c2 == c3).all()
