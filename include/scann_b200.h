@@ -234,14 +234,14 @@ scann_status scann_lut16_scan(const uint8_t* packed, size_t n, size_t S, const u
  * device: v[q][r] = hx[r] - bf16(q * qscale) . bf16(x_r) with f32 accumulation; hx = |x_r|^2 / 2 (of
  * (i8)x * scale for rows_i8) when want_norm, else 0; qscale = scale for i8 rows, 1 otherwise.
  *   thr == NULL: dense[nq*n] receives every score.
- *   thr != NULL: the ids of the rows with v <= thr[q] are appended to cand[q*cap ...] in arbitrary order;
- *                cand_cnt[q] counts them (values above cap mean overflow: only cap ids were stored).
+ *   thr != NULL: the rows with v <= thr[q] are appended to cand[q*cap ...] as (ordered_key(v) << 32 | row) in
+ *                arbitrary order; cand_cnt[q] counts them (values above cap mean overflow: only cap were stored).
  * Host buffers only.  No value this tap returns is ever a search result: the searchers re-score the survivors
  * exactly in the reference's summation order.
  * ------------------------------------------------------------------------------------------- */
 scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const void* rows, int rows_i8, size_t n,
                              size_t stride, float scale, int want_norm, const float* thr, float* dense,
-                             uint32_t* cand, size_t cap, uint32_t* cand_cnt, int device);
+                             uint64_t* cand, size_t cap, uint32_t* cand_cnt, int device);
 
 /* ---------------------------------------------------------------------------------------------
  * Index-build helpers with the reference's exact semantics (needed to build the

@@ -20,7 +20,9 @@
 //      plus f32 accumulation slack).  Any row with v > thr is beaten by the k sample rows whatever the
 //      rounding did, so it cannot be among the exact top-k.
 //   c. FILTER pass over all rows appends the rows with v <= thr to per-query lists (a few hundred to ~1-2k).
-//   d. rescore_lists_kernel: exact distances of the list in the reference's AVX2 order, (distance, id) order.
+//   d. rescore_lists_kernel: second certification inside the list (only the rows within 2*eps of the list's k-th
+//      smallest score can be in the top-k: k + a few tens of the ~900), exact distances of those in the reference's
+//      AVX2 order, (distance, id) order.
 // Results are therefore the exact top-k by the reference's own f32 distances, not "top-k up to GEMM rounding".
 // A list overflow (cap 4096: huge k, or massively duplicated rows) sends that query chunk through steps 1-3.
 #include <string.h>
@@ -400,7 +402,7 @@ struct BfCore {
     const size_t qpad = tc_queries_pad(nqc, dim);
     return Workspace::padded(qpad * tc_kpad(dim) * 2) + Workspace::padded(qpad * 4) +
            Workspace::padded(nqc * tc_sample_tiles() * 128 * 4) +
-           Workspace::padded(nqc * 4) * 2 + Workspace::padded(nqc * kTcCap * 4);
+           Workspace::padded(nqc * 4) * 2 + Workspace::padded(nqc * kTcCap * 8);
   }
   scann_status tc_chunk(const float* qsrc, size_t nqc, size_t k, size_t kk, uint32_t* oid, float* od, uint32_t* oc,
                         cudaStream_t s, bool* overflow) {
@@ -411,7 +413,7 @@ struct BfCore {
     float* dense = ws.take<float>(nqc * scols);
     float* thr = ws.take<float>(nqc);
     uint32_t* cnt = ws.take<uint32_t>(nqc);
-    uint32_t* lists = ws.take<uint32_t>(nqc * kTcCap);
+    unsigned long long* lists = ws.take<unsigned long long>(nqc * kTcCap);
     uint32_t* flag = reinterpret_cast<uint32_t*>(d_small.p + 1);
     SCANN_TRY(tc_prepare_queries(qsrc, nqc, dim, i8 ? scale : 1.0f, qbf, qn, s));
     TcScoreParams p;
@@ -451,7 +453,8 @@ struct BfCore {
     bf_overflow_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(cnt, nqc, kTcCap, flag);
     SCANN_CUDA(cudaMemcpyAsync(h_flag, flag, 4, cudaMemcpyDeviceToHost, s));
     // d. exact re-score (harmless if a list overflowed: the outputs are rewritten by the legacy chunk)
-    SCANN_TRY(launch_rescore_lists(rescore_params(qsrc), lists, cnt, nqc, kTcCap, k, n, oid, od, oc, s));
+    SCANN_TRY(launch_rescore_lists(rescore_params(qsrc), lists, cnt, nqc, kTcCap, k, n, oid, od, oc, s,
+                                   __builtin_huge_valf(), nullptr, qn, xmax2));
     SCANN_CUDA(cudaStreamSynchronize(s));
     *overflow = *h_flag != 0;
     if (!*overflow) ++stat_tc_chunks;
@@ -482,14 +485,14 @@ struct BfCore {
     const size_t chunk = std::min<size_t>(kTcQTile, nq);
     const size_t kpad = tc_kpad(dim), rpad = tc_rows_pad(n);
     size_t need = Workspace::padded(tc_queries_pad(chunk, dim) * kpad * 2) + Workspace::padded(tc_queries_pad(chunk, dim) * 4) +
-                  Workspace::padded(chunk * 4) * 2 + Workspace::padded(chunk * kTcCap * 4) + 4096;
+                  Workspace::padded(chunk * 4) * 2 + Workspace::padded(chunk * kTcCap * 8) + 4096;
     if (host) need += Workspace::padded(chunk * dim * 4) + 2 * Workspace::padded(chunk * k * 4) + Workspace::padded(chunk * 4);
     SCANN_TRY(ws.reserve(need));
     uint16_t* qbf = ws.take<uint16_t>(tc_queries_pad(chunk, dim) * kpad);
     float* qn = ws.take<float>(tc_queries_pad(chunk, dim));
     float* thr = ws.take<float>(chunk);
     uint32_t* cnt = ws.take<uint32_t>(chunk);
-    uint32_t* lists = ws.take<uint32_t>(chunk * kTcCap);
+    unsigned long long* lists = ws.take<unsigned long long>(chunk * kTcCap);
     float* hq = nullptr;
     uint32_t *hids = nullptr, *hcounts = nullptr;
     float* hd = nullptr;

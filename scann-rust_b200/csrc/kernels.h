@@ -30,11 +30,13 @@ void launch_transpose(const float* in, size_t rows, size_t cols, float* out, cud
 //   cand: [nq][kc] candidate row ids (0xFFFFFFFF = empty); writes ids/dists [nq][k], counts [nq]
 scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, size_t nq, size_t kc, size_t k,
                                  uint32_t* ids, float* dists, uint32_t* counts, cudaStream_t s);
-//   lists: [nq][cap] row ids, cnt [nq] entries appended (clamped to cap); rows >= n_rows ignored
-scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists, const uint32_t* cnt,
+//   lists: [nq][cap] (score key << 32 | row), cnt [nq] entries appended (clamped to cap); rows >= n_rows ignored.
+//   qn != nullptr: two-level certification — only the entries within 2*eps of the list's k-th smallest score are
+//   re-scored (qn = |q|^2 per query, xmax2 = max |x|^2; see brute_force.cu)
+scann_status launch_rescore_lists(const RescoreParams& rp, const unsigned long long* lists, const uint32_t* cnt,
                                   size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
                                   uint32_t* counts, cudaStream_t s, float radius = __builtin_huge_valf(),
-                                  uint32_t* flag = nullptr);  // radius: keep d <= radius; flag |= 2 when > k qualify
+                                  uint32_t* flag = nullptr, const float* qn = nullptr, float xmax2 = 0.0f);  // radius: keep d <= radius; flag |= 2 when > k qualify
 //   part_stride: elements between two parts' blocks (0 = nq * k, the dense [parts][nq][k] layout)
 scann_status launch_merge_topk(const uint32_t* ids_in, const float* dists_in, size_t parts, size_t nq, size_t k,
                                uint32_t* ids_out, float* dists_out, uint32_t* counts_out, cudaStream_t s,
@@ -54,7 +56,7 @@ struct TcScoreParams {
   float* dense;              // [nq][ld], column = t * 128 + (row inside tile t); whole tiles are written
   size_t ld;
   const float* thr;          // [nq]
-  uint32_t* cand;            // [nq][cap] row ids, arbitrary order
+  unsigned long long* cand;  // [nq][cap] (ordered score key << 32 | row), arbitrary order
   size_t cap;
   uint32_t* cand_cnt;        // [nq]
   int sms;

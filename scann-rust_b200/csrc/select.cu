@@ -78,38 +78,74 @@ scann_status launch_rescore_topk(const RescoreParams& rp, const uint32_t* cand, 
 }
 
 // Variable-length variant for the tensor-core ranking path (tc_gemm.cu FILTER lists): lists[q][0 .. min(cnt[q], cap))
-// hold row ids in arbitrary order.  Same exact distances, same
-// (distance, id) order, first k written.  One CTA per query; the sort is sized to this query's list.
+// hold (ordered score key << 32 | row) entries in arbitrary order.  One CTA per query:
+//   1. two-level certification (qn != nullptr): the list contains every row whose ranking score v is at most the
+//      filter threshold, hence the k rows with the smallest v overall.  With v_(k) the k-th smallest v of the list and
+//      eps the bound on |v - exact| (brute_force.cu), a row with v > v_(k) + 2*eps is beaten by those k rows whatever
+//      the rounding did — only the rows within 2*eps of v_(k) are re-scored (k + a few tens instead of ~900);
+//   2. exact distances of the survivors in the reference's AVX2 order, (distance, id) order, first k written.
 template <bool I8>
 __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams rp,
-                                                            const uint32_t* __restrict__ lists,
+                                                            const unsigned long long* __restrict__ lists,
                                                             const uint32_t* __restrict__ cnt, int cap, int k,
                                                             uint32_t n_rows, float radius, uint32_t* __restrict__ flag,
+                                                            const float* __restrict__ qn, float xmax2,
                                                             uint32_t* __restrict__ ids, float* __restrict__ dists,
                                                             uint32_t* __restrict__ counts) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int tid = threadIdx.x;
   const size_t q = blockIdx.x;
   const int c = static_cast<int>(min(cnt[q], static_cast<uint32_t>(cap)));
-  const int p2 = next_pow2(c < 1 ? 1 : c);
-  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);                              // [next_pow2(cap)]
-  float* qs = reinterpret_cast<float*>(keys + next_pow2(cap < 1 ? 1 : cap));   // [dim]
+  const int p2cap = next_pow2(cap < 1 ? 1 : cap);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sm);              // [p2cap]
+  uint32_t* sel = reinterpret_cast<uint32_t*>(keys + p2cap);     // [cap] rows to re-score
+  uint32_t* hist = sel + cap;                                    // [264]
+  float* qs = reinterpret_cast<float*>(hist + 264);              // [dim]
   const int dim = static_cast<int>(rp.dim);
+  const float inf = __int_as_float(0x7F800000);
   for (int d = tid; d < dim; d += 256) qs[d] = rp.queries[q * rp.dim + d];
+  const unsigned long long* lq = lists + q * static_cast<size_t>(cap);
+  for (int j = tid; j < c; j += 256) {
+    // padding rows of the operand tiles (row >= n_rows) can enter a list when thr = +inf or hx is skipped (Dot): they
+    // must not take part in the k-th-score selection
+    const unsigned long long e = lq[j];
+    keys[j] = static_cast<uint32_t>(e & 0xFFFFFFFFull) < n_rows ? e : ~0ull;
+  }
+  __syncthreads();
+  float thr2 = inf;
+  if (qn != nullptr && c > k) {  // uniform over the CTA
+    const uint64_t T = block_radix_threshold<256>(keys, c, k, hist);
+    const float vk = key_f32(static_cast<uint32_t>(T >> 32));
+    const float nqr = sqrtf(qn[q]), nx = sqrtf(xmax2);
+    const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+    thr2 = vk + 2.0f * eps;
+    thr2 = thr2 + fabsf(thr2) * 1e-6f;
+    if (!(thr2 == thr2)) thr2 = inf;
+  }
+  if (tid == 0) hist[258] = 0;
+  __syncthreads();
+  for (int j = tid; j < c; j += 256) {
+    const uint64_t key = keys[j];
+    const uint32_t row = static_cast<uint32_t>(key & 0xFFFFFFFFull);
+    const float v = key_f32(static_cast<uint32_t>(key >> 32));
+    // rows >= n_rows: padding rows of the operand tiles can enter a list when thr = +inf or hx is skipped (Dot)
+    if (row < n_rows && !(v > thr2)) sel[atomicAdd(&hist[258], 1u)] = row;
+  }
+  __syncthreads();
+  const int m2 = static_cast<int>(hist[258]);
+  const int p2 = next_pow2(m2 < 1 ? 1 : m2);
   for (int j = tid; j < p2; j += 256) keys[j] = ~0ull;
   __syncthreads();
-  const uint32_t* lq = lists + q * static_cast<size_t>(cap);
   const int grp = tid >> 3, sub = tid & 7;
-  for (int j0 = 0; j0 < c; j0 += 32) {
+  for (int j0 = 0; j0 < m2; j0 += 32) {
     const int j = j0 + grp;
-    uint32_t id = j < c ? lq[j] : 0xFFFFFFFFu;
-    const bool valid = id < n_rows;  // padding rows of the operand tiles can enter a list when thr = +inf
-    if (!valid) id = 0;
+    const bool valid = j < m2;
+    const uint32_t id = valid ? sel[j] : 0u;
     const void* row = I8 ? static_cast<const void*>(rp.raw_i8 + static_cast<size_t>(id) * rp.stride)
                          : static_cast<const void*>(rp.raw + static_cast<size_t>(id) * rp.stride);
     const float d = exact_pair_distance<I8>(qs, row, dim, rp.measure, rp.scale, sub);
     // radius search (searcher.rs:142-167): keep d <= radius only (radius = +inf for the top-k searches)
-    const bool in_radius = radius == __int_as_float(0x7F800000) ? true : d <= radius;
+    const bool in_radius = radius == inf ? true : d <= radius;
     if (valid && sub == 0 && in_radius) keys[j] = (static_cast<uint64_t>(f32_key(d)) << 32) | id;
   }
   __syncthreads();
@@ -118,7 +154,7 @@ __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams 
     const uint64_t key = j < p2 ? keys[j] : ~0ull;
     const bool ok = key != ~0ull;
     ids[q * k + j] = ok ? static_cast<uint32_t>(key & 0xFFFFFFFFu) : 0xFFFFFFFFu;
-    dists[q * k + j] = ok ? key_f32(static_cast<uint32_t>(key >> 32)) : __int_as_float(0x7F800000);
+    dists[q * k + j] = ok ? key_f32(static_cast<uint32_t>(key >> 32)) : inf;
   }
   if (tid == 0) {
     int m = 0;
@@ -130,24 +166,25 @@ __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams 
   }
 }
 
-scann_status launch_rescore_lists(const RescoreParams& rp, const uint32_t* lists, const uint32_t* cnt,
+scann_status launch_rescore_lists(const RescoreParams& rp, const unsigned long long* lists, const uint32_t* cnt,
                                   size_t nq, size_t cap, size_t k, size_t n_rows, uint32_t* ids, float* dists,
-                                  uint32_t* counts, cudaStream_t s, float radius, uint32_t* flag) {
+                                  uint32_t* counts, cudaStream_t s, float radius, uint32_t* flag, const float* qn,
+                                  float xmax2) {
   if (nq == 0) return SCANN_OK;
   SCANN_REQUIRE(cap >= 1 && cap <= 8192, SCANN_INVALID_ARGUMENT, "candidate list capacity %zu out of range", cap);
-  const size_t smem = static_cast<size_t>(next_pow2(static_cast<int>(cap))) * 8 + rp.dim * 4 + 16;
+  const size_t smem = static_cast<size_t>(next_pow2(static_cast<int>(cap))) * 8 + cap * 4 + 264 * 4 + rp.dim * 4 + 16;
   if (rp.raw_i8) {
     SCANN_CUDA(cudaFuncSetAttribute(rescore_lists_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
     rescore_lists_kernel<true><<<static_cast<unsigned>(nq), 256, smem, s>>>(
-        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), radius, flag, ids, dists,
-        counts);
+        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), radius, flag, qn, xmax2,
+        ids, dists, counts);
   } else {
     SCANN_CUDA(cudaFuncSetAttribute(rescore_lists_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));
     rescore_lists_kernel<false><<<static_cast<unsigned>(nq), 256, smem, s>>>(
-        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), radius, flag, ids, dists,
-        counts);
+        rp, lists, cnt, static_cast<int>(cap), static_cast<int>(k), static_cast<uint32_t>(n_rows), radius, flag, qn, xmax2,
+        ids, dists, counts);
   }
   SCANN_CUDA(cudaGetLastError());
   return SCANN_OK;

@@ -18,7 +18,7 @@
 //                              tcgen05.commit releases the B slot and publishes the accumulator
 //   warps 2-17  epilogue       tcgen05.ld 32x32b.x32 (thread = one query row), then either
 //                              DENSE : v -> out[q][row]                                  (first rows / centroids)
-//                              FILTER: v <= thr[q] -> append the row id to the query's candidate list
+//                              FILTER: v <= thr[q] -> append (score key, row) to the query's candidate list
 // A work unit is (query super-tile of MT*128 queries, run of row tiles).  Units that run at the same time
 // share the row run, so the rows are read from HBM once and from L2 by the other CTAs.
 #include <cuda.h>
@@ -44,9 +44,9 @@ constexpr int kTcTmemCols = 512;
 // FILTER staging: every epilogue warp queues its survivors (row, lane) in shared memory and flushes the queue with
 // one global atomic per entry, all lanes at once — a survivor costs a shared-memory atomic instead of a serialised
 // round trip to L2 (at ~1 survivor per 1024 scores nearly every 32x32 chunk has one).
-constexpr int kWqCap = 256;                          // entries per warp queue
+constexpr int kWqCap = 192;                          // entries per warp queue
 constexpr int kWqStep = 128;                         // most entries one filter step can add (32 lanes x 4 columns)
-constexpr int kWqBytes = kWqCap * 4 + kWqCap + 16;   // rows u32, lanes u8, count u32 (+ pad)
+constexpr int kWqBytes = kWqCap * 8 + kWqCap + 16;   // (score key, row) u64, lanes u8, count u32 (+ pad)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -132,7 +132,7 @@ struct TcArgs {
   float* dense;             // DENSE: [nq][ld], column = row - row0
   size_t ld;
   const float* thr;         // FILTER: [nq] keep v <= thr
-  uint32_t* cand;           // FILTER: [nq][cap] row ids in arbitrary order
+  unsigned long long* cand; // FILTER: [nq][cap] (ordered score key << 32 | row) in arbitrary order
   uint32_t cap;
   uint32_t* cand_cnt;       // FILTER: [nq] appended (may exceed cap = overflow)
   int no_hx;                // FILTER with hx == 0 for every real row (Dot): v = -acc, the hx loads and subtractions are
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     constexpr int ncols = MT == 2 ? kTcBN / 2 : kTcBN / 4;
     const int c0 = (MT == 2 ? (grp & 1) : grp) * ncols;
     constexpr int nchunks = ncols / 32;
-    uint32_t* const wq_rows = reinterpret_cast<uint32_t*>(wq_base + e * kWqBytes);
+    unsigned long long* const wq_rows = reinterpret_cast<unsigned long long*>(wq_base + e * kWqBytes);
     uint8_t* const wq_lanes = reinterpret_cast<uint8_t*>(wq_rows + kWqCap);
     volatile uint32_t* const wq_cnt = reinterpret_cast<uint32_t*>(wq_lanes + kWqCap);
     if (lane == 0) *wq_cnt = 0;
@@ -359,7 +359,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     for (int j = 0; j < 4; ++j) {
                       if (v[8 * g8 + 4 * h4 + j] <= thr) {
                         const uint32_t sl = atomicAdd(const_cast<uint32_t*>(wq_cnt), 1u);
-                        wq_rows[sl] = row_tile + cc + 8 * g8 + 4 * h4 + j;
+                        wq_rows[sl] = (static_cast<unsigned long long>(f32_key(v[8 * g8 + 4 * h4 + j])) << 32) |
+                                      (row_tile + cc + 8 * g8 + 4 * h4 + j);
                         wq_lanes[sl] = static_cast<uint8_t>(lane);
                       }
                     }
@@ -570,7 +571,7 @@ extern "C" {
 
 scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const void* rows, int rows_i8, size_t n,
                              size_t stride, float scale, int want_norm, const float* thr, float* dense,
-                             uint32_t* cand, size_t cap, uint32_t* cand_cnt, int device) {
+                             uint64_t* cand, size_t cap, uint32_t* cand_cnt, int device) {
   using namespace scann;
   SCANN_REQUIRE(queries && rows && nq > 0 && n > 0 && dim > 0 && stride >= dim, SCANN_INVALID_ARGUMENT, "bad arguments");
   SCANN_REQUIRE(thr ? (cand && cand_cnt && cap > 0) : dense != nullptr, SCANN_INVALID_ARGUMENT, "missing output");
@@ -582,7 +583,8 @@ scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const 
   DevBuf<float> d_q, d_hx, d_qn, d_dense, d_thr;
   DevBuf<uint8_t> d_rows;
   DevBuf<uint16_t> d_rb, d_qb;
-  DevBuf<uint32_t> d_cand, d_cnt;
+  DevBuf<unsigned long long> d_cand;
+  DevBuf<uint32_t> d_cnt;
   cudaStream_t s = 0;
   SCANN_TRY(d_q.upload(queries, nq * dim, SCANN_HOST, s));
   SCANN_TRY(d_rows.upload(static_cast<const uint8_t*>(rows), n * stride * esz, SCANN_HOST, s));
@@ -623,7 +625,7 @@ scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const 
   }
   SCANN_TRY(launch_tc_scores(p, s));
   if (thr) {
-    SCANN_CUDA(cudaMemcpyAsync(cand, d_cand.p, nq * cap * 4, cudaMemcpyDeviceToHost, s));
+    SCANN_CUDA(cudaMemcpyAsync(cand, d_cand.p, nq * cap * 8, cudaMemcpyDeviceToHost, s));
     SCANN_CUDA(cudaMemcpyAsync(cand_cnt, d_cnt.p, nq * 4, cudaMemcpyDeviceToHost, s));
   } else {
     SCANN_CUDA(cudaMemcpy2DAsync(dense, n * 4, d_dense.p, rpad * 4, n * 4, nq, cudaMemcpyDeviceToHost, s));

@@ -688,7 +688,7 @@ def lut16_scan(packed, S: int, lut8, device: int = 0):
 
 def tc_scores(queries, rows, scale: float = 1.0, want_norm: bool = True, thr=None, cap: int = 0, device: int = 0):
     """Parity tap of the tcgen05 ranking contraction (csrc/tc_gemm.cu): v = hx - bf16(q)·bf16(x).
-    rows f32 or int8 [n, dim]; → dense [nq, n] f32, or with thr [nq]: (cand [nq, cap] u32 row ids, counts [nq])."""
+    rows f32 or int8 [n, dim]; → dense [nq, n] f32, or with thr [nq]: (cand [nq, cap] u64 = score key << 32 | row, counts [nq])."""
     capi.require_gpu()
     q = capi.as_f32(queries)
     i8 = np.asarray(rows).dtype == np.int8
@@ -701,7 +701,7 @@ def tc_scores(queries, rows, scale: float = 1.0, want_norm: bool = True, thr=Non
                                                int(want_norm), None, capi.np_ptr(dense), None, 0, None, device))
         return dense
     t = capi.as_f32(thr)
-    cand = np.zeros((nq, cap), np.uint32)
+    cand = np.zeros((nq, cap), np.uint64)
     cnt = np.zeros(nq, np.uint32)
     capi.check(capi.load().scann_tc_scores(capi.np_ptr(q), nq, dim, capi.np_ptr(r), int(i8), n, stride, scale,
                                            int(want_norm), capi.np_ptr(t), None, capi.np_ptr(cand), cap,

@@ -62,9 +62,9 @@ def test_tc_filter_lists(gpu_lib):
         if i == 11:
             continue
         want = np.nonzero(dense[i] <= thr[i])[0]
-        rows = np.sort(cand[i, :cnt[i]].astype(np.int64))
+        rows = np.sort((cand[i, :cnt[i]] & np.uint64(0xFFFFFFFF)).astype(np.int64))
         assert cnt[i] == len(want) and (rows == want).all(), f"query {i}"
-    rows11 = cand[11].astype(np.int64)
+    rows11 = (cand[11] & np.uint64(0xFFFFFFFF)).astype(np.int64)
     assert len(set(rows11.tolist())) == cap and rows11.max() < (n + 127) // 128 * 128
 
 
