@@ -121,6 +121,17 @@ class BruteForceSearcher {
     if (b.ok() && !b.value.empty()) r.value = std::move(b.value[0]);
     return r;
   }
+  // search_radius(&[T], radius) (searcher.rs:142-167): every row with distance <= radius, ascending.  max_results
+  // bounds the output (ResourceExhausted when more rows qualify).
+  Result<NNResultsVector> search_radius(const std::vector<float>& query, float radius, size_t max_results = 1024) const {
+    Result<NNResultsVector> r;
+    std::vector<uint32_t> ids(max_results), counts(1);
+    std::vector<float> dists(max_results);
+    r.error = make_error(scann_bf_search_radius(h_, query.data(), 1, query.size(), radius, max_results, ids.data(),
+                                                dists.data(), counts.data(), SCANN_HOST, nullptr));
+    if (r.ok()) r.value = detail::unflatten(ids, dists, counts, max_results)[0];
+    return r;
+  }
 
  private:
   scann_bf* h_ = nullptr;
@@ -287,6 +298,19 @@ class TreeXHybridSearcher {
     Result<NNResultsVector> r;
     r.error = b.error;
     if (b.ok() && !b.value.empty()) r.value = std::move(b.value[0]);
+    return r;
+  }
+  // search_with_filter(&[f32], k, Some(filter)) (:245-250): `allowed[i]` = RestrictFilter::is_allowed(i)
+  Result<NNResultsVector> search_with_filter(const std::vector<float>& query, size_t k,
+                                             const std::vector<bool>& allowed) const {
+    std::vector<uint8_t> bits((allowed.size() + 7) / 8, 0);
+    for (size_t i = 0; i < allowed.size(); ++i)
+      if (allowed[i]) bits[i >> 3] |= static_cast<uint8_t>(1u << (i & 7));
+    Result<NNResultsVector> r;
+    r.error = make_error(scann_treeah_set_filter(h_, bits.data(), allowed.size(), SCANN_HOST));
+    if (!r.ok()) return r;
+    r = search(query, k);
+    scann_treeah_set_filter(h_, nullptr, 0, SCANN_HOST);
     return r;
   }
   const TreeXHybridConfig& config() const { return cfg_; }

@@ -36,6 +36,10 @@ int main() {
   auto er = empty.value.search({1.f, 2.f, 3.f}, 5);
   CHECK(er.ok() && er.value.empty());
 
+  auto rad = bf.value.search_radius({0.f, 0.f, 0.f}, 1.5f);  // test_brute_force_radius_search (searcher.rs:327-340)
+  CHECK(rad.ok() && rad.value.size() == 4 && rad.value[0].first == 0);
+  for (auto& pr : rad.value) CHECK(pr.second <= 1.5f);
+
   const float dot3[3 * 2] = {1, 0, 0, 1, 1, 1};
   auto dp = BruteForceSearcher::create(dot3, 3, 2, 2, DistanceMeasure::DotProduct);
   CHECK(dp.ok());
