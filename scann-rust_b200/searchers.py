@@ -122,11 +122,47 @@ def results_to_lists(ids, dists, counts):
     return [[(int(ids[i, j]), float(dists[i, j])) for j in range(int(counts[i]))] for i in range(ids.shape[0])]
 
 
+@dataclass
+class SearchParameters:
+    """SearchParameters (src/searcher.rs:23-77), the fields the GPU path reads."""
+    num_neighbors: Optional[int] = None
+    pre_reordering_num_neighbors: Optional[int] = None
+
+    def with_num_neighbors(self, k: int):
+        self.num_neighbors = int(k)
+        return self
+
+    def with_pre_reordering_neighbors(self, n: int):
+        self.pre_reordering_num_neighbors = int(n)
+        return self
+
+
 class _Handle:
     _destroy = None
 
     def __init__(self):
         self._h = C.c_void_p(None)
+
+    def search_batched_with_params(self, queries, params, default_k: int = 10):
+        """Searcher::search_batched_with_params (src/searcher.rs:164-169): one SearchParameters per query.  Queries
+        that share their parameters go to the GPU as one batch; the result is one [(index, distance)] list per query,
+        in query order.  queries.len() != params.len() → InvalidArgument (brute_force/searcher.rs:233-237)."""
+        q = queries if _is_torch(queries) else np.asarray(queries, np.float32)
+        if len(q) != len(params):
+            raise ScannError(capi.INVALID_ARGUMENT, "Number of queries must match number of parameter sets")
+        groups = {}
+        for i, p in enumerate(params):
+            key = (p.num_neighbors if p.num_neighbors is not None else default_k, p.pre_reordering_num_neighbors)
+            groups.setdefault(key, []).append(i)
+        out = [None] * len(params)
+        for (k, pre), idxs in groups.items():
+            sub = q[idxs]
+            kw = {"pre_reorder_k": pre} if pre is not None and "pre_reorder_k" in self.search_batched.__code__.co_varnames \
+                else {}
+            ids, dists, counts = self.search_batched(sub, k, **kw)[:3]
+            for j, lst in zip(idxs, results_to_lists(ids, dists, counts)):
+                out[j] = lst
+        return out
 
     def close(self):
         if self._h and self._h.value:

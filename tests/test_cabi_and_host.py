@@ -140,3 +140,31 @@ def test_oracle_scann_modes(oracle):
     rc, ids2, d2, c2 = oracle.scann_tree_ah(idx["centers"], idx["part_offsets"], idx["ids"], idx["codebook"],
                                             codes_by_id, x, q, 3, 5)
     assert rc == 0 and (c2 == 5).all() and (np.diff(d2, axis=1) >= 0).all()
+
+
+def test_search_batched_with_params_groups_queries(pkg):
+    """Searcher::search_batched_with_params (src/searcher.rs:164-169) host logic: queries sharing their parameters form
+    one batch, results come back in query order, and a length mismatch is InvalidArgument (searcher.rs:233-237)."""
+    from importlib import import_module
+    s = import_module("scann-rust_b200.searchers")
+    calls = []
+
+    class Stub(s._Handle):  # no GPU: search_batched is replaced by a recorder with a deterministic answer
+        def search_batched(self, queries, k, pre_reorder_k=None):
+            q = np.asarray(queries, np.float32)
+            calls.append((len(q), k, pre_reorder_k))
+            ids = (q[:, :1].astype(np.uint32) * 100 + np.arange(k, dtype=np.uint32)[None, :])
+            return ids, ids.astype(np.float32), np.full(len(q), k, np.uint32)
+
+    st = Stub()
+    q = np.arange(5, dtype=np.float32)[:, None] * np.ones((1, 3), np.float32)
+    P = s.SearchParameters
+    params = [P().with_num_neighbors(2), P().with_num_neighbors(4), P().with_num_neighbors(2),
+              P().with_num_neighbors(2).with_pre_reordering_neighbors(50), P()]
+    out = st.search_batched_with_params(q, params, default_k=3)
+    assert sorted(calls) == [(1, 2, 50), (1, 3, None), (1, 4, None), (2, 2, None)]
+    assert [len(r) for r in out] == [2, 4, 2, 2, 3]
+    assert [r[0][0] for r in out] == [0, 100, 200, 300, 400]          # query order preserved
+    with pytest.raises(pkg.ScannError) as e:
+        st.search_batched_with_params(q, params[:3])
+    assert e.value.code == pkg.capi.INVALID_ARGUMENT
