@@ -517,3 +517,15 @@ def test_treeah_search_with_filter(gpu_lib, oracle, keep_frac, nq):
     rc, pids, _, _ = oracle.treex_search(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"],
                                          x, qs, L, R, k, lut16=True, nthreads=8)
     assert helpers.recall(ids2, pids, k) >= 0.99
+
+
+def test_search_batched_with_params_on_gpu(gpu_lib, oracle):
+    # Searcher::search_batched_with_params: per-query k, grouped into GPU batches, answers in query order
+    db = helpers.gaussian(2000, 16, 3)
+    q = helpers.gaussian(6, 16, 4)
+    P = gpu_lib.SearchParameters
+    ks = [3, 7, 3, 1, 7, 5]
+    out = gpu_lib.BruteForceSearcher(db).search_batched_with_params(q, [P().with_num_neighbors(k) for k in ks])
+    for i, k in enumerate(ks):
+        rc, oi, od, oc = oracle.bf_search(db, q[i:i + 1], k, oracle.SQL2)
+        assert [p[0] for p in out[i]] == list(oi[0]) and len(out[i]) == k
