@@ -147,6 +147,17 @@ scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, con
                                  const uint8_t* packed, const uint32_t* ids, const uint64_t* part_offsets,
                                  size_t n, const float* raw, size_t num_raw, size_t stride, int use_residuals,
                                  int reorder_measure, int device, int memspace, scann_treeah** out);
+/* scann_treeah_create with layout flags (sharded / very large indexes):
+ *   SCANN_TREEAH_RAW_BY_POSITION  raw holds one row per INDEX ROW in the order of packed/ids (row = part_offsets[leaf] +
+ *                                 position) instead of being indexed by datapoint id — a shard keeps only its own rows
+ *                                 while ids stay global (num_raw must equal n);
+ *   SCANN_TREEAH_BORROW_RAW       device arrays only: raw is not copied, the caller keeps it alive until destroy. */
+enum { SCANN_TREEAH_RAW_BY_POSITION = 1, SCANN_TREEAH_BORROW_RAW = 2 };
+scann_status scann_treeah_create_ex(const float* centers, size_t K, size_t dim, const float* codebook, size_t S,
+                                    const uint8_t* packed, const uint32_t* ids, const uint64_t* part_offsets,
+                                    size_t n, const float* raw, size_t num_raw, size_t stride, int use_residuals,
+                                    int reorder_measure, uint32_t flags, int device, int memspace,
+                                    scann_treeah** out);
 scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t nq, size_t qdim, size_t L, size_t R,
                                  size_t k, uint32_t* ids, float* dists, uint32_t* counts, uint32_t* cand_ids,
                                  float* cand_dists, uint32_t* cand_counts, int memspace, void* stream);

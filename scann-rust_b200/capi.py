@@ -25,6 +25,7 @@ _CODE_NAMES = {
 }
 
 SQL2, L2, DOT = 0, 1, 2
+TREEAH_RAW_BY_POSITION, TREEAH_BORROW_RAW = 1, 2
 HOST, DEVICE = 0, 1
 
 # every symbol include/scann_b200.h declares (tests check that the library exports all of them)
@@ -33,7 +34,7 @@ SYMBOLS = [
     "scann_bf_create", "scann_bf_search", "scann_bf_search_radius", "scann_bf_destroy", "scann_bf_path_stats", "scann_sq8_path_stats",
     "scann_sq8_quantize", "scann_sq8_create", "scann_sq8_search", "scann_sq8_destroy",
     "scann_part_create", "scann_part_select", "scann_part_destroy",
-    "scann_treeah_create", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
+    "scann_treeah_create", "scann_treeah_create_ex", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
     "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end", "scann_treeah_partition",
     "scann_treeah_set_filter",
     "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_merge_topk_packed", "scann_tc_scores",
@@ -89,6 +90,8 @@ def load():
     L.scann_part_destroy.restype = None
     L.scann_treeah_create.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, sz, vp, sz, sz, i32, i32, i32, i32,
                                       C.POINTER(vp)]
+    L.scann_treeah_create_ex.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, sz, vp, sz, sz, i32, i32, C.c_uint32, i32, i32,
+                                         C.POINTER(vp)]
     L.scann_treeah_search.argtypes = [vp, vp, sz, sz, sz, sz, sz, vp, vp, vp, vp, vp, vp, i32, vp]
     L.scann_treeah_destroy.argtypes = [vp]
     L.scann_treeah_destroy.restype = None

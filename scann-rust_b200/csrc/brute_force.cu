@@ -16,7 +16,7 @@
 // Default path for dim <= 256 — tensor cores (tc_gemm.cu: tcgen05.mma bf16, TMEM accumulators, TMA operands):
 //   a. DENSE scores v = hx - q~.x~ of a strided sample of <= 16384 rows; per query an upper bound v_k of the k-th
 //      smallest sample score (hence of the k-th best over all rows), from a 256-bucket histogram of the row.
-//   b. thr[q] = v_k + 2*eps_q, eps_q = a rigorous bound on |v - exact| (bf16 operand rounding: 2^-8 |q| max|x|,
+//   b. thr[q] = v_k + 2*eps_q, eps_q = a rigorous bound on |v - exact| (bf16 operand rounding: 2^-7 |q| max|x| for f32 rows, 2^-8 for int8 rows,
 //      plus f32 accumulation slack).  Any row with v > thr is beaten by the k sample rows whatever the
 //      rounding did, so it cannot be among the exact top-k.
 //   c. FILTER pass over all rows appends the rows with v <= thr to per-query lists (a few hundred to ~1-2k).
@@ -217,7 +217,7 @@ __global__ void state_to_cand_kernel(const uint64_t* __restrict__ state, size_t 
 // k-th smallest keeps the certification argument, and it is 4x cheaper than an exact select of the row.
 __global__ void __launch_bounds__(256) bf_bound_kernel(const float* __restrict__ dense, int ld, int ncols, int kk,
                                                        const float* __restrict__ qn, float xmax2, size_t nq,
-                                                       float* __restrict__ thr) {
+                                                       int rows_i8, float* __restrict__ thr) {
   __shared__ uint32_t s_hist[8][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const size_t q = static_cast<size_t>(blockIdx.x) * 8 + warp;
@@ -225,9 +225,7 @@ __global__ void __launch_bounds__(256) bf_bound_kernel(const float* __restrict__
   const float inf = __int_as_float(0x7F800000);
   const float vU = warp_kth_upper_bound(dense + q * ld, ncols, static_cast<uint32_t>(kk), s_hist[warp], lane);
   const float nqr = sqrtf(qn[q]), nx = sqrtf(xmax2);
-  // bf16 RN: |q~.x~ - q.x| <= (2^-8 + 2^-18) sum|q_j x_j| <= 1.001 * 2^-8 |q||x|; the second term covers the f32
-  // accumulation of the tensor core, of hx and of the reference's own AVX2 sum (all <= ~dim * 2^-23 relative)
-  const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+  const float eps = tc_rank_eps(nqr, nx, rows_i8 != 0);  // common.cuh
   float t = vU + 2.0f * eps;
   t = t + fabsf(t) * 1e-6f;
   if (lane == 0) thr[q] = (t == t) ? t : inf;
@@ -236,11 +234,11 @@ __global__ void __launch_bounds__(256) bf_bound_kernel(const float* __restrict__
 // radius search: thr[q] in score units so that every row whose exact distance can be <= radius passes the filter
 //   SqL2: d <= r  <=>  (d - |q|^2)/2 <= (r - |q|^2)/2;  L2: d <= r^2;  Dot: -q.x <= r
 __global__ void bf_radius_thr_kernel(const float* __restrict__ qn, float xmax2, float radius, int measure, size_t nq,
-                                     float* __restrict__ thr) {
+                                     int rows_i8, float* __restrict__ thr) {
   const size_t q = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   const float nqr = sqrtf(qn[q]), nx = sqrtf(xmax2);
-  const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+  const float eps = tc_rank_eps(nqr, nx, rows_i8 != 0);
   float t;
   if (measure == SCANN_DOT) t = radius;
   else if (measure == SCANN_L2) t = radius < 0.0f ? -1.0f - qn[q] : 0.5f * (radius * radius * 1.000001f - qn[q]);
@@ -438,7 +436,7 @@ struct BfCore {
     // b. certified threshold from the sample
     bf_bound_kernel<<<static_cast<unsigned>((nqc + 7) / 8), 256, 0, s>>>(dense, static_cast<int>(scols),
                                                                         static_cast<int>(scols), static_cast<int>(kk),
-                                                                        qn, xmax2, nqc, thr);
+                                                                        qn, xmax2, nqc, i8 ? 1 : 0, thr);
     SCANN_CUDA(cudaMemsetAsync(cnt, 0, nqc * 4, s));
     SCANN_CUDA(cudaMemsetAsync(flag, 0, 4, s));
     p.nrows = rpad;
@@ -511,7 +509,7 @@ struct BfCore {
         qsrc = hq;
       }
       SCANN_TRY(tc_prepare_queries(qsrc, nqc, dim, i8 ? scale : 1.0f, qbf, qn, s));
-      bf_radius_thr_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(qn, xmax2, radius, measure, nqc, thr);
+      bf_radius_thr_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(qn, xmax2, radius, measure, nqc, i8 ? 1 : 0, thr);
       SCANN_CUDA(cudaMemsetAsync(cnt, 0, nqc * 4, s));
       SCANN_CUDA(cudaMemsetAsync(flag, 0, 4, s));
       TcScoreParams p;
@@ -640,44 +638,90 @@ struct BfCore {
 };
 
 // ---- scalar quantiser (build helper) -----------------------------------------------------------
-// QuantizationStats::from_dataset (src/quantization/mod.rs:77-110): f32 min/max, f64 Σ and Σ²
+// QuantizationStats::from_dataset (src/quantization/mod.rs:77-110): f32 min/max (order-independent, parallel)
 __global__ void __launch_bounds__(256) sq8_stats_kernel(const float* __restrict__ db, size_t n, size_t dim,
-                                                        size_t stride, double* __restrict__ acc /* sum, sumsq */,
+                                                        size_t stride,
                                                         float* __restrict__ mm /* min,max as ordered u32 */) {
-  __shared__ double s_sum[256], s_sq[256];
   __shared__ uint32_t s_mn[256], s_mx[256];
-  double sum = 0.0, sq = 0.0;
   uint32_t mn = 0xFFFFFFFFu, mx = 0;
   const size_t total = n * dim;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     size_t r = i / dim, d = i - r * dim;
-    float v = db[r * stride + d];
-    sum += static_cast<double>(v);
-    sq += static_cast<double>(v) * static_cast<double>(v);
-    uint32_t kf = f32_key(v);
+    uint32_t kf = f32_key(db[r * stride + d]);
     mn = min(mn, kf);
     mx = max(mx, kf);
   }
-  s_sum[threadIdx.x] = sum;
-  s_sq[threadIdx.x] = sq;
   s_mn[threadIdx.x] = mn;
   s_mx[threadIdx.x] = mx;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) {
-      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
-      s_sq[threadIdx.x] += s_sq[threadIdx.x + o];
       s_mn[threadIdx.x] = min(s_mn[threadIdx.x], s_mn[threadIdx.x + o]);
       s_mx[threadIdx.x] = max(s_mx[threadIdx.x], s_mx[threadIdx.x + o]);
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    atomicAdd(&acc[0], s_sum[0]);
-    atomicAdd(&acc[1], s_sq[0]);
     atomicMin(reinterpret_cast<uint32_t*>(mm), s_mn[0]);
     atomicMax(reinterpret_cast<uint32_t*>(mm) + 1, s_mx[0]);
+  }
+}
+
+// The f64 sums of QuantizationStats::from_dataset are SEQUENTIAL in the reference (mod.rs:84-94): every add rounds, so
+// the result depends on the order and a parallel reduction differs in the last bits — enough to move mean/std by an
+// f32 ulp and codes across a rounding boundary.  This kernel replays the reference's order exactly: one thread adds
+// the values in row-major order (sum and sum of squares are two independent dependent chains; v*v is exact in f64)
+// out of a shared-memory chunk while the other warps stage the next chunk.  Build-time only: ~0.5 s per 128M values.
+constexpr int kSeqChunk = 4096;  // 2 x 16 KB of static shared memory
+__global__ void __launch_bounds__(256) sq8_seqsum_kernel(const float* __restrict__ db, size_t n, size_t dim,
+                                                         size_t stride, double* __restrict__ acc /* sum, sumsq */) {
+  __shared__ float buf[2][kSeqChunk];
+  const size_t total = n * dim;
+  const size_t nchunks = (total + kSeqChunk - 1) / kSeqChunk;
+  auto load = [&](size_t c, int b) {  // warps 1..7
+    const size_t base = c * kSeqChunk;
+    for (int i = threadIdx.x - 32; i < kSeqChunk; i += 224) {
+      const size_t e = base + i;
+      float v = 0.0f;
+      if (e < total) {
+        const size_t r = e / dim, d = e - r * dim;
+        v = db[r * stride + d];
+      }
+      buf[b][i] = v;
+    }
+  };
+  if (threadIdx.x >= 32) load(0, 0);
+  __syncthreads();
+  double sum = 0.0, sq = 0.0;
+  for (size_t c = 0; c < nchunks; ++c) {
+    const int b = static_cast<int>(c & 1);
+    if (threadIdx.x >= 32) {
+      if (c + 1 < nchunks) load(c + 1, b ^ 1);
+    } else if (threadIdx.x == 0) {
+      const size_t left = total - c * kSeqChunk;
+      const int m = left < static_cast<size_t>(kSeqChunk) ? static_cast<int>(left) : kSeqChunk;
+      const float4* p4 = reinterpret_cast<const float4*>(buf[b]);
+      int i = 0;
+      for (; i + 4 <= m; i += 4) {
+        const float4 v = p4[i >> 2];
+        const double a0 = static_cast<double>(v.x), a1 = static_cast<double>(v.y), a2 = static_cast<double>(v.z),
+                     a3 = static_cast<double>(v.w);
+        sum = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sum, a0), a1), a2), a3);
+        sq = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(sq, __dmul_rn(a0, a0)), __dmul_rn(a1, a1)), __dmul_rn(a2, a2)),
+                       __dmul_rn(a3, a3));
+      }
+      for (; i < m; ++i) {
+        const double a0 = static_cast<double>(buf[b][i]);
+        sum = __dadd_rn(sum, a0);
+        sq = __dadd_rn(sq, __dmul_rn(a0, a0));
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    acc[0] = sum;
+    acc[1] = sq;
   }
 }
 
@@ -828,7 +872,8 @@ scann_status scann_sq8_quantize(const float* db, size_t n, size_t dim, size_t st
   SCANN_CUDA(cudaMemset(d_acc.p, 0, 2 * sizeof(double)));
   uint32_t init_mm[2] = {0xFFFFFFFFu, 0u};
   SCANN_CUDA(cudaMemcpy(d_mm.p, init_mm, sizeof(init_mm), cudaMemcpyHostToDevice));
-  sq8_stats_kernel<<<148 * 4, 256>>>(src, n, dim, stride, d_acc.p, d_mm.p);
+  sq8_stats_kernel<<<148 * 4, 256>>>(src, n, dim, stride, d_mm.p);  // min / max (order-independent)
+  sq8_seqsum_kernel<<<1, 256>>>(src, n, dim, stride, d_acc.p);                // sums in the reference's order
   SCANN_CUDA(cudaGetLastError());
   double acc[2];
   uint32_t mmk[2];
@@ -841,9 +886,8 @@ scann_status scann_sq8_quantize(const float* db, size_t n, size_t dim, size_t st
     return f;
   };
   // Host-side scalar epilogue of QuantizationStats::from_dataset + ScalarQuantizer::calibrate
-  // (quantization/mod.rs:96-102, scalar.rs:112-129).  NOTE: the f64 sums are reduced in a different
-  // order than the reference's sequential loop; mean/std can differ in the last f64 bits before the
-  // cast to f32 (documented in DESIGN.md).
+  // (quantization/mod.rs:96-102, scalar.rs:112-129) on the sequentially accumulated f64 sums: bit-identical to the
+  // reference's calibration.
   const double count = static_cast<double>(n) * static_cast<double>(dim);
   const float data_min = unkey(mmk[0]), data_max = unkey(mmk[1]);
   const float mean = static_cast<float>(acc[0] / count);

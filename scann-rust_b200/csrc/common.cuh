@@ -183,6 +183,16 @@ __device__ __forceinline__ float exact_pair_distance(const float* __restrict__ q
   return r;
 }
 
+// ---- certified error bound of the bf16 tensor-core ranking score (tc_gemm.cu) ------------------------------------------
+// |q~.x~ - q.x| with both operands rounded to bf16 (RN, 8 significant bits: unit roundoff u = 2^-8) is bounded by
+// (2u + u^2) sum|q_j x_j| <= (2^-7 + 2^-16) |q||x| < 0.0079 |q||x|; when the rows are int8 they are exact in bf16 and
+// only the query rounds: u |q||x| < 0.0040 |q||x|.  The second term covers the f32 accumulation of the tensor core, of
+// hx and of the reference's own sum (all <= ~dim * 2^-23 relative).
+__device__ __forceinline__ float tc_rank_eps(float nqr, float nx, bool rows_exact_in_bf16) {
+  const float c = rows_exact_in_bf16 ? 0.0040f : 0.0079f;
+  return c * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+}
+
 // ---- block-level exact selection of the R smallest distinct u64 keys ---------------------------
 // hist: 264 u32 of shared memory ([0..255] bins, [256] digit, [257] below, [258] counter)
 template <int NT>
@@ -287,6 +297,7 @@ __device__ int block_topr_sorted(Gen gen, int n, int R, uint64_t* buf, uint64_t*
     }
     __syncthreads();
     int c = static_cast<int>(hist[258]);
+    __syncthreads();  // every thread has read c before the next chunk's appends can change hist[258]: c is block-uniform
     if (c > R && R > 0) {
       uint64_t T = block_radix_threshold<NT>(buf, c, R, hist);
       if (tid == 0) hist[258] = 0;
@@ -335,6 +346,7 @@ __device__ int block_topr_sorted_grouped(Gen gen, int n, int R, uint64_t* buf, u
     }
     __syncthreads();
     int c = static_cast<int>(hist[258]);
+    __syncthreads();  // every thread has read c before the next chunk's appends can change hist[258]: c is block-uniform
     if (c > R && R > 0) {
       uint64_t T = block_radix_threshold<NT>(buf, c, R, hist);
       if (tid == 0) hist[258] = 0;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kPtWarps * 32) part_tc_select_kernel(
   const float vU = warp_kth_upper_bound(row, K, static_cast<uint32_t>(Leff), hist, lane);
   // (2) certified threshold (same bound as bf_bound_kernel in brute_force.cu)
   const float nqr = sqrtf(qn[q]), nx = sqrtf(cmax2);
-  const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+  const float eps = tc_rank_eps(nqr, nx, false);
   float thr = vU + 2.0f * eps;
   thr = thr + fabsf(thr) * 1e-6f;
   if (!(thr == thr)) thr = inf;

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) rescore_lists_kernel(const RescoreParams 
     const uint64_t T = block_radix_threshold<256>(keys, c, k, hist);
     const float vk = key_f32(static_cast<uint32_t>(T >> 32));
     const float nqr = sqrtf(qn[q]), nx = sqrtf(xmax2);
-    const float eps = 0.0042f * nqr * nx + 1.6e-5f * (nqr + nx) * (nqr + nx);
+    const float eps = tc_rank_eps(nqr, nx, I8);
     thr2 = vk + 2.0f * eps;
     thr2 = thr2 + fabsf(thr2) * 1e-6f;
     if (!(thr2 == thr2)) thr2 = inf;

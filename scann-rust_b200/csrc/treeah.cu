@@ -287,6 +287,8 @@ struct MergeArgs {
   const uint32_t* ids;
   const float* raw;
   size_t stride;
+  size_t num_raw;
+  int raw_by_pos;  // raw rows are stored in leaf order (row = pt_off[leaf] + position) instead of by datapoint id
   const float* queries;
   int dim, L, R, k, measure;
   uint32_t K;
@@ -309,8 +311,9 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
   uint64_t* out = buf + (a.R + kMergeChunk);                    // [p2]
   uint32_t* hist = reinterpret_cast<uint32_t*>(out + p2);       // [264]
   uint32_t* prefix = hist + 264;                                // [L + 1]
-  uint32_t* cid = prefix + (a.L + 1);                           // [p2]
-  float* qs = reinterpret_cast<float*>(cid + p2);               // [dim]
+  uint32_t* cid = prefix + (a.L + 1);                           // [p2] datapoint ids
+  uint32_t* crow = cid + p2;                                    // [p2] raw row of each candidate
+  float* qs = reinterpret_cast<float*>(crow + p2);              // [dim]
   const int tid = threadIdx.x;
   const size_t q = blockIdx.x;
 
@@ -354,16 +357,19 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
 
   // the R approximate candidates, in (approx distance, leaf rank, position) order
   for (int j = tid; j < p2; j += NT) {
-    uint32_t id = 0xFFFFFFFFu;
+    uint32_t id = 0xFFFFFFFFu, row = 0xFFFFFFFFu;
     float ad = __int_as_float(0x7F800000);
     if (j < m) {
       uint64_t key = out[j];
       uint32_t r = static_cast<uint32_t>((key >> 22) & 1023u), pos = static_cast<uint32_t>(key & 0x3FFFFFu);
       uint32_t leaf = a.tokens[q * a.L + r];
-      id = a.ids[a.pt_off[leaf] + pos];
+      const uint64_t at = a.pt_off[leaf] + pos;
+      id = a.ids[at];
+      row = a.raw_by_pos ? static_cast<uint32_t>(at) : id;
       ad = key_f32(static_cast<uint32_t>(key >> 32));
     }
     cid[j] = id;
+    crow[j] = row;
     if (a.cand_ids && j < a.R) {
       a.cand_ids[q * a.R + j] = id;
       a.cand_dists[q * a.R + j] = ad;
@@ -379,9 +385,13 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
     for (int j0 = 0; j0 < m; j0 += NT / 8) {
       int j = j0 + grp;
       bool valid = j < m;
-      const float* row = a.raw + static_cast<size_t>(valid ? cid[j] : cid[0]) * a.stride;
+      // a row index outside the raw array (malformed index: the reference skips it via dataset.get(idx)) is dropped
+      const uint32_t ri = crow[valid ? j : 0];
+      const bool have = ri < a.num_raw;
+      const float* row = a.raw + static_cast<size_t>(have ? ri : 0u) * a.stride;
       float d = exact_pair_distance<false>(qs, row, a.dim, a.measure, 0.0f, sub);
-      if (valid && sub == 0) fin[j] = (static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(j);
+      if (valid && sub == 0)
+        fin[j] = have ? ((static_cast<uint64_t>(f32_key(d)) << 32) | static_cast<uint32_t>(j)) : ~0ull;
     }
     for (int j = m + tid; j < p2; j += NT) fin[j] = ~0ull;
     __syncthreads();
@@ -391,7 +401,8 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
       fin[j] = j < m ? ((out[j] & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>(j)) : ~0ull;
     __syncthreads();
   }
-  const int kk = a.k < m ? a.k : m;
+  int kk = a.k < m ? a.k : m;
+  while (kk > 0 && fin[kk - 1] == ~0ull) --kk;  // candidates whose raw row does not exist were dropped (sorted last)
   for (int j = tid; j < a.k; j += NT) {
     if (j < kk) {
       uint64_t key = fin[j];
@@ -408,7 +419,7 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
 static size_t merge_smem_bytes(int R, int L, int dim) {
   int p2 = next_pow2(R < 1 ? 1 : R);
   return (static_cast<size_t>(R) + kMergeChunk + p2) * 8 + 264 * 4 + (static_cast<size_t>(L) + 1) * 4 +
-         static_cast<size_t>(p2) * 4 + static_cast<size_t>(dim) * 4 + 16;
+         static_cast<size_t>(p2) * 8 + static_cast<size_t>(dim) * 4 + 16;
 }
 
 }  // namespace scann
@@ -420,6 +431,8 @@ struct scann_treeah {
   int use_residuals = 1, reorder_measure = SCANN_SQL2, pos_bits = 18;
   uint32_t max_leaf = 0;
   scann::DevBuf<float> centers, centersT, codebook, raw;
+  const float* raw_p = nullptr;  // raw.p, or the caller's device array (SCANN_TREEAH_BORROW_RAW)
+  bool raw_by_pos = false;       // SCANN_TREEAH_RAW_BY_POSITION
   scann::DevBuf<uint32_t> codes, ids, blk_off, leaf_perm;  // leaf_perm: leaves by descending size
   scann::DevBuf<uint32_t> blk_leaf;                        // leaf of every 256-point block
   scann::DevBuf<uint8_t> allow_blk;                        // restrict filter in block order (scann_treeah_set_filter)
@@ -532,8 +545,10 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   int G = avg >= 6.0 ? 8 : (avg >= 3.0 ? 4 : (avg >= 1.5 ? 2 : 1));
   size_t max_items = P / G + 2 * std::min<size_t>(K, P) + 1;
 
-  float* scratch = reinterpret_cast<float*>(h->ws.take<uint8_t>(
-      std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0))));
+  // centre-score scratch of the partition stage (not needed when the caller partitioned)
+  float* scratch = tokens_in ? nullptr
+                             : reinterpret_cast<float*>(h->ws.take<uint8_t>(std::max(
+                                   nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0))));
   uint32_t* tokens = h->ws.take<uint32_t>(P);
   if (tokens_in) tokens = const_cast<uint32_t*>(tokens_in);  // the caller partitioned (and keeps the array alive)
   uint32_t* leaf_cnt = h->ws.take<uint32_t>(4 * K);  // counts + cursors of the 2K virtual leaves
@@ -662,8 +677,10 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
   m.tokens = h->ck.tokens;
   m.pt_off = h->pt_off.p;
   m.ids = h->ids.p;
-  m.raw = h->raw.p;
+  m.raw = h->raw_p;
   m.stride = h->stride;
+  m.num_raw = h->num_raw;
+  m.raw_by_pos = h->raw_by_pos ? 1 : 0;
   m.queries = h->ck.dq;
   m.dim = static_cast<int>(h->dim);
   m.L = static_cast<int>(L);
@@ -695,11 +712,12 @@ static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t
   return treeah_phase2(h, false, nullptr, d_ids, d_dists, d_counts, d_cand_ids, d_cand_dists, d_cand_counts, s);
 }
 
-static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, size_t R, size_t k, bool host) {
+static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, size_t R, size_t k, bool host,
+                                 bool have_tokens = false) {
   size_t K = h->K, P = nq * L;
   size_t b = 0;
   auto add = [&](size_t bytes) { b += Workspace::padded(bytes); };
-  add(std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0)));
+  if (!have_tokens) add(std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0)));
   add(P * 4);
   add(4 * K * 4);
   add((2 * K + 1) * 4);
@@ -733,7 +751,22 @@ scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, con
                                  const uint8_t* packed, const uint32_t* ids, const uint64_t* part_offsets,
                                  size_t n, const float* raw, size_t num_raw, size_t stride, int use_residuals,
                                  int reorder_measure, int device, int memspace, scann_treeah** out) {
+  return scann_treeah_create_ex(centers, K, dim, codebook, S, packed, ids, part_offsets, n, raw, num_raw, stride,
+                                use_residuals, reorder_measure, 0u, device, memspace, out);
+}
+
+scann_status scann_treeah_create_ex(const float* centers, size_t K, size_t dim, const float* codebook, size_t S,
+                                    const uint8_t* packed, const uint32_t* ids, const uint64_t* part_offsets,
+                                    size_t n, const float* raw, size_t num_raw, size_t stride, int use_residuals,
+                                    int reorder_measure, uint32_t flags, int device, int memspace,
+                                    scann_treeah** out) {
   using namespace scann;
+  SCANN_REQUIRE((flags & ~(SCANN_TREEAH_RAW_BY_POSITION | SCANN_TREEAH_BORROW_RAW)) == 0, SCANN_INVALID_ARGUMENT,
+                "unknown flags 0x%x", flags);
+  SCANN_REQUIRE(!(flags & SCANN_TREEAH_BORROW_RAW) || memspace == SCANN_DEVICE, SCANN_INVALID_ARGUMENT,
+                "SCANN_TREEAH_BORROW_RAW needs device-resident arrays");
+  SCANN_REQUIRE(!(flags & SCANN_TREEAH_RAW_BY_POSITION) || raw == nullptr || num_raw == n, SCANN_INVALID_ARGUMENT,
+                "SCANN_TREEAH_RAW_BY_POSITION: raw must hold one row per index row (num_raw %zu != n %zu)", num_raw, n);
   SCANN_REQUIRE(out != nullptr, SCANN_INVALID_ARGUMENT, "out is NULL");
   *out = nullptr;
   SCANN_REQUIRE(n > 0 && K > 0, SCANN_INVALID_ARGUMENT, "Cannot build from empty dataset");  // tree_x_hybrid/mod.rs:132-134
@@ -833,8 +866,12 @@ scann_status scann_treeah_create(const float* centers, size_t K, size_t dim, con
           d_packed.p, d_blk_leaf.p, h->blk_off.p, h->pt_off.p, static_cast<int>(S), static_cast<int>(h->SG), words,
           h->codes.p);
     }
-    if (raw) {
+    h->raw_by_pos = raw != nullptr && (flags & SCANN_TREEAH_RAW_BY_POSITION) != 0;
+    if (raw && (flags & SCANN_TREEAH_BORROW_RAW)) {
+      h->raw_p = raw;  // the caller keeps the device array alive for the life of the handle
+    } else if (raw) {
       if ((st = h->raw.upload(raw, num_raw * stride, memspace, s)) != SCANN_OK) break;
+      h->raw_p = h->raw.p;
     }
     if ((st = h->stats.alloc(2)) != SCANN_OK) break;
     cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s);
@@ -972,12 +1009,12 @@ scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, si
   SCANN_REQUIRE(R >= 1 && R <= 2048, SCANN_INVALID_ARGUMENT, "pre_reorder_k %zu outside 1..2048", R);
   SCANN_REQUIRE(k >= 1, SCANN_INVALID_ARGUMENT, "k must be >= 1");
   if (L > h->K) L = h->K;
-  SCANN_REQUIRE(nq * L * R * 8 <= (size_t(1) << 30) && nq * h->K * 4 <= (size_t(512) << 20), SCANN_INVALID_ARGUMENT,
-                "batch of %zu queries is too large for the split search (split it)", nq);
+  SCANN_REQUIRE(nq * L * R * 8 <= (size_t(2) << 30) && (tokens != nullptr || nq * h->K * 4 <= (size_t(512) << 20)),
+                SCANN_INVALID_ARGUMENT, "batch of %zu queries is too large for the split search (split it)", nq);
   h->mu.lock();
   DeviceGuard g(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  scann_status st = h->ws.reserve(treeah_chunk_bytes(h, nq, L, R, k, false));
+  scann_status st = h->ws.reserve(treeah_chunk_bytes(h, nq, L, R, k, false, tokens != nullptr));
   if (st == SCANN_OK) {
     cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s);
     h->ws.reset();

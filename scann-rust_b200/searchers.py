@@ -396,7 +396,10 @@ class TreeXHybridSearcher(_Handle):
         self.num_datapoints = 0
         self.dimensionality = 0
 
-    def build_from_index(self, centers, codebook, packed, ids, part_offsets, raw=None):
+    def build_from_index(self, centers, codebook, packed, ids, part_offsets, raw=None, raw_by_position: bool = False,
+                         borrow_raw: bool = False):
+        """raw_by_position: raw holds one row per index row in the order of packed/ids (a shard keeps its own rows, ids
+        stay global); borrow_raw: CUDA tensors only — raw is not copied, this object keeps the tensor alive."""
         capi.require_gpu()
         if packed.shape[0] == 0:
             raise ScannError(capi.INVALID_ARGUMENT, "Cannot build from empty dataset")
@@ -422,9 +425,14 @@ class TreeXHybridSearcher(_Handle):
         if len(spaces) != 1:
             raise ScannError(capi.INVALID_ARGUMENT, "index arrays must all be host or all be device resident")
         self.close()
-        capi.check(capi.load().scann_treeah_create(p_c, K, dim, p_cb, S, p_pk, p_id, p_off, n, p_raw, num_raw, stride,
-                                                   int(self.config.use_residuals), int(self.config.distance_measure),
-                                                   self.device, spaces.pop(), C.byref(self._h)))
+        space = spaces.pop()
+        flags = (capi.TREEAH_RAW_BY_POSITION if raw_by_position and raw is not None else 0) | \
+                (capi.TREEAH_BORROW_RAW if borrow_raw and raw is not None and space == capi.DEVICE else 0)
+        self._raw_keep = k6 if flags & capi.TREEAH_BORROW_RAW else None
+        capi.check(capi.load().scann_treeah_create_ex(p_c, K, dim, p_cb, S, p_pk, p_id, p_off, n, p_raw, num_raw, stride,
+                                                      int(self.config.use_residuals),
+                                                      int(self.config.distance_measure), flags, self.device, space,
+                                                      C.byref(self._h)))
         self.num_datapoints, self.dimensionality, self.num_partitions, self.num_subspaces = n, dim, K, S
         return self
 
