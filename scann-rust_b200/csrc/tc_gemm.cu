@@ -468,6 +468,26 @@ scann_status make_map(CUtensorMap* map, const void* base, size_t rows, size_t kp
   return SCANN_OK;
 }
 
+}  // namespace
+
+// u8 [rows][row_bytes] row-major (row_bytes a multiple of 16); box = 128 bytes x 128 rows; 128-byte swizzle; columns /
+// rows beyond the tensor read as zero (tcscan.cu: the per-group LUT tiles)
+scann_status tc_make_map_u8(void* map, const void* base, size_t rows, size_t row_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  SCANN_REQUIRE(fn != nullptr, SCANN_UNAVAILABLE, "cuTensorMapEncodeTiled is not available in this driver");
+  cuuint64_t dims[2] = {row_bytes, rows};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {128, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(static_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SCANN_REQUIRE(r == CUDA_SUCCESS, SCANN_INTERNAL, "cuTensorMapEncodeTiled(u8) failed (%d)", static_cast<int>(r));
+  return SCANN_OK;
+}
+
+namespace {
+
 template <int MT, int KA>
 scann_status launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int sms, cudaStream_t s) {
   constexpr int kBudget = 225 * 1024 - kTcEpiWarps * kWqBytes;  // operand tiles

@@ -24,6 +24,7 @@
 
 #include "kernels.h"
 #include "lut16_scan_kernel.cuh"
+#include "tcscan.h"
 
 namespace scann {
 
@@ -68,16 +69,17 @@ __global__ void repack_blocked_kernel(const uint8_t* __restrict__ packed, const 
 // scanned) first: the closest leaf almost always yields the smallest "R-th best" distance, so the batch-wide bound
 // tau_q is in place before the bulk of the work starts — and on a sharded index the class-A bounds of all shards can
 // be min-reduced between the two phases (scann_treeah_search_begin / _end).  A "virtual leaf" v = leaf + K * class.
-__device__ __forceinline__ uint32_t wl_virtual_leaf(uint32_t leaf, size_t p, uint32_t L, uint32_t K) {
-  return leaf + ((p % L) ? K : 0u);
+// T = ranks in class A: 1 (the closest leaf) normally; the T closest leaves when the tensor-core scan takes the rest
+__device__ __forceinline__ uint32_t wl_virtual_leaf(uint32_t leaf, size_t p, uint32_t L, uint32_t K, uint32_t T) {
+  return leaf + ((p % L) >= T ? K : 0u);
 }
 
-__global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K, uint32_t L,
+__global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K, uint32_t L, uint32_t T,
                                 const uint64_t* __restrict__ pt_off, uint32_t* __restrict__ leaf_cnt) {
   size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint32_t leaf = tokens[p];
-  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[wl_virtual_leaf(leaf, p, L, K)], 1u);
+  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[wl_virtual_leaf(leaf, p, L, K, T)], 1u);
 }
 
 // Exclusive scans of pair counts and item counts over the 2K virtual leaves (three small kernels so that K = 65,536
@@ -178,8 +180,10 @@ __global__ void __launch_bounds__(1024) wl_scan_blocks_kernel(uint32_t* __restri
   if (threadIdx.x == 1023) {
     counters[0] = s_i[1023];
     counters[1] = 0;
-    atomicAdd(&stats[0], s_b[1023]);
-    atomicAdd(&stats[1], static_cast<unsigned long long>(s_p[1023]));
+    if (stats) {
+      atomicAdd(&stats[0], s_b[1023]);
+      atomicAdd(&stats[1], static_cast<unsigned long long>(s_p[1023]));
+    }
   }
 }
 
@@ -220,14 +224,14 @@ __global__ void __launch_bounds__(kWlBlock) wl_offsets_kernel(const uint32_t* __
   }
 }
 
-__global__ void wl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K, uint32_t L,
+__global__ void wl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K, uint32_t L, uint32_t T,
                                   const uint64_t* __restrict__ pt_off, const uint32_t* __restrict__ pair_start,
                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted_pairs) {
   size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint32_t leaf = tokens[p];
   if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) {
-    const uint32_t v = wl_virtual_leaf(leaf, p, L, K);
+    const uint32_t v = wl_virtual_leaf(leaf, p, L, K, T);
     uint32_t slot = atomicAdd(&cursor[v], 1u);
     sorted_pairs[pair_start[v] + slot] = static_cast<uint32_t>(p);
   }
@@ -298,6 +302,11 @@ struct MergeArgs {
   uint32_t* cand_ids;
   float* cand_dists;
   uint32_t* cand_counts;
+  // tensor-core scan (tcscan.cu): per-query candidate lists; queries with qflag set come from the per-pair lists
+  const unsigned long long* qcand;
+  const uint32_t* qcnt;
+  const uint32_t* qflag;
+  uint32_t qcap;
 };
 
 constexpr int kMergeChunk = 2048;
@@ -317,6 +326,9 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
   const int tid = threadIdx.x;
   const size_t q = blockIdx.x;
 
+  // tensor-core mode: the per-pair lists hold the class-A ranks (all ranks for a flagged query), the per-query list
+  // every other point with approx distance <= tau_q (ignored for a flagged query: it may have overflowed)
+  const int nlist = (a.qcand != nullptr && a.qflag[q] == 0u) ? static_cast<int>(min(a.qcnt[q], a.qcap)) : 0;
   for (int r = tid; r < a.L; r += NT) {
     uint32_t leaf = a.tokens[q * a.L + r];
     prefix[r + 1] = leaf < a.K ? a.cand_cnt[q * a.L + r] : 0u;
@@ -343,7 +355,9 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
   __syncthreads();
   const int total = static_cast<int>(prefix[a.L]);
   const uint2* cq = a.cand + q * static_cast<size_t>(a.L) * a.R;
+  const unsigned long long* lq = a.qcand + (a.qcand ? q * static_cast<size_t>(a.qcap) : 0);
   auto gen = [&](int i) -> uint64_t {
+    if (i >= total) return lq[i - total];  // keys are already (distance, leaf rank, position)
     int lo = 0, hi = a.L;  // largest r with prefix[r] <= i
     while (hi - lo > 1) {
       int mid = (lo + hi) >> 1;
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
     uint2 c = cq[static_cast<size_t>(lo) * a.R + (i - prefix[lo])];
     return (static_cast<uint64_t>(f32_key(__uint_as_float(c.x))) << 32) | (static_cast<uint64_t>(lo) << 22) | c.y;
   };
-  const int m = block_topr_sorted<NT, kMergeChunk>(gen, total, a.R, buf, out, hist);
+  const int m = block_topr_sorted<NT, kMergeChunk>(gen, total + nlist, a.R, buf, out, hist);
 
   // the R approximate candidates, in (approx distance, leaf rank, position) order
   for (int j = tid; j < p2; j += NT) {
@@ -436,6 +450,9 @@ struct scann_treeah {
   scann::DevBuf<uint32_t> codes, ids, blk_off, leaf_perm;  // leaf_perm: leaves by descending size
   scann::DevBuf<uint32_t> blk_leaf;                        // leaf of every 256-point block
   scann::DevBuf<uint8_t> allow_blk;                        // restrict filter in block order (scann_treeah_set_filter)
+  scann::DevBuf<uint8_t> packed_rm;                        // PackedCodes4Bit rows in leaf order (tensor-core scan, tcscan.cu)
+  bool tc_ok = false;                                      // the tensor-core scan can serve this index
+  uint64_t stat_tc = 0, stat_lut = 0;                      // chunks scanned by the tensor-core / the register-LUT kernel
   bool filter_on = false;
   size_t num_blocks = 0;
   scann::DevBuf<uint64_t> pt_off;
@@ -452,6 +469,13 @@ struct scann_treeah {
     int G = 8;
     uint32_t *tokens = nullptr, *counters = nullptr, *cand_cnt = nullptr, *qthr = nullptr;
     uint2* cand = nullptr;
+    // worklist buffers (rebuilt over the flagged queries' tokens after a tensor-core scan)
+    uint32_t *leaf_cnt = nullptr, *pair_start = nullptr, *item_start = nullptr, *wl_blk_pair = nullptr,
+             *wl_blk_item = nullptr, *sorted_pairs = nullptr;
+    unsigned long long* wl_blk_bytes = nullptr;
+    uint4* items = nullptr;
+    bool use_tc = false;
+    int T = 1;  // ranks in class A of the worklist
     scann::ScanArgs a;
   } ck;
   bool split_active = false;  // between scann_treeah_search_begin and _end (mu stays locked)
@@ -535,6 +559,62 @@ static scann_status launch_scan_g(int G, const ScanArgs& a, int sms, cudaStream_
   }
 }
 
+// Worklist of the register-LUT scan over `tokens` (buffers in h->ck): count -> scans -> scatter -> items.  with_stats:
+// add the batch's algorithmic scan bytes / pairs to h->stats.
+static scann_status treeah_worklist(scann_treeah* h, const uint32_t* tokens, size_t nq, size_t L, bool first,
+                                    cudaStream_t s) {
+  const size_t K = h->K, P = nq * L;
+  const int G = h->ck.G;
+  const uint32_t T = static_cast<uint32_t>(h->ck.T);
+  const bool with_stats = first;
+  uint32_t* leaf_cnt = h->ck.leaf_cnt;
+  uint32_t* cursor = leaf_cnt + 2 * K;
+  SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 4 * K * sizeof(uint32_t), s));
+  // the rebuilt worklist (flagged queries after a tensor-core scan) keeps the per-pair lists of the class-A ranks
+  if (first) SCANN_CUDA(cudaMemsetAsync(h->ck.cand_cnt, 0, P * sizeof(uint32_t), s));
+  unsigned pb = static_cast<unsigned>((P + 255) / 256);
+  wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), T, h->pt_off.p,
+                                     leaf_cnt);
+  const uint32_t nwb = static_cast<uint32_t>((2 * K + kWlBlock - 1) / kWlBlock), bpp32 = static_cast<uint32_t>((h->S + 1) / 2);
+  wl_reduce_kernel<<<nwb, kWlBlock, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p, bpp32,
+                                            h->ck.wl_blk_pair, h->ck.wl_blk_item, h->ck.wl_blk_bytes);
+  wl_scan_blocks_kernel<<<1, 1024, 0, s>>>(h->ck.wl_blk_pair, h->ck.wl_blk_item, h->ck.wl_blk_bytes, nwb, h->ck.counters,
+                                           with_stats ? h->stats.p : nullptr);
+  wl_offsets_kernel<<<nwb, kWlBlock, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p, bpp32,
+                                             h->ck.wl_blk_pair, h->ck.wl_blk_item, h->ck.pair_start, h->ck.item_start,
+                                             h->ck.counters);
+  wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), T, h->pt_off.p,
+                                       h->ck.pair_start, cursor, h->ck.sorted_pairs);
+  wl_items_kernel<<<static_cast<unsigned>((2 * K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
+                                                                            h->ck.pair_start, h->ck.item_start,
+                                                                            h->ck.items);
+  SCANN_CUDA(cudaGetLastError());
+  return SCANN_OK;
+}
+
+// candidate list capacity per query of the tensor-core scan
+static size_t tc_qcap(size_t R) { return std::min<size_t>(4096, std::max<size_t>(512, 16 * R)); }
+
+// tensor-core scan for this chunk?  SCANN_SCAN_TC=0 never, =1 whenever the index supports it, default: when a leaf is
+// probed by enough queries of the batch to fill the 128-wide query tiles
+static bool treeah_use_tc(const scann_treeah* h, size_t nq, size_t L, size_t R) {
+  if (!h->tc_ok || h->filter_on || h->packed_rm.p == nullptr || L > 1024 || R < 1) return false;
+  const char* e = getenv("SCANN_SCAN_TC");
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '1') return true;
+  const size_t P = nq * L;
+  return static_cast<double>(P) / static_cast<double>(std::min<size_t>(h->K, P)) >= 32.0;
+}
+
+// ranks (closest leaves of every query) the register-LUT kernel scans in full before the tensor-core pass: their exact
+// per-leaf top-R lists give the bound tau_q the tensor-core pass filters with.  SCANN_TC_RANKS overrides (tuning).
+static size_t tc_ranks(size_t L) {
+  const char* e = getenv("SCANN_TC_RANKS");
+  size_t v = e ? static_cast<size_t>(atoi(e)) : 2;
+  if (v < 1) v = 1;
+  return std::min(v, L);
+}
+
 // Phase 1 of a chunk: partition -> worklist -> (two_phase: scan of the class-A items, i.e. every query's closest leaf
 // on this shard; tau_out receives the bounds they prove).  State for phase 2 stays in h->ck / the workspace.
 static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
@@ -552,7 +632,6 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   uint32_t* tokens = h->ws.take<uint32_t>(P);
   if (tokens_in) tokens = const_cast<uint32_t*>(tokens_in);  // the caller partitioned (and keeps the array alive)
   uint32_t* leaf_cnt = h->ws.take<uint32_t>(4 * K);  // counts + cursors of the 2K virtual leaves
-  uint32_t* cursor = leaf_cnt + 2 * K;
   uint32_t* pair_start = h->ws.take<uint32_t>(2 * K + 1);
   uint32_t* item_start = h->ws.take<uint32_t>(2 * K + 1);
   uint32_t* counters = h->ws.take<uint32_t>(4);
@@ -577,25 +656,21 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   h->span_end(s);
   // 2. worklist
   h->span_begin(1, s);
-  SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 4 * K * sizeof(uint32_t), s));
-  SCANN_CUDA(cudaMemsetAsync(cand_cnt, 0, P * sizeof(uint32_t), s));
+  h->ck.use_tc = two_phase && treeah_use_tc(h, nq, L, R);  // the tensor-core scan needs the bounds of phase 1
+  h->ck.T = h->ck.use_tc ? static_cast<int>(tc_ranks(L)) : 1;
+  h->ck.G = G;
+  h->ck.leaf_cnt = leaf_cnt;
+  h->ck.pair_start = pair_start;
+  h->ck.item_start = item_start;
+  h->ck.wl_blk_pair = wl_blk_pair;
+  h->ck.wl_blk_item = wl_blk_item;
+  h->ck.wl_blk_bytes = wl_blk_bytes;
+  h->ck.sorted_pairs = sorted_pairs;
+  h->ck.items = items;
+  h->ck.counters = counters;
+  h->ck.cand_cnt = cand_cnt;
   SCANN_CUDA(cudaMemsetAsync(qthr, 0xFF, nq * sizeof(uint32_t), s));
-  unsigned pb = static_cast<unsigned>((P + 255) / 256);
-  wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), h->pt_off.p,
-                                     leaf_cnt);
-  {
-    const uint32_t nwb = static_cast<uint32_t>((2 * K + kWlBlock - 1) / kWlBlock), bpp32 = static_cast<uint32_t>((h->S + 1) / 2);
-    wl_reduce_kernel<<<nwb, kWlBlock, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p, bpp32,
-                                              wl_blk_pair, wl_blk_item, wl_blk_bytes);
-    wl_scan_blocks_kernel<<<1, 1024, 0, s>>>(wl_blk_pair, wl_blk_item, wl_blk_bytes, nwb, counters, h->stats.p);
-    wl_offsets_kernel<<<nwb, kWlBlock, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p, bpp32,
-                                               wl_blk_pair, wl_blk_item, pair_start, item_start, counters);
-  }
-  wl_scatter_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), h->pt_off.p,
-                                       pair_start, cursor, sorted_pairs);
-  wl_items_kernel<<<static_cast<unsigned>((2 * K + 255) / 256), 256, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G,
-                                                                            pair_start, item_start, items);
-  SCANN_CUDA(cudaGetLastError());
+  SCANN_TRY(treeah_worklist(h, tokens, nq, L, true, s));
   h->span_end(s);
   ScanArgs& a = h->ck.a;
   a.codes = reinterpret_cast<const uint4*>(h->codes.p);
@@ -643,7 +718,9 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
     // bounded time (a full scan of the largest leaves would serialise on a few CTAs); phase 2 scans them in full
     h->span_begin(2, s);
     a.end_idx = 2;
-    a.max_blocks = probe_blocks();
+    // tensor-core mode: the class-A ranks are scanned in full here (their per-leaf lists are final, phase 2 does not
+    // come back to them); otherwise a bounded probe of the closest leaf
+    a.max_blocks = h->ck.use_tc ? 0 : probe_blocks();
     SCANN_TRY(launch_scan_g(h->ck.G, a, h->sms, s));
     if (tau_out) tau_out_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(qthr, nq, tau_out);
     SCANN_CUDA(cudaGetLastError());
@@ -665,6 +742,39 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
     SCANN_CUDA(cudaMemsetAsync(h->ck.counters + 1, 0, sizeof(uint32_t), s));  // restart the item counter
     if (tau_in) tau_in_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, s>>>(tau_in, nq, h->ck.qthr);
   }
+  TcScanOut tco;
+  tco.qcand = nullptr;
+  tco.qcnt = nullptr;
+  tco.qflag = nullptr;
+  tco.fb_tokens = nullptr;
+  tco.launches = 0;
+  (h->ck.use_tc ? h->stat_tc : h->stat_lut) += 1;
+  if (h->ck.use_tc) {
+    // 3b. tensor-core scan (tcscan.cu) under the bounds of the probe: per-query candidate lists; the queries it flags
+    // (no bound, list overflow) are re-done by the register-LUT kernel over a worklist of their tokens only
+    TcScanParams tp;
+    tp.tokens = h->ck.tokens;
+    tp.nq = nq;
+    tp.L = L;
+    tp.T = static_cast<size_t>(h->ck.T);
+    tp.K = K;
+    tp.dim = h->dim;
+    tp.S = h->S;
+    tp.pt_off = h->pt_off.p;
+    tp.leaf_perm = h->leaf_perm.p;
+    tp.codes_rm = h->packed_rm.p;
+    tp.queries = h->ck.dq;
+    tp.centers = h->centers.p;
+    tp.codebook = h->codebook.p;
+    tp.qthr = h->ck.qthr;
+    tp.use_residuals = h->use_residuals;
+    tp.max_leaf = h->max_leaf;
+    tp.qcap = tc_qcap(R);
+    tp.sms = h->sms;
+    SCANN_TRY(launch_tc_scan(tp, h->ws, &tco, s));
+    SCANN_TRY(treeah_worklist(h, tco.fb_tokens, nq, L, false, s));
+    h->prof_launches += tco.launches + 6;
+  }
   a.end_idx = 0;
   a.max_blocks = 0;
   SCANN_TRY(launch_scan_g(h->ck.G, a, h->sms, s));
@@ -672,6 +782,10 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
   // 4. merge + reorder
   h->span_begin(3, s);
   MergeArgs m;
+  m.qcand = tco.qcand;
+  m.qcnt = tco.qcnt;
+  m.qflag = tco.qflag;
+  m.qcap = h->ck.use_tc ? static_cast<uint32_t>(tc_qcap(R)) : 0u;
   m.cand = h->ck.cand;
   m.cand_cnt = h->ck.cand_cnt;
   m.tokens = h->ck.tokens;
@@ -708,8 +822,10 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
 static scann_status treeah_search_chunk(scann_treeah* h, const float* dq, size_t nq, size_t L, size_t R, size_t k,
                                         uint32_t* d_ids, float* d_dists, uint32_t* d_counts, uint32_t* d_cand_ids,
                                         float* d_cand_dists, uint32_t* d_cand_counts, cudaStream_t s) {
-  SCANN_TRY(treeah_phase1(h, dq, nq, L, R, k, false, nullptr, nullptr, s));
-  return treeah_phase2(h, false, nullptr, d_ids, d_dists, d_counts, d_cand_ids, d_cand_dists, d_cand_counts, s);
+  // with the tensor-core scan the chunk runs as probe (bounds from every query's closest leaf) + bulk scan
+  const bool tc = treeah_use_tc(h, nq, L, R);
+  SCANN_TRY(treeah_phase1(h, dq, nq, L, R, k, tc, nullptr, nullptr, s));
+  return treeah_phase2(h, tc, nullptr, d_ids, d_dists, d_counts, d_cand_ids, d_cand_dists, d_cand_counts, s);
 }
 
 static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, size_t R, size_t k, bool host,
@@ -731,6 +847,7 @@ static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, siz
   add(P * R * 8);
   add(P * 4);
   add(nq * 4);
+  if (treeah_use_tc(h, nq, L, R)) b += tc_scan_workspace_bytes(nq, L, K, h->S, h->max_leaf, tc_qcap(R));
   if (host) {
     add(nq * h->dim * 4);
     add(nq * k * 4);
@@ -859,12 +976,20 @@ scann_status scann_treeah_create_ex(const float* centers, size_t K, size_t dim, 
     if ((st = h->leaf_perm.upload(perm.data(), K, SCANN_HOST, s)) != SCANN_OK) break;
     if ((st = d_blk_leaf.upload(blk_leaf.data(), nb, SCANN_HOST, s)) != SCANN_OK) break;
     if ((st = d_packed.upload(packed, n * bpp, memspace, s)) != SCANN_OK) break;
+    h->tc_ok = tc_scan_supported(S, dim);
     size_t words = static_cast<size_t>(nb) * h->SG * 128;
     if ((st = h->codes.alloc(words > 0 ? words : 4)) != SCANN_OK) break;
     if (words > 0) {
       repack_blocked_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, s>>>(
           d_packed.p, d_blk_leaf.p, h->blk_off.p, h->pt_off.p, static_cast<int>(S), static_cast<int>(h->SG), words,
           h->codes.p);
+    }
+    if (h->tc_ok) {  // the tensor-core scan reads the row-major PackedCodes4Bit rows (one point per thread)
+      cudaStreamSynchronize(s);  // the repack kernel has read d_packed
+      h->packed_rm.p = d_packed.p;
+      h->packed_rm.n = d_packed.n;
+      d_packed.p = nullptr;
+      d_packed.n = 0;
     }
     h->raw_by_pos = raw != nullptr && (flags & SCANN_TREEAH_RAW_BY_POSITION) != 0;
     if (raw && (flags & SCANN_TREEAH_BORROW_RAW)) {
@@ -1078,6 +1203,14 @@ scann_status scann_treeah_set_filter(scann_treeah* h, const uint8_t* allow_by_id
   return SCANN_OK;
 }
 
+scann_status scann_treeah_path_stats(scann_treeah* h, uint64_t* tc_chunks, uint64_t* lut_chunks) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  if (tc_chunks) *tc_chunks = h->stat_tc;
+  if (lut_chunks) *lut_chunks = h->stat_lut;
+  return SCANN_OK;
+}
+
 scann_status scann_treeah_set_profiling(scann_treeah* h, int enable) {
   using namespace scann;
   SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
@@ -1124,6 +1257,7 @@ void scann_treeah_destroy(scann_treeah* h) {
     h->leaf_perm.free_();
     h->blk_leaf.free_();
     h->allow_blk.free_();
+    h->packed_rm.free_();
     h->ptc.cbf.free_();
     h->ptc.hx.free_();
     h->ptc.small.free_();

@@ -545,6 +545,12 @@ class TreeXHybridSearcher(_Handle):
         capi.check(capi.load().scann_treeah_get_profile(self._h, ms, C.byref(n)))
         return dict(zip(("partition", "worklist", "scan", "merge"), [float(v) for v in ms])), int(n.value)
 
+    def path_stats(self):
+        """(query chunks scanned by the tensor-core LUT16 kernel, by the register-LUT kernel) since construction."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        capi.check(capi.load().scann_treeah_path_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def last_scan_bytes(self):
         by, pr = C.c_uint64(0), C.c_uint64(0)
         capi.check(capi.load().scann_treeah_last_scan_bytes(self._h, C.byref(by), C.byref(pr)))
