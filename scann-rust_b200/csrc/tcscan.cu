@@ -45,7 +45,7 @@ namespace scann {
 
 namespace {
 
-constexpr int kTsThreads = 32 * 15;  // TMA, MMA 0, 8 expanders, 4 epilogue, MMA 1
+constexpr int kTsThreads = 32 * 19;  // TMA, MMA 0, 8 expanders, 4 epilogue, MMA 1, 4 epilogue
 constexpr int kTsRing = 8;            // A slots of 32 TMEM columns (128 K-bytes per point row)
 constexpr int kTsHalf = kTsRing / 2;  // each expander group owns half of the ring: every use of a slot is by the same
                                       // group, so a waiter is never more than one mbarrier phase ahead
@@ -128,6 +128,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -311,57 +324,105 @@ struct LutArgs {
   int dim, S, ds, L, use_residuals, row_bytes;
 };
 
-// 8 warps per CTA, one LUT row (one pair of one group) per warp
+// Persistent warps, one LUT row (one pair of one group) per warp iteration.  DS = dims per subspace when the warp can
+// keep its slice of the codebook in registers (entry e = lane + 32 t is always the same codeword for a lane), 0 = any
+// ds (codewords re-read through L1).  Same operations in the same order as warp_build_lut16 (lut16_device.cuh):
+// sequential un-fused sum of squares, global min/max, scale = 255 / range, round half away, saturate.
+template <int DS>
 __global__ void __launch_bounds__(256) tc_lut_kernel(const LutArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* qres = reinterpret_cast<float*>(sm) + warp * a.dim;
-  uint8_t* l8 = sm + 8 * a.dim * sizeof(float) + warp * (a.S * 16);
-  const uint32_t g = blockIdx.x / (kTcsGroup / 8);
-  const uint32_t j = (blockIdx.x % (kTcsGroup / 8)) * 8 + warp;
-  if (g >= a.counters[1]) return;
-  const uint4 G = a.groups[g];
-  const uint32_t ncol = (G.z + 15u) & ~15u;  // the MMA's N: rows beyond it are never read
-  if (j >= ncol) return;
-  const size_t row = static_cast<size_t>(g) * kTcsGroup + j;
-  uint8_t* out = a.lut + row * a.row_bytes;
-  const int nvec = a.S;  // 16-byte vectors of table bytes in a row
-  uint32_t val = kTsBig + 1u;  // never hits
-  float mult = 1.0f, biasS = 0.0f;
-  uint32_t pair = kNoKey;
-  if (j < G.z) {
-    pair = a.sorted_pairs[G.y + j];
-    const uint32_t q = pair / static_cast<uint32_t>(a.L);
-    for (int d = lane; d < a.dim; d += 32) {
-      float v = a.queries[static_cast<size_t>(q) * a.dim + d];
-      if (a.use_residuals) v = __fsub_rn(v, __ldg(a.centers + static_cast<size_t>(G.x) * a.dim + d));
-      qres[d] = v;
+  const int nent = a.S * 16;
+  constexpr int kDs = DS > 0 ? DS : 1;
+  float cbr[32][kDs];
+  if (DS > 0) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const int e = lane + 32 * t;
+#pragma unroll
+      for (int j = 0; j < kDs; ++j) cbr[t][j] = e < nent ? __ldg(a.codebook + e * DS + j) : 0.0f;
     }
-    __syncwarp();
-    float bias;
-    warp_build_lut16(qres, a.codebook, a.S, a.S, a.ds, l8, &mult, &bias, lane);
-    __syncwarp();
-    mult = __shfl_sync(0xFFFFFFFFu, mult, 0);
-    bias = __shfl_sync(0xFFFFFFFFu, bias, 0);
-    biasS = __fmul_rn(bias, static_cast<float>(a.S));  // bias * S, rounded once (lut16_simd.rs:137)
-    const uint32_t tk = a.qthr[q];
-    int s = -2;
-    if (tk != kNoKey) s = score_bound_from_tau(key_f32(tk), mult, biasS, 255 * a.S);
-    if (s == -2) {
-      if (lane == 0) a.qflag[q] = 1u;  // no usable bound: the register-LUT kernel re-does this query
+  }
+  const uint32_t ngroups = a.counters[1];
+  const uint32_t total = ngroups * kTcsGroup;
+  for (uint32_t r = blockIdx.x * 8 + warp; r < total; r += gridDim.x * 8) {
+    const uint32_t g = r / kTcsGroup, j = r % kTcsGroup;
+    const uint4 G = a.groups[g];
+    const uint32_t ncol = (G.z + 15u) & ~15u;  // the MMA's N: rows beyond it are never read
+    if (j >= ncol) continue;
+    uint8_t* out = a.lut + static_cast<size_t>(r) * a.row_bytes;
+    uint32_t val = kTsBig + 1u;  // never hits
+    float mult = 1.0f, biasS = 0.0f;
+    uint32_t pair = kNoKey;
+    if (j < G.z) {
+      pair = a.sorted_pairs[G.y + j];
+      const uint32_t q = pair / static_cast<uint32_t>(a.L);
+      __syncwarp();
+      for (int d = lane; d < a.dim; d += 32) {
+        float v = a.queries[static_cast<size_t>(q) * a.dim + d];
+        if (a.use_residuals) v = __fsub_rn(v, __ldg(a.centers + static_cast<size_t>(G.x) * a.dim + d));
+        qres[d] = v;
+      }
+      __syncwarp();
+      float vals[32];
+      float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const int e = lane + 32 * t;
+        vals[t] = 0.0f;
+        if (e < nent) {
+          if (DS > 0) {
+            const int s = e >> 4;
+            float sum = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < kDs; ++jj) {
+              const float d = __fsub_rn(qres[s * DS + jj], cbr[t][jj]);
+              sum = __fadd_rn(sum, __fmul_rn(d, d));
+            }
+            vals[t] = sum;
+          } else {
+            vals[t] = lut_entry(qres, a.codebook, e, a.ds);
+          }
+          mn = fminf(mn, vals[t]);
+          mx = fmaxf(mx, vals[t]);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+      }
+      const float range = __fsub_rn(mx, mn);
+      float scale = 1.0f;
+      if (!(range < 1e-10f)) {
+        scale = __fdiv_rn(255.0f, range);
+        mult = __fdiv_rn(1.0f, scale);
+      }
+#pragma unroll
+      for (int t = 0; t < 32; ++t) {
+        const int e = lane + 32 * t;
+        if (e < nent) out[e] = lut16_quantize_entry(vals[t], mn, scale);  // 32 lanes = one full 32-byte sector
+      }
+      biasS = __fmul_rn(mn, static_cast<float>(a.S));  // bias * S, rounded once (lut16_simd.rs:137)
+      const uint32_t tk = a.qthr[q];
+      int sb = -2;
+      if (tk != kNoKey) sb = score_bound_from_tau(key_f32(tk), mult, biasS, 255 * a.S);
+      if (sb == -2) {
+        if (lane == 0) a.qflag[q] = 1u;  // no usable bound: the register-LUT kernel re-does this query
+      } else {
+        val = kTsBig - static_cast<uint32_t>(sb);  // sb = -1 -> BIG + 1
+      }
     } else {
-      val = kTsBig - static_cast<uint32_t>(s);  // s = -1 -> BIG + 1
+      for (int v = lane; v < a.S; v += 32) reinterpret_cast<uint4*>(out)[v] = make_uint4(0, 0, 0, 0);
     }
-    for (int v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(out)[v] = reinterpret_cast<const uint4*>(l8)[v];
-  } else {
-    for (int v = lane; v < nvec; v += 32) reinterpret_cast<uint4*>(out)[v] = make_uint4(0, 0, 0, 0);
+    if (lane < 2) {  // the 32-byte tail: (d0, d1, 0, ...) with d0 + 255 * d1 = val
+      uint4 t = make_uint4(0, 0, 0, 0);
+      if (lane == 0) t.x = (val % 255u) | ((val / 255u) << 8);
+      reinterpret_cast<uint4*>(out + a.S * 16)[lane] = t;
+    }
+    if (lane == 0) a.meta[r] = make_uint4(__float_as_uint(mult), __float_as_uint(biasS), val, pair);
   }
-  if (lane < 2) {  // the 32-byte tail: (d0, d1, 0, ...) with d0 + 255 * d1 = val
-    uint4 t = make_uint4(0, 0, 0, 0);
-    if (lane == 0) t.x = (val % 255u) | ((val / 255u) << 8);
-    reinterpret_cast<uint4*>(out + a.S * 16)[lane] = t;
-  }
-  if (lane == 0) a.meta[row] = make_uint4(__float_as_uint(mult), __float_as_uint(biasS), val, pair);
 }
 
 // ------------------------------------------------------------------------------------------------ the scan
@@ -398,7 +459,7 @@ __device__ __forceinline__ void tcs_emit(const TcsArgs& a, uint32_t lut_row, uin
         (static_cast<unsigned long long>(f32_key(dist)) << 32) | (static_cast<unsigned long long>(rank) << 22) | pos;
 }
 
-constexpr int kWqCap = 384;    // entries of one epilogue warp's survivor queue (uint4 {lut_row, acc, pos, -})
+constexpr int kWqCap = 320;    // entries of one epilogue warp's survivor queue (uint4 {lut_row, acc, pos, -})
 constexpr int kWqStep = 256;   // most entries one filter step (32 lanes x 8 columns) can add
 
 __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmB, const TcsArgs a) {
@@ -409,8 +470,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
   constexpr int kBFull = 0, kBEmpty = 1, kAFull = 2, kAEmpty = 2 + kTsRing, kTFull = 2 + 2 * kTsRing,
                 kTEmpty = 4 + 2 * kTsRing, kNumBars = 6 + 2 * kTsRing;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-  uint4* wq_base = reinterpret_cast<uint4*>(tmem_slot + 4);         // [4][kWqCap] survivor queues of the epilogue warps
-  uint32_t* wq_cnt_base = reinterpret_cast<uint32_t*>(wq_base + 4 * kWqCap);  // [4]
+  uint4* wq_base = reinterpret_cast<uint4*>(tmem_slot + 4);         // [8][kWqCap] survivor queues of the epilogue warps
+  uint32_t* wq_cnt_base = reinterpret_cast<uint32_t*>(wq_base + 8 * kWqCap);  // [8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * static_cast<uint32_t>(i); };
@@ -425,7 +486,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(kTFull + i), 1);
-      mbar_init(bar(kTEmpty + i), 4);  // the four epilogue warps
+      mbar_init(bar(kTEmpty + i), 8);  // the eight epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -460,40 +521,45 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
     // which is 3-4x the 64 cycles the tensor core needs.  The whole warp runs the loop converged and one elected lane
     // issues, so the addresses stay warp-uniform; the two warps alternate tiles and share only the B tile.
     const uint32_t pp = warp == 1 ? 0u : 1u;
-    uint32_t it = 0, ts = 0;
-    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint4 I = a.items[item];
-      const uint32_t ncol = (a.groups[I.x].z + 15u) & ~15u;
-      const uint32_t idesc = (2u << 4) | ((ncol >> 3) << 17) | ((128u >> 4) << 24);  // s32 += u8 x u8, K-major both
-      mbar_wait(bar(kBFull), it & 1u, 0x200u + it);
-      for (uint32_t t = I.y; t < I.z; ++t, ++ts) {
-        if ((ts & 1u) != pp) continue;
-        const uint32_t k = ts >> 1;  // tiles of this pipeline so far
-        mbar_wait(bar(kTEmpty + pp), (k & 1u) ^ 1u, 0x300000u + ts);  // the epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d = tmem + pp * kTcsGroup;
-        uint32_t m = k * static_cast<uint32_t>(nchunk);  // chunks of this pipeline so far
-        for (int c = 0; c < nchunk; ++c, ++m) {
-          const uint32_t slot = pp * kTsHalf + (m % kTsHalf);
-          mbar_wait(bar(kAFull + slot), (m / kTsHalf) & 1u, 0x400000u + m);
+    if (elect_one()) {  // one lane runs the whole issue loop (elect.sync: the compiler knows it is a single thread)
+      uint32_t it = 0, ts = 0;
+      const uint64_t bd0 = umma_desc(smem_u32(sB));
+      const uint32_t d = tmem + pp * kTcsGroup;
+      const uint32_t a0 = tmem + kTsAcol + pp * kTsHalf * 32;
+      for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint4 I = a.items[item];
+        const uint32_t ncol = (a.groups[I.x].z + 15u) & ~15u;
+        const uint32_t idesc = (2u << 4) | ((ncol >> 3) << 17) | ((128u >> 4) << 24);  // s32 += u8 x u8, K-major both
+        mbar_wait(bar(kBFull), it & 1u, 0x200u + it);
+        for (uint32_t t = I.y; t < I.z; ++t, ++ts) {
+          if ((ts & 1u) != pp) continue;
+          const uint32_t k = ts >> 1;  // tiles of this pipeline so far
+          mbar_wait(bar(kTEmpty + pp), (k & 1u) ^ 1u, 0x300000u + ts);  // the epilogue has drained this accumulator
           tc_fence_after();
-          if (elect_one()) {
-            const uint64_t bd = umma_desc(smem_u32(sB + c * kTsAtom));
-            const uint32_t at = tmem + kTsAcol + slot * 32;
-            if (c < a.KA) {
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) mma_i8_ts(d, at + 8 * k4, bd + 2u * k4, idesc, (c | k4) != 0 ? 1u : 0u);
-            } else {
-              mma_i8_ts(d, at, bd, idesc, 1u);  // the threshold atom holds 32 K-bytes
-            }
-            tc_commit(bar(kAEmpty + slot));  // the slot may be refilled once these MMAs retire
-            if (c == nchunk - 1) tc_commit(bar(kTFull + pp));
+          uint32_t m = k * static_cast<uint32_t>(nchunk);  // chunks of this pipeline so far
+          for (int c = 0; c < a.KA; ++c, ++m) {
+            const uint32_t sl = m % kTsHalf;
+            mbar_wait(bar(kAFull + pp * kTsHalf + sl), (m / kTsHalf) & 1u, 0x400000u + m);
+            tc_fence_after();
+            const uint64_t bd = bd0 + static_cast<uint64_t>(c) * (kTsAtom >> 4);
+            const uint32_t at = a0 + sl * 32;
+            mma_i8_ts(d, at, bd, idesc, c != 0 ? 1u : 0u);
+            mma_i8_ts(d, at + 8, bd + 2u, idesc, 1u);
+            mma_i8_ts(d, at + 16, bd + 4u, idesc, 1u);
+            mma_i8_ts(d, at + 24, bd + 6u, idesc, 1u);
+            tc_commit(bar(kAEmpty + pp * kTsHalf + sl));  // the slot may be refilled once these MMAs retire
           }
-          __syncwarp();
+          {  // the threshold atom holds 32 K-bytes
+            const uint32_t sl = m % kTsHalf;
+            mbar_wait(bar(kAFull + pp * kTsHalf + sl), (m / kTsHalf) & 1u, 0x400000u + m);
+            tc_fence_after();
+            mma_i8_ts(d, a0 + sl * 32, bd0 + static_cast<uint64_t>(a.KA) * (kTsAtom >> 4), idesc, 1u);
+            tc_commit(bar(kAEmpty + pp * kTsHalf + sl));
+            tc_commit(bar(kTFull + pp));
+          }
         }
+        tc_commit(bar(kBEmpty));  // this pipeline's MMAs on the B tile have retired
       }
-      if (elect_one()) tc_commit(bar(kBEmpty));  // this pipeline's MMAs on the B tile have retired
-      __syncwarp();
     }
   } else if (warp < 10) {
     // ================================================================= expanders: codes -> one-hot A chunks in TMEM
@@ -559,15 +625,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
         }
       }
     }
-  } else if (warp < 14) {
+  } else {
     // ================================================================= epilogue: threshold + candidate append
+    // Eight warps: two per TMEM lane quadrant, one for accumulator columns 0..63 and one for 64..127, so the
+    // accumulator goes back to its MMA warp after ONE round of TMEM loads (a pipeline cannot start its next tile
+    // before that).
+    const uint32_t ew = warp < 14 ? static_cast<uint32_t>(warp - 10) : static_cast<uint32_t>(warp - 15 + 4);  // 0..7
+    const uint32_t half_id = ew >> 2;
     const uint32_t quad = warp & 3;
     const uint32_t row = quad * 32 + lane;
     const uint32_t lane_addr = (quad * 32) << 16;
     // survivors are queued in shared memory and written out 32 at a time, so that the L2 round trips of a flush
     // (meta load, list-slot atomic, store) overlap across lanes instead of serialising per hit
-    uint4* const wq = wq_base + (warp - 10) * kWqCap;
-    volatile uint32_t* const wq_cnt = wq_cnt_base + (warp - 10);
+    uint4* const wq = wq_base + ew * kWqCap;
+    volatile uint32_t* const wq_cnt = wq_cnt_base + ew;
     if (lane == 0) *wq_cnt = 0;
     __syncwarp();
     auto flush = [&]() {
@@ -581,55 +652,60 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
       if (lane == 0) *wq_cnt = 0;
       __syncwarp();
     };
+    // threshold test of 32 accumulator columns starting at column c0 (nlive = 16 or 32 of them are real)
+    auto filter32 = [&](const uint32_t (&v)[32], uint32_t c0, uint32_t nlive, bool valid, uint32_t lut_row0, uint32_t p) {
+      uint32_t m8[4];
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        uint32_t m = v[8 * g8];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) m = min(m, v[8 * g8 + j]);
+        m8[g8] = m;
+      }
+      if (nlive < 32) m8[2] = m8[3] = kNoKey;
+      const uint32_t mall = min(min(m8[0], m8[1]), min(m8[2], m8[3]));
+      if (__any_sync(0xFFFFFFFFu, valid && mall <= kTsBig)) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const bool hit = valid && m8[g8] <= kTsBig;
+          if (__any_sync(0xFFFFFFFFu, hit)) {  // warp-uniform: the room check and the flush are collective
+            if (*wq_cnt > kWqCap - kWqStep) flush();
+            if (hit) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (v[8 * g8 + j] <= kTsBig)
+                  wq[atomicAdd(const_cast<uint32_t*>(wq_cnt), 1u)] =
+                      make_uint4(lut_row0 + c0 + 8 * g8 + j, v[8 * g8 + j], p, 0u);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    };
     uint32_t ts = 0;
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
       const uint4 I = a.items[item];
       const uint32_t ncol = (a.groups[I.x].z + 15u) & ~15u;
       const uint32_t leaf_n = static_cast<uint32_t>(a.pt_off[I.w + 1] - a.pt_off[I.w]);
       const uint32_t lut_row0 = I.x * kTcsGroup;
+      const uint32_t cb = half_id * 64;                                  // first column of this warp
+      const uint32_t nmine = ncol > cb ? min(64u, ncol - cb) : 0u;       // live columns of this warp: 0, 16, .., 64
       for (uint32_t t = I.y; t < I.z; ++t, ++ts) {
         const uint32_t as = ts & 1u;
         const uint32_t p = t * kTcsTile + row;
         const bool valid = p < leaf_n;
         mbar_wait(bar(kTFull + as), (ts >> 1) & 1u, 0x700000u + ts);
         tc_fence_after();
-        for (uint32_t c0 = 0; c0 < ncol; c0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem + lane_addr + as * kTcsGroup + c0, v);
-          if (c0 + 32 >= ncol) {  // the whole accumulator has been read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kTEmpty + as));
-          }
-          const bool half = ncol - c0 < 32;  // N is a multiple of 16: the last chunk may hold 16 live columns
-          uint32_t m8[4];
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            uint32_t m = v[8 * g8];
-#pragma unroll
-            for (int j = 1; j < 8; ++j) m = min(m, v[8 * g8 + j]);
-            m8[g8] = m;
-          }
-          if (half) m8[2] = m8[3] = kNoKey;
-          const uint32_t mall = min(min(m8[0], m8[1]), min(m8[2], m8[3]));
-          if (__any_sync(0xFFFFFFFFu, valid && mall <= kTsBig)) {
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const bool hit = valid && m8[g8] <= kTsBig;
-              if (__any_sync(0xFFFFFFFFu, hit)) {  // warp-uniform: the room check and the flush are collective
-                if (*wq_cnt > kWqCap - kWqStep) flush();
-                if (hit) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (v[8 * g8 + j] <= kTsBig)
-                      wq[atomicAdd(const_cast<uint32_t*>(wq_cnt), 1u)] =
-                          make_uint4(lut_row0 + c0 + 8 * g8 + j, v[8 * g8 + j], p, 0u);
-                }
-                __syncwarp();
-              }
-            }
-          }
-        }
+        uint32_t v0[32], v1[32];
+        const uint32_t taddr = tmem + lane_addr + as * kTcsGroup + cb;
+        if (nmine > 0) tc_ld32_nowait(taddr, v0);
+        if (nmine > 32) tc_ld32_nowait(taddr + 32, v1);
+        if (nmine > 0) tc_wait_ld();
+        tc_fence_before();  // this warp's part of the accumulator is in registers: hand it back to the MMA warp
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(kTEmpty + as));
+        if (nmine > 0) filter32(v0, cb, min(32u, nmine), valid, lut_row0, p);
+        if (nmine > 32) filter32(v1, cb + 32, nmine - 32, valid, lut_row0, p);
       }
     }
     flush();
@@ -755,8 +831,11 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   la.L = static_cast<int>(p.L);
   la.use_residuals = p.use_residuals;
   la.row_bytes = row_bytes;
-  const size_t lsm = 8 * p.dim * sizeof(float) + 8 * S * 16;
-  tc_lut_kernel<<<static_cast<unsigned>(G * (kTcsGroup / 8)), 256, lsm, s>>>(la);
+  const size_t lsm = 8 * p.dim * sizeof(float);
+  const unsigned lgrid = static_cast<unsigned>(p.sms * 8);
+  if (la.ds == 1) tc_lut_kernel<1><<<lgrid, 256, lsm, s>>>(la);
+  else if (la.ds == 2) tc_lut_kernel<2><<<lgrid, 256, lsm, s>>>(la);
+  else tc_lut_kernel<0><<<lgrid, 256, lsm, s>>>(la);
   SCANN_CUDA(cudaGetLastError());
 
   if (dbg) cudaEventRecord(ev[2], s);
@@ -779,7 +858,7 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   a.L = static_cast<int>(p.L);
   // >= 120 KB keeps it at one CTA per SM for every S (a second resident CTA would block in tcgen05.alloc)
   const size_t smem = std::max<size_t>(120 * 1024, 1024 + static_cast<size_t>(a.KA + 1) * kTsAtom + 32 * 8 + 64 +
-                                                       4 * kWqCap * 16 + 64);
+                                                       8 * kWqCap * 16 + 64);
   SCANN_CUDA(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   static uint32_t* h_dbg = nullptr;
   if (dbg && h_dbg == nullptr) {
