@@ -45,7 +45,8 @@ namespace scann {
 
 namespace {
 
-constexpr int kTsThreads = 32 * 19;  // TMA, MMA 0, 8 expanders, 4 epilogue, MMA 1, 4 epilogue
+// warp 0 TMA, 1-2 MMA issuers, 3 TMEM owner, then 4 * EG expander warps, then 8 epilogue warps
+constexpr int ts_threads(int EG) { return 32 * (4 + 4 * EG + 8); }
 constexpr int kTsRing = 8;            // A slots of 32 TMEM columns (128 K-bytes per point row)
 constexpr int kTsHalf = kTsRing / 2;  // each expander group owns half of the ring: every use of a slot is by the same
                                       // group, so a waiter is never more than one mbarrier phase ahead
@@ -176,14 +177,27 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t sh) {  // PTX
 
 // One word of packed codes = the 4-bit codes of 8 consecutive subspaces of one point -> 8 x 16 one-hot bytes (K order:
 // subspace-major, code-minor = the byte order of a LUT row).  Byte (s, c) is 1 iff code_s == c.
-__device__ __forceinline__ void expand_onehot(uint32_t C, uint32_t (&r)[32]) {
+// Pipe balance: the expansion is the ALU-pipe load of the kernel (~5 nibbles per clock per SM at full tensor rate), so
+// the nibble extraction and the three "- 32 k" run as integer multiply-adds on the FMA pipe; the multipliers come from
+// kernel parameters (xm.sh[i] = 1 << (28 - 4 i), xm.eight = 8) so that the compiler cannot turn them back into shifts.
+struct ExpandMul {
+  uint32_t sh[8];
+  uint32_t eight;
+};
+__device__ __forceinline__ void expand_onehot(uint32_t C, uint32_t (&r)[32], const ExpandMul& xm) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const uint32_t t = i == 0 ? ((C << 3) & 0x78u) : ((C >> (4 * i - 3)) & 0x78u);  // 8 * code: bit position of the 1
+    uint32_t x, t, t1, t2, t3;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(x) : "r"(C), "r"(xm.sh[i]));  // nibble i -> bits 28..31 (lower nibbles below it)
+    const uint32_t nib = x >> 28;                                         // the code, 0..15
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(nib), "r"(xm.eight));                // 8 * code: bit position of the 1
+    asm("mad.lo.u32 %0, %1, %2, 0xFFFFFFE0;" : "=r"(t1) : "r"(nib), "r"(xm.eight));  // - 32
+    asm("mad.lo.u32 %0, %1, %2, 0xFFFFFFC0;" : "=r"(t2) : "r"(nib), "r"(xm.eight));  // - 64
+    asm("mad.lo.u32 %0, %1, %2, 0xFFFFFFA0;" : "=r"(t3) : "r"(nib), "r"(xm.eight));  // - 96
     r[4 * i + 0] = shl_clamp(1u, t);
-    r[4 * i + 1] = shl_clamp(1u, t - 32u);
-    r[4 * i + 2] = shl_clamp(1u, t - 64u);
-    r[4 * i + 3] = shl_clamp(1u, t - 96u);
+    r[4 * i + 1] = shl_clamp(1u, t1);
+    r[4 * i + 2] = shl_clamp(1u, t2);
+    r[4 * i + 3] = shl_clamp(1u, t3);
   }
 }
 
@@ -324,25 +338,35 @@ struct LutArgs {
   int dim, S, ds, L, use_residuals, row_bytes;
 };
 
-// Persistent warps, one LUT row (one pair of one group) per warp iteration.  DS = dims per subspace when the warp can
-// keep its slice of the codebook in registers (entry e = lane + 32 t is always the same codeword for a lane), 0 = any
-// ds (codewords re-read through L1).  Same operations in the same order as warp_build_lut16 (lut16_device.cuh):
-// sequential un-fused sum of squares, global min/max, scale = 255 / range, round half away, saturate.
+// Persistent warps, one LUT row (one pair of one group) per warp iteration.  A lane owns the table entries
+// e = 128 t + 4 lane + b (b < 4, t < S / 8): four consecutive codes of one subspace, so a row is written with S / 8
+// coalesced 128-byte stores and the lane's codewords never change.  DS = dims per subspace when they fit in registers
+// (1 or 2), 0 = any ds (codewords re-read through L1).  Same operations in the same order as warp_build_lut16
+// (lut16_device.cuh): sequential un-fused sum of squares, global min/max, scale = 255 / range, round half away from
+// zero (values are >= 0 here: floor + (fraction >= 0.5), which is what roundf does), saturate.
+__device__ __forceinline__ uint32_t lut16_quantize_nonneg(float v, float mn, float scale) {
+  const float y = __fmul_rn(__fsub_rn(v, mn), scale);  // >= 0, or NaN (-> 0 like Rust's `as u8`)
+  uint32_t i = __float2uint_rd(y);
+  i += __fsub_rn(y, __uint2float_rn(i)) >= 0.5f ? 1u : 0u;
+  return min(i, 255u);
+}
+
 template <int DS>
 __global__ void __launch_bounds__(256) tc_lut_kernel(const LutArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* qres = reinterpret_cast<float*>(sm) + warp * a.dim;
-  const int nent = a.S * 16;
+  const int nstep = a.S / 8;  // 128 table bytes per step (S is a multiple of 16)
   constexpr int kDs = DS > 0 ? DS : 1;
-  float cbr[32][kDs];
+  float cbr[8][4][kDs];
   if (DS > 0) {
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      const int e = lane + 32 * t;
+    for (int t = 0; t < 8; ++t)
 #pragma unroll
-      for (int j = 0; j < kDs; ++j) cbr[t][j] = e < nent ? __ldg(a.codebook + e * DS + j) : 0.0f;
-    }
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int j = 0; j < kDs; ++j)
+          cbr[t][b][j] = t < nstep ? __ldg(a.codebook + (128 * t + 4 * lane + b) * DS + j) : 0.0f;
   }
   const uint32_t ngroups = a.counters[1];
   const uint32_t total = ngroups * kTcsGroup;
@@ -365,27 +389,28 @@ __global__ void __launch_bounds__(256) tc_lut_kernel(const LutArgs a) {
         qres[d] = v;
       }
       __syncwarp();
-      float vals[32];
+      float vals[8][4];
       float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const int e = lane + 32 * t;
-        vals[t] = 0.0f;
-        if (e < nent) {
-          if (DS > 0) {
-            const int s = e >> 4;
-            float sum = 0.0f;
+      for (int t = 0; t < 8; ++t) {
+        if (t < nstep) {
+          const int s = 8 * t + (lane >> 2);  // subspace of this lane's four entries
 #pragma unroll
-            for (int jj = 0; jj < kDs; ++jj) {
-              const float d = __fsub_rn(qres[s * DS + jj], cbr[t][jj]);
-              sum = __fadd_rn(sum, __fmul_rn(d, d));
+          for (int b = 0; b < 4; ++b) {
+            float sum = 0.0f;
+            if (DS > 0) {
+#pragma unroll
+              for (int jj = 0; jj < kDs; ++jj) {
+                const float d = __fsub_rn(qres[s * DS + jj], cbr[t][b][jj]);
+                sum = __fadd_rn(sum, __fmul_rn(d, d));
+              }
+            } else {
+              sum = lut_entry(qres, a.codebook, 128 * t + 4 * lane + b, a.ds);
             }
-            vals[t] = sum;
-          } else {
-            vals[t] = lut_entry(qres, a.codebook, e, a.ds);
+            vals[t][b] = sum;
+            mn = fminf(mn, sum);
+            mx = fmaxf(mx, sum);
           }
-          mn = fminf(mn, vals[t]);
-          mx = fmaxf(mx, vals[t]);
         }
       }
 #pragma unroll
@@ -400,9 +425,13 @@ __global__ void __launch_bounds__(256) tc_lut_kernel(const LutArgs a) {
         mult = __fdiv_rn(1.0f, scale);
       }
 #pragma unroll
-      for (int t = 0; t < 32; ++t) {
-        const int e = lane + 32 * t;
-        if (e < nent) out[e] = lut16_quantize_entry(vals[t], mn, scale);  // 32 lanes = one full 32-byte sector
+      for (int t = 0; t < 8; ++t) {
+        if (t < nstep) {
+          const uint32_t w = lut16_quantize_nonneg(vals[t][0], mn, scale) | (lut16_quantize_nonneg(vals[t][1], mn, scale) << 8) |
+                             (lut16_quantize_nonneg(vals[t][2], mn, scale) << 16) |
+                             (lut16_quantize_nonneg(vals[t][3], mn, scale) << 24);
+          reinterpret_cast<uint32_t*>(out)[32 * t + lane] = w;
+        }
       }
       biasS = __fmul_rn(mn, static_cast<float>(a.S));  // bias * S, rounded once (lut16_simd.rs:137)
       const uint32_t tk = a.qthr[q];
@@ -438,6 +467,7 @@ struct TcsArgs {
   uint32_t* err;             // protocol-error counter (must stay 0)
   uint32_t qcap;
   uint32_t nq;
+  ExpandMul xm;              // opaque multipliers of expand_onehot
   int KA;                    // S / 8: 128-byte K atoms of table bytes (the threshold atom follows)
   int bpp;                   // S / 2
   int L;
@@ -462,7 +492,8 @@ __device__ __forceinline__ void tcs_emit(const TcsArgs& a, uint32_t lut_row, uin
 constexpr int kWqCap = 320;    // entries of one epilogue warp's survivor queue (uint4 {lut_row, acc, pos, -})
 constexpr int kWqStep = 256;   // most entries one filter step (32 lanes x 8 columns) can add
 
-__global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmB, const TcsArgs a) {
+template <int EG>  // expander groups: 2 (one per pipeline) or 4 (two per pipeline, alternate chunks)
+__global__ void __launch_bounds__(ts_threads(EG), 1) tc_scan_kernel(const __grid_constant__ CUtensorMap tmB, const TcsArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;  // [KA + 1] atom tiles
@@ -490,7 +521,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -514,7 +545,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
           tma_load_2d(smem_u32(sB + c * kTsAtom), &tmB, bar(kBFull), c * 128, static_cast<int>(I.x * kTcsGroup));
       }
     }
-  } else if (warp == 1 || warp == 14) {
+  } else if (warp == 1 || warp == 2) {
     // ================================================================= MMA issuers
     // Two issuing warps, one per accumulator / expander group ("pipeline" pp): a single thread needs ~200 cycles of
     // dependent instructions per tcgen05.mma when the operands have to be moved into uniform registers one by one,
@@ -561,9 +592,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
         tc_commit(bar(kBEmpty));  // this pipeline's MMAs on the B tile have retired
       }
     }
-  } else if (warp < 10) {
+  } else if (warp >= 4 && warp < 4 + 4 * EG) {
     // ================================================================= expanders: codes -> one-hot A chunks in TMEM
-    const uint32_t eg = static_cast<uint32_t>(warp - 2) >> 2;  // group 0 takes the even tiles, group 1 the odd ones
+    // Four groups of four warps (one warp per TMEM lane quadrant): pipeline pp = group / 2 takes the tiles of parity
+    // pp, and inside a pipeline the two groups take alternate chunks (by the parity of the pipeline's running chunk
+    // count m), so each A slot (m % 4) is always filled by the same group.
+    const uint32_t gi = static_cast<uint32_t>(warp - 4) >> 2;
+    const uint32_t pp = EG == 4 ? gi >> 1 : gi, sg = gi & 1u;
     const uint32_t quad = warp & 3;
     const uint32_t row = quad * 32 + lane;
     const uint32_t lane_addr = (quad * 32) << 16;
@@ -573,7 +608,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
       const uint64_t base = a.pt_off[I.w];
       const uint32_t leaf_n = static_cast<uint32_t>(a.pt_off[I.w + 1] - base);
       for (uint32_t t = I.y; t < I.z; ++t, ++ts) {
-        if ((ts & 1u) != eg) continue;
+        if ((ts & 1u) != pp) continue;
         const uint32_t p = t * kTcsTile + row;
         uint32_t w[8];
 #pragma unroll
@@ -588,9 +623,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
               w[2 * c2 + 1] = v.y;
             }
         }
-        uint32_t n = (ts >> 1) * static_cast<uint32_t>(nchunk);  // chunks this group has produced so far
-        // software pipeline: the tcgen05.st of chunk c is left in flight while chunk c + 1 is expanded; its completion
-        // (wait::st) and the hand-over to the MMA warp come right before the next store
+        const uint32_t m0 = (ts >> 1) * static_cast<uint32_t>(nchunk);  // chunks of this pipeline before this tile
+        // software pipeline: the tcgen05.st of a chunk is left in flight while this group's next chunk is expanded; its
+        // completion (wait::st) and the hand-over to the MMA warp come right before the next store
         int prev_slot = -1;
         auto publish = [&]() {
           if (prev_slot >= 0) {
@@ -602,35 +637,38 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
         };
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          if (c < a.KA) {
-            const uint32_t slot = eg * kTsHalf + (n % kTsHalf);
+          const uint32_t m = m0 + c;
+          if (c < a.KA && (EG == 2 || (m & 1u) == sg)) {
+            const uint32_t slot = pp * kTsHalf + (m % kTsHalf);
             uint32_t r[32];
-            expand_onehot(w[c], r);  // rows past the end of the leaf expand code 0: the epilogue ignores them
+            expand_onehot(w[c], r, a.xm);  // rows past the end of the leaf expand code 0: the epilogue ignores them
             publish();
-            mbar_wait(bar(kAEmpty + slot), ((n / kTsHalf) & 1u) ^ 1u, 0x500000u + n);
+            mbar_wait(bar(kAEmpty + slot), ((m / kTsHalf) & 1u) ^ 1u, 0x500000u + m);
             tc_fence_after();
             tc_st32(tmem + lane_addr + kTsAcol + slot * 32, r);
             prev_slot = static_cast<int>(slot);
-            ++n;
           }
         }
         {  // threshold chunk: K bytes (1, 255, 0, ...) against the LUT row's digits (d0, d1)
-          const uint32_t slot = eg * kTsHalf + (n % kTsHalf);
-          publish();
-          mbar_wait(bar(kAEmpty + slot), ((n / kTsHalf) & 1u) ^ 1u, 0x600000u + n);
-          tc_fence_after();
-          tc_st8(tmem + lane_addr + kTsAcol + slot * 32, 0x0000FF01u);
-          prev_slot = static_cast<int>(slot);
+          const uint32_t m = m0 + static_cast<uint32_t>(a.KA);
+          if (EG == 2 || (m & 1u) == sg) {
+            const uint32_t slot = pp * kTsHalf + (m % kTsHalf);
+            publish();
+            mbar_wait(bar(kAEmpty + slot), ((m / kTsHalf) & 1u) ^ 1u, 0x600000u + m);
+            tc_fence_after();
+            tc_st8(tmem + lane_addr + kTsAcol + slot * 32, 0x0000FF01u);
+            prev_slot = static_cast<int>(slot);
+          }
           publish();
         }
       }
     }
-  } else {
+  } else if (warp >= 4 + 4 * EG) {
     // ================================================================= epilogue: threshold + candidate append
     // Eight warps: two per TMEM lane quadrant, one for accumulator columns 0..63 and one for 64..127, so the
     // accumulator goes back to its MMA warp after ONE round of TMEM loads (a pipeline cannot start its next tile
     // before that).
-    const uint32_t ew = warp < 14 ? static_cast<uint32_t>(warp - 10) : static_cast<uint32_t>(warp - 15 + 4);  // 0..7
+    const uint32_t ew = static_cast<uint32_t>(warp - (4 + 4 * EG));  // 0..7
     const uint32_t half_id = ew >> 2;
     const uint32_t quad = warp & 3;
     const uint32_t row = quad * 32 + lane;
@@ -696,16 +734,26 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
         const bool valid = p < leaf_n;
         mbar_wait(bar(kTFull + as), (ts >> 1) & 1u, 0x700000u + ts);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
         const uint32_t taddr = tmem + lane_addr + as * kTcsGroup + cb;
-        if (nmine > 0) tc_ld32_nowait(taddr, v0);
-        if (nmine > 32) tc_ld32_nowait(taddr + 32, v1);
-        if (nmine > 0) tc_wait_ld();
-        tc_fence_before();  // this warp's part of the accumulator is in registers: hand it back to the MMA warp
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(kTEmpty + as));
+        uint32_t v0[32];
+        if (nmine > 0) {
+          tc_ld32_nowait(taddr, v0);
+          tc_wait_ld();
+        }
+        if (nmine <= 32) {  // this warp's part of the accumulator is in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kTEmpty + as));
+        }
         if (nmine > 0) filter32(v0, cb, min(32u, nmine), valid, lut_row0, p);
-        if (nmine > 32) filter32(v1, cb + 32, nmine - 32, valid, lut_row0, p);
+        if (nmine > 32) {
+          tc_ld32_nowait(taddr + 32, v0);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(kTEmpty + as));
+          filter32(v0, cb + 32, nmine - 32, valid, lut_row0, p);
+        }
       }
     }
     flush();
@@ -713,7 +761,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) tc_scan_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 3) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
@@ -853,13 +901,18 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   a.qcap = static_cast<uint32_t>(p.qcap);
   a.nq = static_cast<uint32_t>(p.nq);
   a.err = counters + 2;
+  for (int i = 0; i < 8; ++i) a.xm.sh[i] = 1u << (28 - 4 * i);
+  a.xm.eight = 8u;
   a.KA = static_cast<int>(S / 8);
   a.bpp = static_cast<int>(S / 2);
   a.L = static_cast<int>(p.L);
   // >= 120 KB keeps it at one CTA per SM for every S (a second resident CTA would block in tcgen05.alloc)
   const size_t smem = std::max<size_t>(120 * 1024, 1024 + static_cast<size_t>(a.KA + 1) * kTsAtom + 32 * 8 + 64 +
                                                        8 * kWqCap * 16 + 64);
-  SCANN_CUDA(cudaFuncSetAttribute(tc_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const char* eg_env = getenv("SCANN_TC_EXP");
+  const bool eg4 = eg_env && eg_env[0] == '4';
+  if (eg4) SCANN_CUDA(cudaFuncSetAttribute(tc_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  else SCANN_CUDA(cudaFuncSetAttribute(tc_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   static uint32_t* h_dbg = nullptr;
   if (dbg && h_dbg == nullptr) {
     uint32_t* d_dbg = nullptr;
@@ -869,7 +922,8 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
       cudaMemcpyToSymbol(g_tcs_dbg, &d_dbg, sizeof(d_dbg));
     }
   }
-  tc_scan_kernel<<<p.sms, kTsThreads, smem, s>>>(tmB, a);
+  if (eg4) tc_scan_kernel<4><<<p.sms, ts_threads(4), smem, s>>>(tmB, a);
+  else tc_scan_kernel<2><<<p.sms, ts_threads(2), smem, s>>>(tmB, a);
   SCANN_CUDA(cudaGetLastError());
   if (dbg) {
     cudaError_t e = cudaStreamSynchronize(s);

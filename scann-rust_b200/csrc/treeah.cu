@@ -593,7 +593,7 @@ static scann_status treeah_worklist(scann_treeah* h, const uint32_t* tokens, siz
 }
 
 // candidate list capacity per query of the tensor-core scan
-static size_t tc_qcap(size_t R) { return std::min<size_t>(8192, std::max<size_t>(1024, 32 * R)); }
+static size_t tc_qcap(size_t R) { return std::min<size_t>(16384, std::max<size_t>(2048, 64 * R)); }
 
 // tensor-core scan for this chunk?  SCANN_SCAN_TC=0 never, =1 whenever the index supports it, default: when a leaf is
 // probed by enough queries of the batch to fill the 128-wide query tiles
