@@ -194,9 +194,15 @@ scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint3
 scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint64_t* pairs);
 /* which scan kernel served the query chunks of this handle so far: the tensor-core LUT16 scan (tcgen05.mma kind::i8 over
  * one-hot expanded codes, csrc/tcscan.cu; used when the index supports it — S a multiple of 16, S <= 64 — and a leaf is
- * probed by >= 32 queries of the batch on average; SCANN_SCAN_TC=0/1 overrides) or the register-LUT kernel.  Both
+ * probed by >= 12 queries of the batch on average; SCANN_SCAN_TC=0/1 overrides) or the register-LUT kernel.  Both
  * compute the same u32 sums and return identical results. */
 scann_status scann_treeah_path_stats(scann_treeah* h, uint64_t* tc_chunks, uint64_t* lut_chunks);
+/* tensor-core scan share of the profile (valid while profiling is enabled, call BEFORE scann_treeah_get_profile, which
+ * resets the accumulators): milliseconds of the LUT-tile build kernel and of the tcgen05 scan kernel summed over their
+ * launches, the number of launches, and the algorithmic (query, point) pairs of the LAST search's tensor-core part
+ * (Σ over its (query, leaf) pairs of the leaf size; x S*16 x 2 = integer operations of the one-hot contraction). */
+scann_status scann_treeah_tc_profile(scann_treeah* h, double* lut_ms, double* scan_ms, uint64_t* launches,
+                                     uint64_t* pair_points);
 /* live per-stage device timing for the roofline (CUDA events recorded on the search stream around each
  * stage; no host synchronisation while enabled).  get_profile synchronises, returns the milliseconds
  * accumulated since set_profiling(h, 1) / the previous get_profile as ms4 = {partition, worklist,

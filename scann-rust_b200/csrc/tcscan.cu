@@ -245,8 +245,10 @@ __global__ void __launch_bounds__(1024) tcwl_scan_kernel(const uint32_t* __restr
                                                          uint32_t* __restrict__ pair_start,
                                                          uint32_t* __restrict__ group_start,
                                                          uint32_t* __restrict__ item_start,
-                                                         uint32_t* __restrict__ counters) {
+                                                         uint32_t* __restrict__ counters,
+                                                         unsigned long long* __restrict__ pair_points) {
   __shared__ uint32_t s_p[1024], s_g[1024], s_i[1024];
+  unsigned long long pp_local = 0;
   const uint32_t per = (K + 1023) / 1024;
   const uint32_t b = threadIdx.x * per, e = min(K, b + per);
   uint32_t sp = 0, sg = 0, si = 0;
@@ -256,7 +258,9 @@ __global__ void __launch_bounds__(1024) tcwl_scan_kernel(const uint32_t* __restr
     sp += pc;
     sg += g;
     si += g * c;
+    pp_local += static_cast<unsigned long long>(pc) * (pt_off[perm[i] + 1] - pt_off[perm[i]]);
   }
+  if (pair_points && pp_local) atomicAdd(pair_points, pp_local);
   s_p[threadIdx.x] = sp;
   s_g[threadIdx.x] = sg;
   s_i[threadIdx.x] = si;
@@ -855,13 +859,14 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   tcwl_count_kernel<<<pb, 256, 0, s>>>(p.tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(p.L),
                                        static_cast<uint32_t>(p.T), p.pt_off, leaf_cnt);
   tcwl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), p.leaf_perm, p.pt_off, pair_start, group_start,
-                                      item_start, counters);
+                                      item_start, counters, p.pair_points);
   tcwl_scatter_kernel<<<pb, 256, 0, s>>>(p.tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(p.L),
                                          static_cast<uint32_t>(p.T), p.pt_off, pair_start, cursor, sorted_pairs);
   tcwl_items_kernel<<<static_cast<unsigned>((K + 127) / 128), 128, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), p.pt_off,
                                                                           pair_start, group_start, item_start, groups,
                                                                           items);
   if (dbg) cudaEventRecord(ev[1], s);
+  if (p.ev[0]) cudaEventRecord(p.ev[0], s);
   LutArgs la;
   la.groups = groups;
   la.counters = counters;
@@ -887,6 +892,7 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   SCANN_CUDA(cudaGetLastError());
 
   if (dbg) cudaEventRecord(ev[2], s);
+  if (p.ev[1]) cudaEventRecord(p.ev[1], s);
   alignas(64) CUtensorMap tmB;
   SCANN_TRY(tc_make_map_u8(&tmB, lut, G * kTcsGroup, static_cast<size_t>(row_bytes)));
   TcsArgs a;
@@ -937,6 +943,7 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
     }
   }
   if (dbg) cudaEventRecord(ev[3], s);
+  if (p.ev[2]) cudaEventRecord(p.ev[2], s);
   tcs_flag_kernel<<<pb, 256, 0, s>>>(p.tokens, P, static_cast<uint32_t>(p.L), static_cast<uint32_t>(p.T), qcnt,
                                      static_cast<uint32_t>(p.qcap), qflag, fb_tokens);
   SCANN_CUDA(cudaGetLastError());

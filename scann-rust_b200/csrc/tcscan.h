@@ -24,6 +24,8 @@ struct TcScanParams {
   size_t max_leaf;
   size_t qcap;               // candidate list capacity per query
   int sms;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // optional: recorded before the LUT kernel, before and after the scan
+  unsigned long long* pair_points = nullptr;        // optional: += Σ over scanned (pair, leaf) of leaf size
 };
 
 struct TcScanOut {

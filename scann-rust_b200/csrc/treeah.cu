@@ -486,6 +486,10 @@ struct scann_treeah {
     cudaEvent_t e0, e1;
   };
   std::vector<Span> prof_spans;
+  struct TcSpan {
+    cudaEvent_t e[3];
+  };
+  std::vector<TcSpan> tc_spans;  // (before LUT build, before scan, after scan) of every tensor-core scan while profiling
   uint64_t prof_launches = 0;
   void span_begin(int stage, cudaStream_t s) {
     if (!profiling) return;
@@ -504,6 +508,10 @@ struct scann_treeah {
       if (sp.e1) cudaEventDestroy(sp.e1);
     }
     prof_spans.clear();
+    for (TcSpan& t : tc_spans)
+      for (cudaEvent_t e : t.e)
+        if (e) cudaEventDestroy(e);
+    tc_spans.clear();
   }
 };
 
@@ -603,7 +611,7 @@ static bool treeah_use_tc(const scann_treeah* h, size_t nq, size_t L, size_t R) 
   if (e && e[0] == '0') return false;
   if (e && e[0] == '1') return true;
   const size_t P = nq * L;
-  return static_cast<double>(P) / static_cast<double>(std::min<size_t>(h->K, P)) >= 32.0;
+  return static_cast<double>(P) / static_cast<double>(std::min<size_t>(h->K, P)) >= 12.0;
 }
 
 // ranks (closest leaves of every query) the register-LUT kernel scans in full before the tensor-core pass: their exact
@@ -771,6 +779,16 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
     tp.max_leaf = h->max_leaf;
     tp.qcap = tc_qcap(R);
     tp.sms = h->sms;
+    tp.pair_points = h->stats.p + 2;
+    if (h->profiling) {
+      scann_treeah::TcSpan sp{{nullptr, nullptr, nullptr}};
+      bool ok = true;
+      for (auto& e : sp.e) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+      if (ok) {
+        for (int i = 0; i < 3; ++i) tp.ev[i] = sp.e[i];
+        h->tc_spans.push_back(sp);
+      }
+    }
     SCANN_TRY(launch_tc_scan(tp, h->ws, &tco, s));
     SCANN_TRY(treeah_worklist(h, tco.fb_tokens, nq, L, false, s));
     h->prof_launches += tco.launches + 6;
@@ -998,8 +1016,8 @@ scann_status scann_treeah_create_ex(const float* centers, size_t K, size_t dim, 
       if ((st = h->raw.upload(raw, num_raw * stride, memspace, s)) != SCANN_OK) break;
       h->raw_p = h->raw.p;
     }
-    if ((st = h->stats.alloc(2)) != SCANN_OK) break;
-    cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s);
+    if ((st = h->stats.alloc(4)) != SCANN_OK) break;
+    cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s);
     if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
       st = cuda_fail(cudaGetLastError(), "treeah_create sync", __FILE__, __LINE__);
       break;
@@ -1038,7 +1056,7 @@ scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t n
   chunk = std::min(chunk, std::max<size_t>(1, (size_t(512) << 20) / (h->K * 4)));
   const bool host = memspace == SCANN_HOST;
   SCANN_TRY(h->ws.reserve(treeah_chunk_bytes(h, chunk, L, Reff, k, host)));
-  SCANN_CUDA(cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s));
+  SCANN_CUDA(cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s));
   for (size_t q0 = 0; q0 < nq; q0 += chunk) {
     size_t nqc = std::min(chunk, nq - q0);
     h->ws.reset();
@@ -1141,7 +1159,7 @@ scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, si
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   scann_status st = h->ws.reserve(treeah_chunk_bytes(h, nq, L, R, k, false, tokens != nullptr));
   if (st == SCANN_OK) {
-    cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), s);
+    cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s);
     h->ws.reset();
     st = treeah_phase1(h, queries, nq, L, R, k, true, tau_out, tokens, s);
   }
@@ -1237,6 +1255,30 @@ scann_status scann_treeah_get_profile(scann_treeah* h, double* ms4, uint64_t* ke
   h->clear_spans();
   if (kernel_launches) *kernel_launches = h->prof_launches;
   h->prof_launches = 0;
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_tc_profile(scann_treeah* h, double* lut_ms, double* scan_ms, uint64_t* launches,
+                                     uint64_t* pair_points) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard g(h->device);
+  SCANN_CUDA(cudaDeviceSynchronize());
+  double a = 0.0, b = 0.0;
+  for (const scann_treeah::TcSpan& t : h->tc_spans) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, t.e[0], t.e[1]) == cudaSuccess) a += ms;
+    if (cudaEventElapsedTime(&ms, t.e[1], t.e[2]) == cudaSuccess) b += ms;
+  }
+  if (lut_ms) *lut_ms = a;
+  if (scan_ms) *scan_ms = b;
+  if (launches) *launches = h->tc_spans.size();
+  if (pair_points) {
+    unsigned long long v = 0;
+    SCANN_CUDA(cudaMemcpy(&v, h->stats.p + 2, sizeof(v), cudaMemcpyDeviceToHost));
+    *pair_points = v;
+  }
   return SCANN_OK;
 }
 

@@ -551,6 +551,13 @@ class TreeXHybridSearcher(_Handle):
         capi.check(capi.load().scann_treeah_path_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def tc_profile(self):
+        """→ {'lut_ms', 'scan_ms', 'launches', 'pair_points'} of the tensor-core scan while profiling is on (call before
+        get_profile, which resets)."""
+        a, b, n, pp = C.c_double(0), C.c_double(0), C.c_uint64(0), C.c_uint64(0)
+        capi.check(capi.load().scann_treeah_tc_profile(self._h, C.byref(a), C.byref(b), C.byref(n), C.byref(pp)))
+        return {"lut_ms": a.value, "scan_ms": b.value, "launches": int(n.value), "pair_points": int(pp.value)}
+
     def last_scan_bytes(self):
         by, pr = C.c_uint64(0), C.c_uint64(0)
         capi.check(capi.load().scann_treeah_last_scan_bytes(self._h, C.byref(by), C.byref(pr)))
