@@ -57,11 +57,13 @@ DEFAULTS = {
     "c1": dict(n=10_000, dim=128, nq=1_000, k=10),
     "c2": dict(n=1_000_000, dim=128, nq=10_000, k=10),
     "c3": dict(n=10_000_000, dim=96, partitions=2000, subspaces=48, leaves=64, reorder=100, k=10, nq=10_000,
-               latent=8192, spread=0.5, decay=1.0),
+               latent=8192, spread=0.5, decay=1.0, balance=0.0),
     "c4": dict(n=100_000_000, dim=128, partitions=8192, subspaces=64, leaves=64, reorder=100, k=10, nq=10_000,
-               latent=16384, spread=0.5, decay=1.0, sweep="32,64,128", train_rows=1_000_000, kmeans_iters=15),
+               latent=16384, spread=0.5, decay=1.0, sweep="32,64,128", train_rows=1_000_000, kmeans_iters=15,
+               balance=3.0),
     "c5": dict(n=1_000_000_000, dim=96, partitions=65536, subspaces=48, leaves=64, reorder=100, k=10, nq=10_000,
-               latent=65536, spread=0.5, decay=1.0, sweep="16,32,64,128,256", train_rows=2_000_000, kmeans_iters=8),
+               latent=65536, spread=0.5, decay=1.0, sweep="16,32,64,128,256", train_rows=2_000_000, kmeans_iters=10,
+               balance=3.0),
 }
 
 
@@ -75,7 +77,7 @@ def parse():
     p.add_argument("--rows", dest="n", type=int, default=None, help="same as --n (torchrun's own parser trips over --n)")
     for name, typ in [("n", int), ("dim", int), ("partitions", int), ("subspaces", int), ("leaves", int),
                       ("reorder", int), ("k", int), ("nq", int), ("latent", int), ("spread", float), ("decay", float),
-                      ("train_rows", int), ("kmeans_iters", int)]:
+                      ("train_rows", int), ("kmeans_iters", int), ("balance", float)]:
         p.add_argument("--" + name.replace("_", "-"), type=typ, default=None)
     p.add_argument("--sweep", default=None, help="c4/c5: comma list of leaves_to_search values (first JSON value = --leaves)")
     p.add_argument("--sq8", action="store_true", help="c2: ScalarQuantizedBruteForceSearcher (Int8) instead of f32")
@@ -218,6 +220,8 @@ def c3_config(a, K, shard_world, shard):
             "leaves_to_search": a.leaves, "reorder": a.reorder, "k": a.k, "batch_queries": a.nq,
             "data_model": f"mixture of {a.latent} latent centres, spread {a.spread}, noise spectrum j^-{a.decay}, "
                           "L2-normalised; seeds db 42 / queries 123+ / train 7",
+            "index_training": "in-library Lloyd k-means (scann_kmeans_fit / scann_pq_train), 1M-row sample, 20 iterations"
+                              + (f", partitions balanced to <= {a.balance:g}x the mean leaf" if a.balance > 1 else ""),
             "l2_policy": "inputs larger than L2: 24 B/point codes of the probed leaves (7.7 MB/query, 240 MB index) "
                          "+ 3.84 GB raw rows; two alternating query batches",
             "parallelism": (f"index {shard}-sharded x{shard_world}; per batch: token slices all-gathered, closest-leaf "
@@ -278,7 +282,8 @@ def reference_arm(a, emit):
     q = make_points(torch, a.nq, a.dim, lat, a.spread, a.decay, 123, dev, normalize=normalize)
     t0 = time.time()
     K = a.partitions
-    idx = ref_index.build_treeah(torch, x, K, a.subspaces, min(a.train_rows or 1_000_000, n), 20 if a.config == "c3" else 8)
+    idx = ref_index.build_treeah(torch, x, K, a.subspaces, min(a.train_rows or 1_000_000, n), 20 if a.config == "c3" else 8,
+                                 balance_ratio=a.balance)
     log(f"reference arm: torch index K={idx['centers'].shape[0]} over {n} rows in {time.time() - t0:.1f}s")
     hc, hcb = idx["centers"].cpu().numpy(), idx["codebook"].cpu().numpy()
     hoff = idx["off"].cpu().numpy().astype(np.uint64)
@@ -414,6 +419,9 @@ def sharded_config(a, world):
             "data_model": f"mixture of {a.latent} latent centres, spread {a.spread}, noise spectrum j^-{a.decay}"
                           + (", L2-normalised" if a.config == "c5" else "") +
                           f"; generated on the device per rank in chunks of {a.chunk_rows} rows (seed per chunk)",
+            "index_training": f"in-library Lloyd k-means (scann_kmeans_fit / scann_pq_train) on the first {a.train_rows} rows, "
+                              f"{a.kmeans_iters} iterations" +
+                              (f", partitions balanced to <= {a.balance:g}x the mean leaf" if a.balance > 1 else ""),
             "l2_policy": l2 + "; two alternating query batches",
             "parallelism": (f"index partition-sharded x{world}; per batch: token slices all-gathered, closest-leaf bounds "
                             "all-reduced (MIN), local top-k all-gathered + merge kernel (NCCL)" if world > 1
@@ -483,7 +491,7 @@ def bench_sharded(a, emit, torch, dist, pkg, dev, rank, world, local_rank):
         sample = torch.cat(parts)[:a.train_rows].contiguous()
         del parts
         torch.backends.cuda.matmul.allow_tf32 = True   # index TRAINING only (k-means matmuls)
-        centers = ix.kmeans(sample, K, a.kmeans_iters, 7, chunk=max(4096, min(262144, (1 << 31) // (4 * K))))
+        centers = ix.kmeans(sample, K, a.kmeans_iters, 7, balance_ratio=a.balance)
         a_s = ix.assign_partitions(sample, centers, local_rank)
         codebook = ix.train_codebook(sample - centers[a_s.long()], S, 16, 20, 42)
         torch.backends.cuda.matmul.allow_tf32 = False  # the exact ground truth below is plain f32
@@ -864,7 +872,7 @@ def bench_c3(a, emit, torch, dist, pkg, dev, rank, world, local_rank):
         gs.manual_seed(7)
         ns = min(1_000_000, a.n)
         sample = x[torch.randperm(a.n, generator=gs, device=dev)[:ns]].contiguous() if ns < a.n else x
-        centers = ix.kmeans(sample, a.partitions, 20, 7)
+        centers = ix.kmeans(sample, a.partitions, 20, 7, balance_ratio=a.balance)
         a_s = ix.assign_partitions(sample, centers, local_rank)
         codebook = ix.train_codebook(sample - centers[a_s.long()], a.subspaces, 16, 20, 42)
         del sample, a_s

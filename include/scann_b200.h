@@ -168,6 +168,10 @@ void scann_treeah_destroy(scann_treeah* h);
  * cleared with allow_by_id = NULL.  Filtered-out points are skipped inside the LUT16 scan exactly where the reference
  * skips them (before the per-leaf top-R), so a leaf contributes its R best ALLOWED points. */
 scann_status scann_treeah_set_filter(scann_treeah* h, const uint8_t* allow_by_id, size_t num_ids, int memspace);
+/* AsymmetricHasher::search vs ::search_with_reordering (src/hashes/hasher.rs:162-229) on one handle: enable = 0 makes the
+ * following searches return the R best approximate (LUT16) distances without the exact re-score even though the handle
+ * holds raw rows; enable = 1 (default) restores the re-score.  Handle-wide state, like the filter. */
+scann_status scann_treeah_set_reorder(scann_treeah* h, int enable);
 /* Split search for a SHARDED index (one process per GPU, every shard sees the whole query batch).
  *   scann_treeah_search_begin: partition -> worklist -> LUT16 probe of every query's CLOSEST leaf when this shard
  *       owns it (its first 4096 points: any R points prove a bound, and a bounded probe keeps this phase short).
@@ -275,6 +279,39 @@ scann_status scann_tc_scores(const float* queries, size_t nq, size_t dim, const 
 scann_status scann_pq_encode(const float* codebook, size_t S, size_t ds, const float* x, size_t n, size_t stride,
                              const float* centers, const uint32_t* assign, uint8_t* packed, int device,
                              int memspace);
+
+/* ---------------------------------------------------------------------------------------------
+ * Index build inside the library (csrc/build_index.cu) — the training side of the searchers.
+ * The reference seeds its k-means++ from an unpinned rand::StdRng (src/utils/random.rs:20-46), so centroids are
+ * not reproducible by anybody; what HAS reference semantics (assignment = TreePartitioner::partition(x, 1), residual
+ * encode = Codebook::encode, packing = PackedCodes4Bit::from_codes) runs through the exact kernels of the search path.
+ *   scann_kmeans_fit   <- KMeans::fit (src/trees/kmeans.rs:166-432): Lloyd's algorithm from K distinct pseudo-random rows,
+ *       exact nearest-centre assignment (ties -> lower id), f64 cluster sums, empty clusters re-seeded; centers[K*dim].
+ *       balance_ratio > 1: after every update but the last two, clusters heavier than balance_ratio * n/K rows are split
+ *       by re-seeding light clusters (< 0.6 * n/K rows) on hashed member rows — keeps leaves within the LUT16 scan's
+ *       in-leaf position limit and the probe load even; 0 = plain Lloyd (what Codebook::train uses).
+ *       "Cannot cluster empty dataset" / K outside 1..n -> SCANN_INVALID_ARGUMENT (kmeans.rs:171-184).
+ *   scann_pq_train     <- Codebook::train (src/hashes/codebook.rs:146-202): one 16-code k-means per subspace (seed + s)
+ *       over x, or over x - centers[assign] when centers/assign are given (tree_x_hybrid/mod.rs:177-189);
+ *       codebook[S*16*(dim/S)].  dim % S != 0 -> SCANN_INVALID_ARGUMENT (codebook.rs:154-159).
+ *   scann_treeah_build <- TreeXHybridSearcher::build (src/tree_x_hybrid/mod.rs:131-209) / AsymmetricHasher::build
+ *       (src/hashes/hasher.rs:109-159, K = 1 and use_residuals = 0): train on `train_rows` distinct rows (0 = all),
+ *       assign + encode + pack every row, group rows by partition in ascending id, return a ready searcher;
+ *       keep_raw != 0 keeps the rows for the exact reorder.
+ *   scann_ivf_build    <- Scann::init_partitioning (src/scann.rs:140-152): centres + partition_indices -> the searcher of
+ *       Scann::search_partitioned (scann_ivf_search mode 0).
+ * x is host or device memory per `memspace`; everything is computed on `device`.
+ * ------------------------------------------------------------------------------------------- */
+scann_status scann_kmeans_fit(const float* x, size_t n, size_t dim, size_t stride, size_t K, int iters, uint64_t seed,
+                              float balance_ratio, float* centers, int device, int memspace);
+scann_status scann_pq_train(const float* x, size_t n, size_t dim, size_t stride, const float* centers,
+                            const uint32_t* assign, size_t num_centers, size_t S, int iters, uint64_t seed,
+                            float* codebook, int device, int memspace);
+scann_status scann_treeah_build(const float* x, size_t n, size_t dim, size_t stride, size_t K, size_t S,
+                                size_t train_rows, int kmeans_iters, uint64_t seed, int use_residuals,
+                                int reorder_measure, int keep_raw, int device, int memspace, scann_treeah** out);
+scann_status scann_ivf_build(const float* x, size_t n, size_t dim, size_t stride, size_t K, int kmeans_iters,
+                             uint64_t seed, int device, int memspace, scann_ivf** out);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU merge: k-way merge of `parts` per-shard result lists laid out

@@ -243,6 +243,19 @@ class TreePartitioner {
 };
 
 // ------------------------------------------------------------------------------------------------
+struct SearchParameters {  // src/searcher.rs:23-77, the fields the GPU path reads (0 = not set)
+  size_t num_neighbors = 0;
+  size_t pre_reordering_num_neighbors = 0;
+  SearchParameters& with_num_neighbors(size_t k) {
+    num_neighbors = k;
+    return *this;
+  }
+  SearchParameters& with_pre_reordering_neighbors(size_t n) {
+    pre_reordering_num_neighbors = n;
+    return *this;
+  }
+};
+
 struct TreeXHybridConfig {  // src/tree_x_hybrid/mod.rs:23-78
   size_t num_partitions = 100;
   size_t partitions_to_search = 10;
@@ -275,22 +288,7 @@ class TreeXHybridSearcher {
   }
 
   Result<std::vector<NNResultsVector>> search_batched(const std::vector<std::vector<float>>& queries, size_t k) const {
-    Result<std::vector<NNResultsVector>> r;
-    if (queries.empty()) return r;
-    std::vector<float> flat;
-    size_t dim;
-    if (!detail::flatten(queries, &flat, &dim)) {
-      r.error = {ErrorCode::InvalidArgument, "Query dimensionality mismatch"};
-      return r;
-    }
-    size_t nq = queries.size();
-    std::vector<uint32_t> ids(nq * k), counts(nq);
-    std::vector<float> dists(nq * k);
-    r.error = make_error(scann_treeah_search(h_, flat.data(), nq, dim, cfg_.partitions_to_search, cfg_.pre_reorder_k(k), k,
-                                             ids.data(), dists.data(), counts.data(), nullptr, nullptr, nullptr,
-                                             SCANN_HOST, nullptr));
-    if (r.ok()) r.value = detail::unflatten(ids, dists, counts, k);
-    return r;
+    return search_impl(queries, k, cfg_.pre_reorder_k(k));
   }
   // search(&[f32], k) (:240-242)
   Result<NNResultsVector> search(const std::vector<float>& query, size_t k) const {
@@ -313,10 +311,141 @@ class TreeXHybridSearcher {
     scann_treeah_set_filter(h_, nullptr, 0, SCANN_HOST);
     return r;
   }
+  // build(dataset) (:131-209) on the GPU: k-means partition centres, residual PQ codebook (16 codes), exact assignment
+  // and encode, all inside the library (scann_treeah_build)
+  ScannError build(const float* data, size_t n, size_t dim, size_t stride, size_t train_rows = 1000000,
+                   int kmeans_iters = 20, uint64_t seed = 7, int device = 0) {
+    scann_treeah_destroy(h_);
+    h_ = nullptr;
+    return make_error(scann_treeah_build(data, n, dim, stride, cfg_.num_partitions, cfg_.num_subspaces, train_rows,
+                                         kmeans_iters, seed, cfg_.use_residuals ? 1 : 0,
+                                         static_cast<int>(cfg_.distance_measure), 1, device, SCANN_HOST, &h_));
+  }
+  // Searcher::search_batched_with_params (src/searcher.rs:164-169): one SearchParameters per query; queries that share
+  // their parameters go to the GPU as one batch; queries.len() != params.len() -> InvalidArgument (searcher.rs:233-237)
+  Result<std::vector<NNResultsVector>> search_batched_with_params(const std::vector<std::vector<float>>& queries,
+                                                                  const std::vector<SearchParameters>& params) const {
+    Result<std::vector<NNResultsVector>> r;
+    if (queries.size() != params.size()) {
+      r.error = {ErrorCode::InvalidArgument, "Number of queries must match number of parameter sets"};
+      return r;
+    }
+    r.value.resize(queries.size());
+    std::vector<char> done(queries.size(), 0);
+    for (size_t i = 0; i < queries.size(); ++i) {
+      if (done[i]) continue;
+      std::vector<size_t> idx;
+      std::vector<std::vector<float>> sub;
+      for (size_t j = i; j < queries.size(); ++j)
+        if (!done[j] && params[j].num_neighbors == params[i].num_neighbors &&
+            params[j].pre_reordering_num_neighbors == params[i].pre_reordering_num_neighbors) {
+          idx.push_back(j);
+          sub.push_back(queries[j]);
+          done[j] = 1;
+        }
+      const size_t k = params[i].num_neighbors ? params[i].num_neighbors : 10;
+      auto b = search_impl(sub, k, params[i].pre_reordering_num_neighbors ? params[i].pre_reordering_num_neighbors
+                                                                           : cfg_.pre_reorder_k(k));
+      if (!b.ok()) {
+        r.error = b.error;  // the first Err aborts the whole batch (searcher.rs:192-208)
+        r.value.clear();
+        return r;
+      }
+      for (size_t t = 0; t < idx.size(); ++t) r.value[idx[t]] = std::move(b.value[t]);
+    }
+    return r;
+  }
   const TreeXHybridConfig& config() const { return cfg_; }
+  TreeXHybridConfig& config() { return cfg_; }
+  scann_treeah* handle() const { return h_; }
 
  private:
+  Result<std::vector<NNResultsVector>> search_impl(const std::vector<std::vector<float>>& queries, size_t k,
+                                                   size_t pre_reorder_k) const {
+    Result<std::vector<NNResultsVector>> r;
+    if (queries.empty()) return r;
+    std::vector<float> flat;
+    size_t dim;
+    if (!detail::flatten(queries, &flat, &dim)) {
+      r.error = {ErrorCode::InvalidArgument, "Query dimensionality mismatch"};
+      return r;
+    }
+    size_t nq = queries.size();
+    std::vector<uint32_t> ids(nq * k), counts(nq);
+    std::vector<float> dists(nq * k);
+    r.error = make_error(scann_treeah_search(h_, flat.data(), nq, dim, cfg_.partitions_to_search, pre_reorder_k, k,
+                                             ids.data(), dists.data(), counts.data(), nullptr, nullptr, nullptr,
+                                             SCANN_HOST, nullptr));
+    if (r.ok()) r.value = detail::unflatten(ids, dists, counts, k);
+    return r;
+  }
   TreeXHybridConfig cfg_;
+  scann_treeah* h_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// AsymmetricHasher on the LUT16 path (src/hashes/hasher.rs:75-259): one partition holding every point, no residuals.
+struct AsymmetricHasherConfig {  // hasher.rs:19-69 (num_codes is 16 on the GPU path)
+  size_t num_subspaces = 8;
+  uint64_t seed = 42;
+  int kmeans_iters = 20;
+};
+
+class AsymmetricHasher {
+ public:
+  explicit AsymmetricHasher(AsymmetricHasherConfig cfg = {}) : cfg_(cfg) {}
+  AsymmetricHasher(AsymmetricHasher&& o) noexcept : cfg_(o.cfg_), h_(o.h_) { o.h_ = nullptr; }
+  AsymmetricHasher(const AsymmetricHasher&) = delete;
+  ~AsymmetricHasher() { scann_treeah_destroy(h_); }
+
+  // build(dataset) (:109-159): Codebook::train on the dataset + encode; "Cannot build from empty dataset" (:110-112)
+  ScannError build(const float* data, size_t n, size_t dim, size_t stride, int device = 0) {
+    scann_treeah_destroy(h_);
+    h_ = nullptr;
+    return make_error(scann_treeah_build(data, n, dim, stride, 1, cfg_.num_subspaces, 0, cfg_.kmeans_iters, cfg_.seed, 0,
+                                         SCANN_SQL2, 1, device, SCANN_HOST, &h_));
+  }
+  // search (:162-185): approximate (LUT16) distances, no re-ranking
+  Result<NNResultsVector> search(const std::vector<float>& query, size_t k) const { return one(query, k, k, false); }
+  // search_with_reordering (:188-229): pre_reorder_k best by the LUT, exact SquaredL2 (hard-wired, :208), first k
+  Result<NNResultsVector> search_with_reordering(const std::vector<float>& query, size_t k, size_t pre_reorder_k) const {
+    return one(query, k, pre_reorder_k, true);
+  }
+  // search_batched(&[&[f32]], k) (:232-238)
+  Result<std::vector<NNResultsVector>> search_batched(const std::vector<std::vector<float>>& queries, size_t k) const {
+    return run(queries, k, k, false);
+  }
+
+ private:
+  Result<std::vector<NNResultsVector>> run(const std::vector<std::vector<float>>& queries, size_t k, size_t pre,
+                                           bool reorder) const {
+    Result<std::vector<NNResultsVector>> r;
+    if (queries.empty()) return r;
+    if (h_ == nullptr) return r;  // empty / unbuilt hasher -> Ok(vec![]) (:163-165)
+    std::vector<float> flat;
+    size_t dim;
+    if (!detail::flatten(queries, &flat, &dim)) {
+      r.error = {ErrorCode::InvalidArgument, "Query dimensionality mismatch"};
+      return r;
+    }
+    size_t nq = queries.size();
+    std::vector<uint32_t> ids(nq * k), counts(nq);
+    std::vector<float> dists(nq * k);
+    r.error = make_error(scann_treeah_set_reorder(h_, reorder ? 1 : 0));
+    if (!r.ok()) return r;
+    r.error = make_error(scann_treeah_search(h_, flat.data(), nq, dim, 1, pre, k, ids.data(), dists.data(), counts.data(),
+                                             nullptr, nullptr, nullptr, SCANN_HOST, nullptr));
+    if (r.ok()) r.value = detail::unflatten(ids, dists, counts, k);
+    return r;
+  }
+  Result<NNResultsVector> one(const std::vector<float>& query, size_t k, size_t pre, bool reorder) const {
+    auto b = run({query}, k, pre, reorder);
+    Result<NNResultsVector> r;
+    r.error = b.error;
+    if (b.ok() && !b.value.empty()) r.value = std::move(b.value[0]);
+    return r;
+  }
+  AsymmetricHasherConfig cfg_;
   scann_treeah* h_ = nullptr;
 };
 
@@ -372,6 +501,175 @@ class LeafScanSearcher {
     return r;
   }
   scann_ivf* h_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Scann / ScannBuilder facade (src/scann.rs:35-432).  Mode selection follows Scann::with_config (:88-100):
+// brute_force -> BruteForce; tree + hash -> TreeAH; tree only -> Partitioned; hash only -> Hashed.
+//   BruteForce  -> scann_bf_*            exact
+//   TreeAH      -> scann_treeah_build    residual LUT16 scan + exact reorder (the north-star path)
+//   Hashed      -> scann_treeah_build    one partition, no residuals (flat AsymmetricHasher)
+//   Partitioned -> scann_ivf_build       exact distances inside the L closest leaves (:215-253)
+enum class SearchMode { BruteForce, Partitioned, Hashed, TreeAH };
+
+struct ScannConfig {  // src/config.rs:11-29, the fields the hot path reads (0 = not configured)
+  size_t num_neighbors = 10;
+  DistanceMeasure distance_measure = DistanceMeasure::SquaredL2;
+  bool brute_force = false;
+  size_t num_partitions = 0, num_partitions_to_search = 10;
+  size_t hash_num_blocks = 0;
+  size_t reorder_num_candidates = 0;
+};
+
+class Scann {
+ public:
+  Scann() = default;
+  Scann(Scann&& o) noexcept : cfg_(o.cfg_), mode_(o.mode_), bf_(o.bf_), tree_(o.tree_), leaf_(o.leaf_), pre_(o.pre_) {
+    o.bf_ = nullptr;
+    o.tree_ = nullptr;
+    o.leaf_ = nullptr;
+  }
+  Scann(const Scann&) = delete;
+  ~Scann() {
+    scann_bf_destroy(bf_);
+    scann_treeah_destroy(tree_);
+    scann_ivf_destroy(leaf_);
+  }
+
+  // with_config (:64-103); "Dataset cannot be empty" (:66-68)
+  static Result<Scann> with_config(const float* data, size_t n, size_t dim, size_t stride, const ScannConfig& cfg,
+                                   int device = 0) {
+    Result<Scann> r;
+    if (n == 0 || data == nullptr) {
+      r.error = {ErrorCode::InvalidArgument, "Dataset cannot be empty"};
+      return r;
+    }
+    Scann& s = r.value;
+    s.cfg_ = cfg;
+    if (cfg.brute_force) s.mode_ = SearchMode::BruteForce;
+    else if (cfg.num_partitions && cfg.hash_num_blocks) s.mode_ = SearchMode::TreeAH;
+    else if (cfg.num_partitions) s.mode_ = SearchMode::Partitioned;
+    else if (cfg.hash_num_blocks) s.mode_ = SearchMode::Hashed;
+    else s.mode_ = SearchMode::BruteForce;
+    const int measure = static_cast<int>(cfg.distance_measure);
+    if (s.mode_ == SearchMode::BruteForce) {
+      r.error = make_error(scann_bf_create(data, n, dim, stride, measure, device, SCANN_HOST, &s.bf_));
+    } else if (s.mode_ == SearchMode::Partitioned) {
+      r.error = make_error(scann_ivf_build(data, n, dim, stride, cfg.num_partitions, 20, 7, device, SCANN_HOST, &s.leaf_));
+    } else {
+      const bool flat = s.mode_ == SearchMode::Hashed;
+      r.error = make_error(scann_treeah_build(data, n, dim, stride, flat ? 1 : cfg.num_partitions, cfg.hash_num_blocks,
+                                              1000000, 20, 7, flat ? 0 : 1, measure, cfg.reorder_num_candidates ? 1 : 0,
+                                              device, SCANN_HOST, &s.tree_));
+      s.pre_ = cfg.reorder_num_candidates ? cfg.reorder_num_candidates : cfg.num_neighbors;
+    }
+    return r;
+  }
+  static Result<Scann> brute_force(const float* data, size_t n, size_t dim, size_t stride, int device = 0) {  // :106-109
+    ScannConfig c;
+    c.brute_force = true;
+    return with_config(data, n, dim, stride, c, device);
+  }
+  static Result<Scann> partitioned(const float* data, size_t n, size_t dim, size_t stride, size_t num_partitions,
+                                   size_t partitions_to_search, int device = 0) {  // :112-124
+    ScannConfig c;
+    c.num_partitions = num_partitions;
+    c.num_partitions_to_search = partitions_to_search;
+    return with_config(data, n, dim, stride, c, device);
+  }
+  static Result<Scann> hashed(const float* data, size_t n, size_t dim, size_t stride, size_t num_blocks,
+                              int device = 0) {  // :127-137
+    ScannConfig c;
+    c.hash_num_blocks = num_blocks;
+    return with_config(data, n, dim, stride, c, device);
+  }
+
+  // search_batched (:297-303); k = 0 -> config.num_neighbors
+  Result<std::vector<NNResultsVector>> search_batched(const std::vector<std::vector<float>>& queries, size_t k = 0) const {
+    Result<std::vector<NNResultsVector>> r;
+    if (queries.empty()) return r;
+    if (k == 0) k = cfg_.num_neighbors;
+    std::vector<float> flat;
+    size_t dim;
+    if (!detail::flatten(queries, &flat, &dim)) {
+      r.error = {ErrorCode::InvalidArgument, "Query dimensionality mismatch"};
+      return r;
+    }
+    const size_t nq = queries.size();
+    std::vector<uint32_t> ids(nq * k), counts(nq);
+    std::vector<float> dists(nq * k);
+    if (mode_ == SearchMode::BruteForce) {
+      r.error = make_error(scann_bf_search(bf_, flat.data(), nq, dim, k, ids.data(), dists.data(), counts.data(),
+                                           SCANN_HOST, nullptr));
+    } else if (mode_ == SearchMode::Partitioned) {
+      r.error = make_error(scann_ivf_search(leaf_, 0, flat.data(), nq, dim, cfg_.num_partitions_to_search, k,
+                                            static_cast<int>(cfg_.distance_measure), -1, ids.data(), dists.data(),
+                                            counts.data(), SCANN_HOST, nullptr));
+    } else {
+      const size_t L = mode_ == SearchMode::Hashed ? 1 : cfg_.num_partitions_to_search;
+      r.error = make_error(scann_treeah_search(tree_, flat.data(), nq, dim, L, pre_ > k ? pre_ : k, k, ids.data(),
+                                               dists.data(), counts.data(), nullptr, nullptr, nullptr, SCANN_HOST,
+                                               nullptr));
+    }
+    if (r.ok()) r.value = detail::unflatten(ids, dists, counts, k);
+    return r;
+  }
+  Result<NNResultsVector> search(const std::vector<float>& query, size_t k = 0) const {  // :175-178
+    auto b = search_batched({query}, k);
+    Result<NNResultsVector> r;
+    r.error = b.error;
+    if (b.ok() && !b.value.empty()) r.value = std::move(b.value[0]);
+    return r;
+  }
+  SearchMode search_mode() const { return mode_; }
+  const ScannConfig& config() const { return cfg_; }
+
+ private:
+  ScannConfig cfg_;
+  SearchMode mode_ = SearchMode::BruteForce;
+  scann_bf* bf_ = nullptr;
+  scann_treeah* tree_ = nullptr;
+  scann_ivf* leaf_ = nullptr;
+  size_t pre_ = 0;
+};
+
+class ScannBuilder {  // src/scann.rs:364-432
+ public:
+  ScannBuilder& num_neighbors(size_t k) {
+    cfg_.num_neighbors = k;
+    return *this;
+  }
+  ScannBuilder& distance_measure(DistanceMeasure m) {
+    cfg_.distance_measure = m;
+    return *this;
+  }
+  ScannBuilder& brute_force() {
+    cfg_.brute_force = true;
+    return *this;
+  }
+  ScannBuilder& tree(size_t num_partitions, size_t partitions_to_search) {  // .partitioned() in the README spelling
+    cfg_.num_partitions = num_partitions;
+    cfg_.num_partitions_to_search = partitions_to_search;
+    return *this;
+  }
+  ScannBuilder& partitioned(size_t num_partitions, size_t partitions_to_search) {
+    return tree(num_partitions, partitions_to_search);
+  }
+  ScannBuilder& hash(size_t num_blocks) {  // .hashed() in the README spelling
+    cfg_.hash_num_blocks = num_blocks;
+    return *this;
+  }
+  ScannBuilder& hashed(size_t num_blocks) { return hash(num_blocks); }
+  ScannBuilder& reorder(size_t num_candidates) {
+    cfg_.reorder_num_candidates = num_candidates;
+    return *this;
+  }
+  Result<Scann> build(const float* data, size_t n, size_t dim, size_t stride, int device = 0) const {
+    return Scann::with_config(data, n, dim, stride, cfg_, device);
+  }
+
+ private:
+  ScannConfig cfg_;
 };
 
 }  // namespace scann

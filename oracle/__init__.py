@@ -21,9 +21,16 @@ OK, INVALID_ARGUMENT, FAILED_PRECONDITION = 0, 3, 9
 
 
 def build(force: bool = False) -> str:
+    import fcntl
+
     src = os.path.join(_HERE, "scann_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libscann_oracle.so"], stdout=subprocess.DEVNULL)
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:  # ranks of one torchrun serialise here
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+                subprocess.check_call(["make", "-C", _HERE, "-B", "libscann_oracle.so"], stdout=subprocess.DEVNULL)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return _LIB_PATH
 
 

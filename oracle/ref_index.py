@@ -15,14 +15,18 @@ def _chunk(K):
     return max(4096, min(262144, (1 << 31) // (4 * max(K, 1))))
 
 
-def kmeans(torch, x, K, iters=20, seed=7, chunk=None):
+def kmeans(torch, x, K, iters=20, seed=7, chunk=None, balance_ratio=0.0):
+    """balance_ratio > 1: the same rule as the product trainer (csrc/build_index.cu) — after every update but the last
+    two, clusters heavier than balance_ratio * n/K donate floor(cnt / (n/K)) - 1 member rows as new centres of light
+    clusters (< 0.6 * n/K rows)."""
     n, d = x.shape
     K = min(K, n)
     chunk = chunk or _chunk(K)
     g = torch.Generator(device=x.device)
     g.manual_seed(seed)
     centers = x[torch.randperm(n, generator=g, device=x.device)[:K]].clone().float()
-    for _ in range(iters):
+    for it in range(iters):
+        centers_prev = centers
         sums = torch.zeros((K, d), dtype=torch.float32, device=x.device)
         cnts = torch.zeros((K,), dtype=torch.float32, device=x.device)
         cn = (centers * centers).sum(1)
@@ -37,6 +41,18 @@ def kmeans(torch, x, K, iters=20, seed=7, chunk=None):
         if empty.numel() > 0:
             new_centers[empty] = x[torch.randint(0, n, (empty.numel(),), generator=g, device=x.device)].float()
         centers = new_centers
+        if balance_ratio > 1.0 and K >= 2 and n // K >= 4 and it + 2 < iters:
+            target = max(1, n // K)
+            a_all = assign(torch, x, centers_prev, chunk)
+            cnt = torch.bincount(a_all, minlength=K)
+            want = (torch.clamp(cnt // target, max=64) - 1).clamp(min=0)
+            heavy = cnt > int(balance_ratio * target)
+            p = torch.where(heavy, want.float() / cnt.clamp(min=1).float(), torch.zeros_like(cnt, dtype=torch.float32))
+            pick = (torch.rand((n,), generator=g, device=x.device) < p[a_all]).nonzero().flatten()
+            donors = (cnt < int(0.6 * target)).nonzero().flatten()
+            m = min(pick.numel(), donors.numel())
+            if m > 0:
+                centers[donors[:m]] = x[pick[:m]].float()
     return centers.contiguous()
 
 
@@ -73,14 +89,14 @@ def encode_packed(torch, x, centers, a, codebook, chunk=262144):
     return out
 
 
-def build_treeah(torch, x, K, S, train_sample=1_000_000, iters=20, seed=7):
+def build_treeah(torch, x, K, S, train_sample=1_000_000, iters=20, seed=7, balance_ratio=0.0):
     """-> dict of torch tensors on x.device: centers, codebook, packed (grouped by partition), ids (i64), off (i64)"""
     n = x.shape[0]
     g = torch.Generator(device=x.device)
     g.manual_seed(seed)
     ns = min(train_sample, n)
     sample = x[torch.randperm(n, generator=g, device=x.device)[:ns]].contiguous() if ns < n else x
-    centers = kmeans(torch, sample, K, iters, seed)
+    centers = kmeans(torch, sample, K, iters, seed, balance_ratio=balance_ratio)
     K = centers.shape[0]
     a_s = assign(torch, sample, centers)
     codebook = train_codebook(torch, sample - centers[a_s], S, 16, iters, 42)

@@ -39,6 +39,7 @@ SYMBOLS = [
     "scann_treeah_set_filter", "scann_treeah_path_stats", "scann_treeah_tc_profile",
     "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_merge_topk_packed", "scann_tc_scores",
     "scann_ivf_create", "scann_ivf_search", "scann_ivf_destroy",
+    "scann_kmeans_fit", "scann_pq_train", "scann_treeah_build", "scann_ivf_build", "scann_treeah_set_reorder",
 ]
 
 
@@ -115,6 +116,12 @@ def load():
     L.scann_ivf_destroy.restype = None
     L.scann_merge_topk_packed.argtypes = [vp, sz, sz, sz, vp, vp, vp, i32, vp]
     L.scann_tc_scores.argtypes = [vp, sz, sz, vp, i32, sz, sz, f32, i32, vp, vp, vp, sz, vp, i32]
+    u64 = C.c_uint64
+    L.scann_kmeans_fit.argtypes = [vp, sz, sz, sz, sz, i32, u64, f32, vp, i32, i32]
+    L.scann_pq_train.argtypes = [vp, sz, sz, sz, vp, vp, sz, sz, i32, u64, vp, i32, i32]
+    L.scann_treeah_build.argtypes = [vp, sz, sz, sz, sz, sz, sz, i32, u64, i32, i32, i32, i32, i32, C.POINTER(vp)]
+    L.scann_ivf_build.argtypes = [vp, sz, sz, sz, sz, i32, u64, i32, i32, C.POINTER(vp)]
+    L.scann_treeah_set_reorder.argtypes = [vp, i32]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("scann_last_error", "scann_version") and not name.endswith("_destroy"):

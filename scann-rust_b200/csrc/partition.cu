@@ -423,7 +423,7 @@ scann_status scann_part_select(scann_part* h, const float* queries, size_t nq, s
   cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(stream)
                                              : (stream ? static_cast<cudaStream_t>(stream) : h->stream);
   // bounded scratch: process the batch in chunks of queries
-  size_t chunk = (size_t(256) << 20) / (h->K * sizeof(float));
+  size_t chunk = (size_t(2) << 30) / (h->K * sizeof(float));  // dense score scratch: 2 GiB keeps >= 8192 rows per pass at K = 65,536
   if (chunk < 1) chunk = 1;
   if (chunk > nq) chunk = nq;
   size_t need = Workspace::padded(std::max(chunk * h->K * sizeof(float),

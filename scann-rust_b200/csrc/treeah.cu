@@ -447,6 +447,7 @@ struct scann_treeah {
   scann::DevBuf<float> centers, centersT, codebook, raw;
   const float* raw_p = nullptr;  // raw.p, or the caller's device array (SCANN_TREEAH_BORROW_RAW)
   bool raw_by_pos = false;       // SCANN_TREEAH_RAW_BY_POSITION
+  bool reorder_on = true;        // scann_treeah_set_reorder: exact re-score of the R candidates (needs raw)
   scann::DevBuf<uint32_t> codes, ids, blk_off, leaf_perm;  // leaf_perm: leaves by descending size
   scann::DevBuf<uint32_t> blk_leaf;                        // leaf of every 256-point block
   scann::DevBuf<uint8_t> allow_blk;                        // restrict filter in block order (scann_treeah_set_filter)
@@ -809,7 +810,7 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
   m.tokens = h->ck.tokens;
   m.pt_off = h->pt_off.p;
   m.ids = h->ids.p;
-  m.raw = h->raw_p;
+  m.raw = h->reorder_on ? h->raw_p : nullptr;
   m.stride = h->stride;
   m.num_raw = h->num_raw;
   m.raw_by_pos = h->raw_by_pos ? 1 : 0;
@@ -1279,6 +1280,13 @@ scann_status scann_treeah_tc_profile(scann_treeah* h, double* lut_ms, double* sc
     SCANN_CUDA(cudaMemcpy(&v, h->stats.p + 2, sizeof(v), cudaMemcpyDeviceToHost));
     *pair_points = v;
   }
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_set_reorder(scann_treeah* h, int enable) {
+  SCANN_REQUIRE(h != nullptr, SCANN_INVALID_ARGUMENT, "NULL handle");
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->reorder_on = enable != 0;
   return SCANN_OK;
 }
 

@@ -7,13 +7,14 @@ not reproducible anyway.  What IS the reference's semantics, and is done by the 
   * residual = x - centre[assign], codes = Codebook::encode(residual)   (tree_x_hybrid/mod.rs:177-189,
                                                                           hashes/codebook.rs:82-95)
   * PackedCodes4Bit::from_codes packing                                  (hashes/lut16.rs:43-61)
-torch is used for the training matmuls only.
+Training runs in the library too (scann_kmeans_fit / scann_pq_train, csrc/build_index.cu); torch only holds the device
+buffers.
 """
 from __future__ import annotations
 
 import numpy as np
 
-from . import searchers
+from . import capi, searchers
 
 
 def _torch():
@@ -21,51 +22,37 @@ def _torch():
     return torch
 
 
-def kmeans(x, K: int, iters: int = 20, seed: int = 7, chunk: int = 262144):
-    """Lloyd's k-means on a torch tensor [n, d]; returns centres [K, d] (f32).  Empty clusters are
-    re-seeded from the points farthest from their centre."""
+def kmeans(x, K: int, iters: int = 20, seed: int = 7, chunk: int = 0, balance_ratio: float = 0.0):
+    """KMeans::fit (src/trees/kmeans.rs:166-432) on the GPU through the C ABI (scann_kmeans_fit, csrc/build_index.cu):
+    Lloyd's algorithm with the library's exact nearest-centre assignment (tensor-core scoring + exact re-score) and f64
+    cluster sums.  x: torch CUDA tensor [n, d] f32; returns centres [min(K, n), d].  `chunk` is ignored (kept for
+    callers of the old torch trainer); balance_ratio > 1 splits clusters heavier than that multiple of n/K."""
     torch = _torch()
+    x = x.float().contiguous()
     n, d = x.shape
     K = min(K, n)
-    g = torch.Generator(device=x.device)
-    g.manual_seed(seed)
-    perm = torch.randperm(n, generator=g, device=x.device)[:K]
-    centers = x[perm].clone().float()
-    for _ in range(iters):
-        sums = torch.zeros((K, d), dtype=torch.float32, device=x.device)
-        cnts = torch.zeros((K,), dtype=torch.float32, device=x.device)
-        cn = (centers * centers).sum(1)
-        far_val, far_idx = None, None
-        for s in range(0, n, chunk):
-            xb = x[s:s + chunk].float()
-            dist = cn[None, :] - 2.0 * (xb @ centers.t())
-            md, a = dist.min(1)
-            sums.index_add_(0, a, xb)
-            cnts.index_add_(0, a, torch.ones_like(md))
-            md = md + (xb * xb).sum(1)
-            v, i = md.max(0)
-            if far_val is None or v > far_val:
-                far_val, far_idx = v, i + s
-        nonempty = cnts > 0
-        new_centers = torch.where(nonempty[:, None], sums / cnts.clamp(min=1.0)[:, None], centers)
-        empty = (~nonempty).nonzero().flatten()
-        if empty.numel() > 0:
-            repl = torch.randint(0, n, (empty.numel(),), generator=g, device=x.device)
-            new_centers[empty] = x[repl].float()
-        centers = new_centers
-    return centers.contiguous()
+    centers = torch.empty((K, d), dtype=torch.float32, device=x.device)
+    dev = x.device.index or 0
+    capi.require_gpu()
+    capi.check(capi.load().scann_kmeans_fit(x.data_ptr(), n, d, d, K, iters, seed, float(balance_ratio), centers.data_ptr(),
+                                            dev, capi.DEVICE))
+    return centers
 
 
 def train_codebook(residuals, S: int, num_codes: int = 16, iters: int = 20, seed: int = 42):
-    """Per-subspace k-means (Codebook::train, hashes/codebook.rs:146-202: subspace s uses seed+s) on
-    residuals [n, D] → codebook [S, num_codes, ds]."""
+    """Codebook::train (hashes/codebook.rs:146-202: subspace s uses seed+s) on residuals [n, D] → codebook
+    [S, 16, ds], through the C ABI (scann_pq_train)."""
     torch = _torch()
-    n, D = residuals.shape
-    ds = D // S
-    cb = torch.empty((S, num_codes, ds), dtype=torch.float32, device=residuals.device)
-    for s in range(S):
-        cb[s] = kmeans(residuals[:, s * ds:(s + 1) * ds].contiguous(), num_codes, iters, seed + s)
-    return cb.contiguous()
+    if num_codes != 16:
+        raise capi.ScannError(capi.INVALID_ARGUMENT, "the GPU trainer builds 16-code (LUT16) codebooks")
+    r = residuals.float().contiguous()
+    n, D = r.shape
+    cb = torch.empty((S, 16, D // S), dtype=torch.float32, device=r.device)
+    dev = r.device.index or 0
+    capi.require_gpu()
+    capi.check(capi.load().scann_pq_train(r.data_ptr(), n, D, D, None, None, 0, S, iters, seed, cb.data_ptr(), dev,
+                                          capi.DEVICE))
+    return cb
 
 
 def assign_partitions(x, centers, device: int = 0, chunk: int = 1 << 20):

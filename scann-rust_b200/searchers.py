@@ -436,6 +436,26 @@ class TreeXHybridSearcher(_Handle):
         self.num_datapoints, self.dimensionality, self.num_partitions, self.num_subspaces = n, dim, K, S
         return self
 
+    def build(self, dataset, train_rows: int = 1_000_000, kmeans_iters: int = 20, seed: int = 7, keep_raw: bool = True):
+        """TreeXHybridSearcher::build (:131-209) inside the library (scann_treeah_build, csrc/build_index.cu): k-means
+        partition centres, residual LUT16 codebook, exact assignment / encode / packing.  dataset: numpy or torch
+        (CPU/CUDA) [n, dim] f32."""
+        capi.require_gpu()
+        if dataset is None or int(dataset.shape[0]) == 0:
+            raise ScannError(capi.INVALID_ARGUMENT, "Cannot build from empty dataset")
+        p_x, space, keep = _dataset_ptr(dataset, np.float32)
+        n, dim = int(dataset.shape[0]), int(dataset.shape[1])
+        S = int(self.config.hash_config.num_subspaces)
+        self.close()
+        capi.check(capi.load().scann_treeah_build(p_x, n, dim, dim, int(self.config.num_partitions), S, int(train_rows),
+                                                  int(kmeans_iters), int(seed), int(self.config.use_residuals),
+                                                  int(self.config.distance_measure), int(keep_raw), self.device, space,
+                                                  C.byref(self._h)))
+        del keep
+        self.num_datapoints, self.dimensionality, self.num_subspaces = n, dim, S
+        self.num_partitions = min(int(self.config.num_partitions), n if train_rows <= 0 else min(n, int(train_rows)))
+        return self
+
     def search_batched(self, queries, k: int, partitions_to_search: Optional[int] = None,
                        pre_reorder_k: Optional[int] = None, want_candidates: bool = False):
         if not (self._h and self._h.value):

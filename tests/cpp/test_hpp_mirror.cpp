@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "scann_b200.hpp"
 
@@ -75,6 +76,84 @@ int main() {
   CHECK(lp2.ok() && lp2.value[0].size() == 2 && lp2.value[0][0].first == 3 && lp2.value[0][0].second == 0.0f);
   auto lbad = leaf.search_tree_ah({{0.f, 0.f}}, 2, 1);  // no hasher in this index
   CHECK(!lbad.ok() && lbad.error.code == ErrorCode::FailedPrecondition);
+  // ---- native index build + the Scann facade (src/scann.rs tests :438-520: build, search, sorted results) ----
+  {
+    const size_t n = 6000, dim = 32, nc = 12;
+    std::vector<float> data(n * dim), cen(nc * dim);
+    uint64_t st = 88172645463325252ull;
+    auto rnd = [&]() {  // xorshift, uniform in [-1, 1)
+      st ^= st << 13;
+      st ^= st >> 7;
+      st ^= st << 17;
+      return static_cast<float>(static_cast<double>(st >> 11) / 9007199254740992.0 * 2.0 - 1.0);
+    };
+    for (auto& v : cen) v = 4.0f * rnd();
+    for (size_t i = 0; i < n; ++i)
+      for (size_t d = 0; d < dim; ++d) data[i * dim + d] = cen[(i % nc) * dim + d] + 0.3f * rnd();
+    std::vector<std::vector<float>> qs;
+    for (size_t q = 0; q < 40; ++q) {
+      std::vector<float> v(dim);
+      for (size_t d = 0; d < dim; ++d) v[d] = data[(q * 37) * dim + d] + 0.01f * rnd();
+      qs.push_back(v);
+    }
+    auto exact = Scann::brute_force(data.data(), n, dim, dim);
+    CHECK(exact.ok() && exact.value.search_mode() == SearchMode::BruteForce);
+    auto truth = exact.value.search_batched(qs, 10);
+    CHECK(truth.ok() && truth.value.size() == 40 && truth.value[0].size() == 10);
+    auto recall = [&](const std::vector<NNResultsVector>& got) {
+      size_t hit = 0;
+      for (size_t q = 0; q < got.size(); ++q)
+        for (auto& a : got[q])
+          for (auto& b : truth.value[q]) hit += a.first == b.first;
+      return static_cast<double>(hit) / (10.0 * got.size());
+    };
+    auto tree_ah = ScannBuilder().num_neighbors(10).tree(16, 6).hash(16).reorder(60).build(data.data(), n, dim, dim);
+    CHECK(tree_ah.ok() && tree_ah.value.search_mode() == SearchMode::TreeAH);
+    auto ta = tree_ah.value.search_batched(qs);
+    CHECK(ta.ok() && ta.value.size() == 40);
+    for (auto& r1 : ta.value) {
+      CHECK(r1.size() == 10);
+      for (size_t i = 1; i < r1.size(); ++i) CHECK(r1[i].second >= r1[i - 1].second);
+    }
+    CHECK(recall(ta.value) >= 0.9);
+    auto parted = Scann::partitioned(data.data(), n, dim, dim, 16, 6);
+    CHECK(parted.ok() && parted.value.search_mode() == SearchMode::Partitioned);
+    auto pa = parted.value.search_batched(qs, 10);
+    CHECK(pa.ok() && recall(pa.value) >= 0.95);
+    auto hashed = ScannBuilder().hashed(16).reorder(100).build(data.data(), n, dim, dim);
+    CHECK(hashed.ok() && hashed.value.search_mode() == SearchMode::Hashed);
+    auto ha = hashed.value.search_batched(qs, 10);
+    CHECK(ha.ok() && recall(ha.value) >= 0.9);
+    auto none = Scann::brute_force(nullptr, 0, dim, dim);  // "Dataset cannot be empty"
+    CHECK(!none.ok() && none.error.code == ErrorCode::InvalidArgument);
+
+    AsymmetricHasherConfig hc;
+    hc.num_subspaces = 16;
+    AsymmetricHasher hasher(hc);
+    CHECK(hasher.search(qs[0], 5).ok() && hasher.search(qs[0], 5).value.empty());  // unbuilt -> Ok(vec![])
+    CHECK(hasher.build(data.data(), n, dim, dim).code == ErrorCode::Ok);
+    auto hs = hasher.search(qs[0], 5);
+    CHECK(hs.ok() && hs.value.size() == 5);
+    auto hr = hasher.search_with_reordering(qs[0], 5, 50);
+    CHECK(hr.ok() && hr.value.size() == 5 && hr.value[0].first == truth.value[0][0].first);
+    CHECK(std::fabs(hr.value[0].second - truth.value[0][0].second) <= 1e-5f * (1.0f + truth.value[0][0].second));
+    auto hb = hasher.search_batched(qs, 5);
+    CHECK(hb.ok() && hb.value.size() == 40);
+
+    TreeXHybridConfig tcfg;
+    tcfg.num_partitions = 16;
+    tcfg.partitions_to_search = 6;
+    tcfg.num_subspaces = 16;
+    TreeXHybridSearcher tx(tcfg);
+    CHECK(tx.build(data.data(), n, dim, dim).code == ErrorCode::Ok);
+    std::vector<SearchParameters> params(qs.size());
+    for (size_t i = 0; i < params.size(); ++i) params[i].with_num_neighbors(i % 2 ? 5 : 10).with_pre_reordering_neighbors(50);
+    auto wp = tx.search_batched_with_params(qs, params);
+    CHECK(wp.ok() && wp.value.size() == qs.size() && wp.value[0].size() == 10 && wp.value[1].size() == 5);
+    params.pop_back();
+    auto wbad = tx.search_batched_with_params(qs, params);
+    CHECK(!wbad.ok() && wbad.error.code == ErrorCode::InvalidArgument);
+  }
   std::puts("hpp mirror ok");
   return 0;
 }
