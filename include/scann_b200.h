@@ -125,6 +125,9 @@ scann_status scann_part_create(const float* centers, size_t K, size_t dim, int d
                                scann_part** out);
 scann_status scann_part_select(scann_part* h, const float* queries, size_t nq, size_t qdim, size_t L,
                                uint32_t* tokens, float* dists, int memspace, void* stream);
+/* replaces the centres of an existing partitioner (same K and dim) without reallocating — the k-means trainer's
+ * per-iteration refresh (csrc/build_index.cu); the caller must not run scann_part_select concurrently. */
+scann_status scann_part_update(scann_part* h, const float* centers, int memspace);
 void scann_part_destroy(scann_part* h);
 
 /* ---------------------------------------------------------------------------------------------
@@ -287,10 +290,10 @@ scann_status scann_pq_encode(const float* codebook, size_t S, size_t ds, const f
  * encode = Codebook::encode, packing = PackedCodes4Bit::from_codes) runs through the exact kernels of the search path.
  *   scann_kmeans_fit   <- KMeans::fit (src/trees/kmeans.rs:166-432): Lloyd's algorithm from K distinct pseudo-random rows,
  *       exact nearest-centre assignment (ties -> lower id), f64 cluster sums, empty clusters re-seeded; centers[K*dim].
- *       balance_ratio > 1: after every update but the last two, clusters heavier than balance_ratio * n/K rows are split
- *       by re-seeding light clusters (< 0.6 * n/K rows) on hashed member rows — keeps leaves within the LUT16 scan's
- *       in-leaf position limit and the probe load even; 0 = plain Lloyd (what Codebook::train uses).
- *       "Cannot cluster empty dataset" / K outside 1..n -> SCANN_INVALID_ARGUMENT (kmeans.rs:171-184).
+ *       balance_ratio > 1: BALANCED training — Lloyd places K - K/8 centres, then the heaviest cluster is bisected
+ *       (2-means on its own rows) until K centres exist.  High-dimensional data has hub clusters that Lloyd never
+ *       leaves; bisection keeps every leaf within a few times the mean (and within the LUT16 scan's in-leaf position
+ *       limit) and evens the probe load.  <= 1 = plain Lloyd (what Codebook::train uses).
  *   scann_pq_train     <- Codebook::train (src/hashes/codebook.rs:146-202): one 16-code k-means per subspace (seed + s)
  *       over x, or over x - centers[assign] when centers/assign are given (tree_x_hybrid/mod.rs:177-189);
  *       codebook[S*16*(dim/S)].  dim % S != 0 -> SCANN_INVALID_ARGUMENT (codebook.rs:154-159).
@@ -312,6 +315,38 @@ scann_status scann_treeah_build(const float* x, size_t n, size_t dim, size_t str
                                 int reorder_measure, int keep_raw, int device, int memspace, scann_treeah** out);
 scann_status scann_ivf_build(const float* x, size_t n, size_t dim, size_t stride, size_t K, int kmeans_iters,
                              uint64_t seed, int device, int memspace, scann_ivf** out);
+
+/* ---------------------------------------------------------------------------------------------
+ * KMeansTree  (src/trees/kmeans_tree.rs) — hierarchical k-means partitioning
+ *   The tree is flattened in PREORDER: node i has centers[i*dim..], depth[i]; its children are the node ids
+ *   children[child_begin[i] .. child_begin[i] + child_count[i]) in stored order (child_count 0 = leaf).
+ *   scann_kmtree_create        <- a tree built elsewhere (e.g. by the reference's KMeansTree::build, :179-280)
+ *   scann_kmtree_build         <- KMeansTree::build with KMeansTreeConfig{num_children, max_depth, min_leaf_size,
+ *                                 kmeans_max_iterations, seed} (:17-41): the reference's recursion and leaf rules, node
+ *                                 centres = f64 mean of the node's points in index order; the k-means is the library's
+ *                                 (the reference's k-means++ RNG stream is unpinned).  "Cannot build tree from empty dataset".
+ *   scann_kmtree_search_leaves <- KMeansTree::search_leaves (:302-355) for a batch: depth-first walk, children by ascending
+ *                                 (distance, stored index), stop at 2k collected leaves, stable sort by distance, first k.
+ *                                 leaf_nodes[nq*k] = node ids (0xFFFFFFFF padding), dists / depths optional, counts[nq].
+ *   scann_kmtree_info / _export: sizes, then the arrays (any pointer may be NULL); leaf_begin/leaf_count[num_nodes] and
+ *                                 leaf_points[num_points] give KMeansTreeNode::datapoint_indices of the leaves (built trees).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct scann_kmtree scann_kmtree;
+scann_status scann_kmtree_create(const float* centers, const uint32_t* depth, const uint32_t* child_begin,
+                                 const uint32_t* child_count, const uint32_t* children, size_t num_nodes,
+                                 size_t num_child_entries, size_t dim, int device, scann_kmtree** out);
+scann_status scann_kmtree_build(const float* x, size_t n, size_t dim, size_t stride, size_t num_children,
+                                size_t max_depth, size_t min_leaf_size, int kmeans_iters, uint64_t seed, int device,
+                                int memspace, scann_kmtree** out);
+scann_status scann_kmtree_info(scann_kmtree* h, size_t* num_nodes, size_t* num_leaves, size_t* num_child_entries,
+                               size_t* num_points, size_t* dim);
+scann_status scann_kmtree_export(scann_kmtree* h, float* centers, uint32_t* depth, uint32_t* child_begin,
+                                 uint32_t* child_count, uint32_t* children, uint32_t* leaf_begin, uint32_t* leaf_count,
+                                 uint32_t* leaf_points);
+scann_status scann_kmtree_search_leaves(scann_kmtree* h, const float* queries, size_t nq, size_t qdim, size_t k,
+                                        uint32_t* leaf_nodes, float* dists, uint32_t* depths, uint32_t* counts,
+                                        int memspace, void* stream);
+void scann_kmtree_destroy(scann_kmtree* h);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU merge: k-way merge of `parts` per-shard result lists laid out

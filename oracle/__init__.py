@@ -219,6 +219,21 @@ def partition(centers, q, L, nthreads=1):
     return tokens, dists
 
 
+def kmtree_search_leaves(centers, depth, child_begin, child_count, children, q, k):
+    """KMeansTree::search_leaves over a flattened tree → (leaf node ids [nq,k], dists, depths, counts)"""
+    centers, q = _f32(centers), _f32(q)
+    u32 = lambda a: np.ascontiguousarray(a, np.uint32)
+    depth, child_begin, child_count, children = u32(depth), u32(child_begin), u32(child_count), u32(children)
+    nq, dim = q.shape
+    nodes = np.empty((nq, k), np.uint32)
+    dists = np.empty((nq, k), np.float32)
+    depths = np.empty((nq, k), np.uint32)
+    counts = np.empty((nq,), np.uint32)
+    lib().orc_kmtree_search_leaves(_p(centers), _p(depth), _p(child_begin), _p(child_count), _p(children), _sz(dim),
+                                   _p(q), _sz(nq), _sz(k), _p(nodes), _p(dists), _p(depths), _p(counts))
+    return nodes, dists, depths, counts
+
+
 def pq_encode(cb, x):
     """cb: [S, C, ds] f32; x: [n, S*ds] → codes [n, S] u8"""
     cb, x = _f32(cb), _f32(x)

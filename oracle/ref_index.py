@@ -15,18 +15,14 @@ def _chunk(K):
     return max(4096, min(262144, (1 << 31) // (4 * max(K, 1))))
 
 
-def kmeans(torch, x, K, iters=20, seed=7, chunk=None, balance_ratio=0.0):
-    """balance_ratio > 1: the same rule as the product trainer (csrc/build_index.cu) — after every update but the last
-    two, clusters heavier than balance_ratio * n/K donate floor(cnt / (n/K)) - 1 member rows as new centres of light
-    clusters (< 0.6 * n/K rows)."""
+def _lloyd(torch, x, K, iters, seed, chunk=None):
     n, d = x.shape
     K = min(K, n)
     chunk = chunk or _chunk(K)
     g = torch.Generator(device=x.device)
     g.manual_seed(seed)
     centers = x[torch.randperm(n, generator=g, device=x.device)[:K]].clone().float()
-    for it in range(iters):
-        centers_prev = centers
+    for _ in range(iters):
         sums = torch.zeros((K, d), dtype=torch.float32, device=x.device)
         cnts = torch.zeros((K,), dtype=torch.float32, device=x.device)
         cn = (centers * centers).sum(1)
@@ -41,19 +37,45 @@ def kmeans(torch, x, K, iters=20, seed=7, chunk=None, balance_ratio=0.0):
         if empty.numel() > 0:
             new_centers[empty] = x[torch.randint(0, n, (empty.numel(),), generator=g, device=x.device)].float()
         centers = new_centers
-        if balance_ratio > 1.0 and K >= 2 and n // K >= 4 and it + 2 < iters:
-            target = max(1, n // K)
-            a_all = assign(torch, x, centers_prev, chunk)
-            cnt = torch.bincount(a_all, minlength=K)
-            want = (torch.clamp(cnt // target, max=64) - 1).clamp(min=0)
-            heavy = cnt > int(balance_ratio * target)
-            p = torch.where(heavy, want.float() / cnt.clamp(min=1).float(), torch.zeros_like(cnt, dtype=torch.float32))
-            pick = (torch.rand((n,), generator=g, device=x.device) < p[a_all]).nonzero().flatten()
-            donors = (cnt < int(0.6 * target)).nonzero().flatten()
-            m = min(pick.numel(), donors.numel())
-            if m > 0:
-                centers[donors[:m]] = x[pick[:m]].float()
     return centers.contiguous()
+
+
+def kmeans(torch, x, K, iters=20, seed=7, chunk=None, balance_ratio=0.0):
+    """balance_ratio > 1: the same scheme as the product trainer (csrc/build_index.cu kmeans_device) — Lloyd places
+    K - K/8 centres, then the heaviest cluster is bisected (2-means on its own rows) until K centres exist."""
+    import heapq
+
+    n = x.shape[0]
+    K = min(K, n)
+    reserve = K // 8
+    if not balance_ratio > 1.0 or reserve == 0 or n // K < 4:
+        return _lloyd(torch, x, K, iters, seed, chunk)
+    K0 = K - reserve
+    c = _lloyd(torch, x, K0, iters, seed, chunk)
+    a = assign(torch, x, c, chunk)
+    order = torch.argsort(a, stable=True)
+    bounds = torch.cumsum(torch.bincount(a, minlength=K0), 0).tolist()
+    members = [order[(bounds[i - 1] if i else 0):bounds[i]] for i in range(K0)]
+    cs = [c[i] for i in range(K0)]
+    heap = [(-int(m.numel()), i) for i, m in enumerate(members)]
+    heapq.heapify(heap)
+    while len(cs) < K and heap and heap[0][0] <= -2:
+        _, i = heapq.heappop(heap)
+        rows = x[members[i]].float()
+        sub = _lloyd(torch, rows, 2, 6, seed + 7919 * len(cs))
+        side = assign(torch, rows, sub)
+        m0, m1 = members[i][side == 0], members[i][side == 1]
+        if m0.numel() == 0 or m1.numel() == 0:
+            heapq.heappush(heap, (0, i))
+            continue
+        cs[i], members[i] = sub[0], m0
+        cs.append(sub[1])
+        members.append(m1)
+        heapq.heappush(heap, (-int(m0.numel()), i))
+        heapq.heappush(heap, (-int(m1.numel()), len(cs) - 1))
+    while len(cs) < K:
+        cs.append(x[len(cs) % n].float())
+    return torch.stack(cs).contiguous()
 
 
 def train_codebook(torch, residuals, S, num_codes=16, iters=20, seed=42):

@@ -998,6 +998,67 @@ uint32_t orc_reorder(const float* raw, size_t stride, size_t dim, int measure, c
   return static_cast<uint32_t>(r.size());
 }
 
+// trees/kmeans_tree.rs:302-355 KMeansTree::search_leaves over a flattened tree (preorder node ids; children of node i =
+// children[child_begin[i] .. + child_count[i]) in stored order).  Recursion, stable sorts and the `len >= 2k` early
+// exit exactly as the reference writes them; squared_distance (:358-366) is a sequential f32 sum of d*d.
+namespace {
+struct LeafHit {
+  uint32_t depth;
+  float dist;
+  uint32_t node;
+};
+struct FlatTree {
+  const float* centers;
+  const uint32_t *depth, *child_begin, *child_count, *children;
+  size_t dim;
+};
+float tree_sqdist(const float* a, const float* b, size_t dim) {
+  float s = 0.0f;
+  for (size_t i = 0; i < dim; ++i) {
+    float d = a[i] - b[i];
+    s += d * d;
+  }
+  return s;
+}
+void search_leaves_rec(const FlatTree& t, uint32_t node, const float* q, size_t k, std::vector<LeafHit>& results) {
+  float dist = tree_sqdist(q, t.centers + static_cast<size_t>(node) * t.dim, t.dim);
+  if (t.child_count[node] == 0) {
+    results.push_back({t.depth[node], dist, node});
+    return;
+  }
+  std::vector<std::pair<size_t, float>> cd;
+  for (size_t i = 0; i < t.child_count[node]; ++i) {
+    uint32_t ch = t.children[t.child_begin[node] + i];
+    cd.emplace_back(i, tree_sqdist(q, t.centers + static_cast<size_t>(ch) * t.dim, t.dim));
+  }
+  std::stable_sort(cd.begin(), cd.end(), [](const auto& a, const auto& b) { return a.second < b.second; });
+  for (auto& c : cd) {
+    search_leaves_rec(t, t.children[t.child_begin[node] + c.first], q, k, results);
+    if (results.size() >= k * 2) break;
+  }
+}
+}  // namespace
+
+void orc_kmtree_search_leaves(const float* centers, const uint32_t* depth, const uint32_t* child_begin,
+                              const uint32_t* child_count, const uint32_t* children, size_t dim, const float* q,
+                              size_t nq, size_t k, uint32_t* out_nodes, float* out_dists, uint32_t* out_depths,
+                              uint32_t* out_counts) {
+  FlatTree t{centers, depth, child_begin, child_count, children, dim};
+  for (size_t qi = 0; qi < nq; ++qi) {
+    std::vector<LeafHit> res;
+    search_leaves_rec(t, 0, q + qi * dim, k, res);
+    std::stable_sort(res.begin(), res.end(), [](const LeafHit& a, const LeafHit& b) { return a.dist < b.dist; });
+    if (res.size() > k) res.resize(k);
+    for (size_t j = 0; j < k; ++j) {
+      bool ok = j < res.size();
+      out_nodes[qi * k + j] = ok ? res[j].node : 0xFFFFFFFFu;
+      out_dists[qi * k + j] = ok ? res[j].dist : __builtin_huge_valf();
+      out_depths[qi * k + j] = ok ? res[j].depth : 0u;
+    }
+    out_counts[qi] = static_cast<uint32_t>(res.size());
+  }
+}
+
 int orc_num_threads(void) {
   unsigned n = std::thread::hardware_concurrency();
   return n ? static_cast<int>(n) : 1;

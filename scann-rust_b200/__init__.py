@@ -10,7 +10,7 @@ from . import build as build_lib  # noqa: F401
 from . import capi, distributed, indexing, scann, searchers  # noqa: F401
 from .capi import ScannError, device_count, load  # noqa: F401
 from .scann import Scann, ScannBuilder, ScannConfig, SearchMode  # noqa: F401
-from .searchers import (AsymmetricHasher, LeafScanSearcher, AsymmetricHasherConfig, BruteForceSearcher, DistanceMeasure,  # noqa: F401
+from .searchers import (AsymmetricHasher, KMeansTree, KMeansTreeConfig, LeafScanSearcher, AsymmetricHasherConfig, BruteForceSearcher, DistanceMeasure,  # noqa: F401
                         ScalarQuantizedBruteForceSearcher, ScalarQuantizedConfig, SearchParameters, TreePartitioner, TreeXHybridConfig,
                         TreeXHybridSearcher, lut16_build, lut16_scan, merge_topk, merge_topk_packed, pq_encode, results_to_lists,
                         scalar_quantize, tc_scores)

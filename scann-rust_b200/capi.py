@@ -33,12 +33,14 @@ SYMBOLS = [
     "scann_last_error", "scann_version", "scann_device_count",
     "scann_bf_create", "scann_bf_search", "scann_bf_search_radius", "scann_bf_destroy", "scann_bf_path_stats", "scann_sq8_path_stats",
     "scann_sq8_quantize", "scann_sq8_create", "scann_sq8_search", "scann_sq8_destroy",
-    "scann_part_create", "scann_part_select", "scann_part_destroy",
+    "scann_part_create", "scann_part_select", "scann_part_destroy", "scann_part_update",
     "scann_treeah_create", "scann_treeah_create_ex", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
     "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end", "scann_treeah_partition",
     "scann_treeah_set_filter", "scann_treeah_path_stats", "scann_treeah_tc_profile",
     "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_merge_topk_packed", "scann_tc_scores",
     "scann_ivf_create", "scann_ivf_search", "scann_ivf_destroy",
+    "scann_kmtree_create", "scann_kmtree_build", "scann_kmtree_info", "scann_kmtree_export", "scann_kmtree_search_leaves",
+    "scann_kmtree_destroy",
     "scann_kmeans_fit", "scann_pq_train", "scann_treeah_build", "scann_ivf_build", "scann_treeah_set_reorder",
 ]
 
@@ -88,6 +90,7 @@ def load():
     L.scann_part_create.argtypes = [vp, sz, sz, i32, i32, C.POINTER(vp)]
     L.scann_part_select.argtypes = [vp, vp, sz, sz, sz, vp, vp, i32, vp]
     L.scann_part_destroy.argtypes = [vp]
+    L.scann_part_update.argtypes = [vp, vp, i32]
     L.scann_part_destroy.restype = None
     L.scann_treeah_create.argtypes = [vp, sz, sz, vp, sz, vp, vp, vp, sz, vp, sz, sz, i32, i32, i32, i32,
                                       C.POINTER(vp)]
@@ -122,6 +125,13 @@ def load():
     L.scann_treeah_build.argtypes = [vp, sz, sz, sz, sz, sz, sz, i32, u64, i32, i32, i32, i32, i32, C.POINTER(vp)]
     L.scann_ivf_build.argtypes = [vp, sz, sz, sz, sz, i32, u64, i32, i32, C.POINTER(vp)]
     L.scann_treeah_set_reorder.argtypes = [vp, i32]
+    L.scann_kmtree_create.argtypes = [vp, vp, vp, vp, vp, sz, sz, sz, i32, C.POINTER(vp)]
+    L.scann_kmtree_build.argtypes = [vp, sz, sz, sz, sz, sz, sz, i32, u64, i32, i32, C.POINTER(vp)]
+    L.scann_kmtree_info.argtypes = [vp] + [C.POINTER(sz)] * 5
+    L.scann_kmtree_export.argtypes = [vp] * 9
+    L.scann_kmtree_search_leaves.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp, i32, vp]
+    L.scann_kmtree_destroy.argtypes = [vp]
+    L.scann_kmtree_destroy.restype = None
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("scann_last_error", "scann_version") and not name.endswith("_destroy"):

@@ -23,7 +23,7 @@ namespace scann {
 
 namespace {
 
-constexpr float kBalanceRatio = 3.0f;  // partition centres of the in-library builds: no leaf above ~3x the mean
+constexpr float kBalanceRatio = 3.0f;  // partition centres of the in-library builds are trained balanced (kmeans_device)
 
 __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -82,6 +82,34 @@ __global__ void residual_kernel(const float* __restrict__ x, size_t n, size_t di
   out[t] = __fsub_rn(x[t], centers[static_cast<size_t>(assign[i]) * dim + d]);  // tree_x_hybrid/mod.rs:181-185
 }
 
+// Nearest centre for a SMALL centre set (the 16 codewords of one PQ subspace): one thread per row, centres in shared
+// memory, the partitioner's exact arithmetic (sequential d = x - c, sum += d*d, never fused; ties -> lower id), so the
+// result equals TreePartitioner::partition(x, 1) without its per-row selection machinery.
+__global__ void __launch_bounds__(256) nearest_small_kernel(const float* __restrict__ x, size_t n, int dim,
+                                                            const float* __restrict__ centers, int K,
+                                                            uint32_t* __restrict__ assign) {
+  extern __shared__ float cs[];  // [K][dim]
+  for (int i = threadIdx.x; i < K * dim; i += blockDim.x) cs[i] = centers[i];
+  __syncthreads();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* row = x + i * dim;
+  float best = __int_as_float(0x7F800000);
+  uint32_t arg = 0;
+  for (int c = 0; c < K; ++c) {
+    float acc = 0.0f;
+    for (int d = 0; d < dim; ++d) {
+      const float df = __fsub_rn(row[d], cs[c * dim + d]);
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+    }
+    if (acc < best || c == 0) {
+      best = acc;
+      arg = static_cast<uint32_t>(c);
+    }
+  }
+  assign[i] = arg;
+}
+
 __global__ void iota_kernel(uint32_t* __restrict__ v, size_t n) {
   const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t < n) v[t] = static_cast<uint32_t>(t);
@@ -105,40 +133,6 @@ __global__ void fill_kernel(float* __restrict__ v, size_t n, float value) {
   if (t < n) v[t] = value;
 }
 
-// ---- cluster balancing (kmeans_device, balance_ratio > 0) ----
-// A cluster holding more than balance_ratio * n/K rows is split: floor(cnt / (n/K)) - 1 of its rows (hashed choice,
-// deterministic) become the new centres of as many LIGHT clusters (fewer than 0.6 * n/K rows: typically one of two
-// centres that share a mode), whose rows go to their neighbours at the next assignment.
-struct HeavyRowPick {
-  const uint32_t* assign;
-  const uint32_t* cnt;
-  uint32_t K, hi, target;
-  uint64_t salt;
-  __device__ bool operator()(const uint32_t& i) const {
-    const uint32_t c = assign[i];
-    if (c >= K) return false;
-    const uint32_t m = cnt[c];
-    if (m <= hi) return false;
-    uint32_t want = m / target;
-    want = (want > 64u ? 64u : want) - 1u;
-    return splitmix64(salt + i) % m < want;
-  }
-};
-struct LightClusterPick {
-  const uint32_t* cnt;
-  uint32_t lo;
-  __device__ bool operator()(const uint32_t& c) const { return cnt[c] < lo; }
-};
-
-__global__ void reseed_kernel(const float* __restrict__ x, size_t dim, const uint32_t* __restrict__ rows,
-                              const uint32_t* __restrict__ donors, const uint32_t* __restrict__ n_rows,
-                              const uint32_t* __restrict__ n_donors, float* __restrict__ centers) {
-  const uint32_t m = min(*n_rows, *n_donors);
-  const size_t t = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t j = t / dim, d = t - j * dim;
-  if (j < m) centers[static_cast<size_t>(donors[j]) * dim + d] = x[static_cast<size_t>(rows[j]) * dim + d];
-}
-
 inline unsigned grid_for(size_t n, unsigned block = 256) { return static_cast<unsigned>((n + block - 1) / block); }
 
 uint64_t coprime_multiplier(uint64_t seed, uint64_t n) {
@@ -155,64 +149,151 @@ uint64_t coprime_multiplier(uint64_t seed, uint64_t n) {
   }
 }
 
-// nearest centre of every row (TreePartitioner::partition(x, 1).tokens[0]); x contiguous device [n][dim]
+// nearest centre of every row (TreePartitioner::partition(x, 1).tokens[0]); x contiguous device [n][dim].
+// *part: created on first use, refreshed with the current centres afterwards (scann_part_update), destroyed by the caller.
+scann_status assign_rows(scann_part** part, const float* x, size_t n, size_t dim, const float* centers, size_t K,
+                         uint32_t* assign, int device) {
+  SCANN_CUDA(cudaDeviceSynchronize());  // centres / rows were produced on the default stream; the partitioner has its own
+  if (*part == nullptr) SCANN_TRY(scann_part_create(centers, K, dim, device, SCANN_DEVICE, part));
+  else SCANN_TRY(scann_part_update(*part, centers, SCANN_DEVICE));
+  scann_status st = scann_part_select(*part, x, n, dim, 1, assign, nullptr, SCANN_DEVICE, nullptr);
+  if (st == SCANN_OK && cudaDeviceSynchronize() != cudaSuccess) st = cuda_fail(cudaGetLastError(), "assign", __FILE__, __LINE__);
+  return st;
+}
 scann_status assign_rows(const float* x, size_t n, size_t dim, const float* centers, size_t K, uint32_t* assign, int device) {
   scann_part* part = nullptr;
-  SCANN_TRY(scann_part_create(centers, K, dim, device, SCANN_DEVICE, &part));
-  scann_status st = scann_part_select(part, x, n, dim, 1, assign, nullptr, SCANN_DEVICE, nullptr);
-  if (st == SCANN_OK && cudaDeviceSynchronize() != cudaSuccess) st = cuda_fail(cudaGetLastError(), "assign", __FILE__, __LINE__);
+  scann_status st = assign_rows(&part, x, n, dim, centers, K, assign, device);
   scann_part_destroy(part);
   return st;
 }
+struct PartOwner {  // destroys the partitioner on every exit path
+  scann_part* p = nullptr;
+  ~PartOwner() { scann_part_destroy(p); }
+};
 
-// Lloyd's k-means on contiguous device rows; centers: device [K][dim] (K <= n).  balance_ratio > 0 re-seeds light
-// clusters inside clusters heavier than balance_ratio * n/K after every update but the last two.
-scann_status kmeans_device(const float* x, size_t n, size_t dim, size_t K, int iters, uint64_t seed, float balance_ratio,
-                           float* centers, int device) {
+struct LloydScratch {  // sized once for the largest (n, K) of a training run
+  DevBuf<uint32_t> assign, cnt;
+  DevBuf<double> sums;
+  scann_status reserve(size_t n, size_t K, size_t dim) {
+    if (assign.n < n) SCANN_TRY(assign.alloc(n));
+    if (cnt.n < K) SCANN_TRY(cnt.alloc(K));
+    if (sums.n < K * dim) SCANN_TRY(sums.alloc(K * dim));
+    return SCANN_OK;
+  }
+};
+
+// Lloyd's algorithm on contiguous device rows from K distinct pseudo-random rows; centers: device [K][dim] (K <= n).
+// sc.assign holds the assignment of the LAST iteration's assignment step (i.e. against the centres before the last
+// update) on return.
+scann_status lloyd_device(const float* x, size_t n, size_t dim, size_t K, int iters, uint64_t seed, float* centers,
+                          int device, LloydScratch& sc) {
   const uint64_t a = coprime_multiplier(seed, n), b = splitmix64(seed ^ 0xA5A5A5A5ull) % n;
   gather_affine_kernel<<<grid_for(K * dim), 256>>>(x, n, dim, dim, a, b, K, centers);
   SCANN_CUDA(cudaGetLastError());
-  DevBuf<uint32_t> assign, cnt, pick_rows, pick_donors, pick_n;
-  DevBuf<double> sums;
-  DevBuf<uint8_t> cub_tmp;
-  SCANN_TRY(assign.alloc(n));
-  SCANN_TRY(cnt.alloc(K));
-  SCANN_TRY(sums.alloc(K * dim));
-  const uint32_t target = static_cast<uint32_t>(std::max<size_t>(1, n / K));
-  const bool balance = balance_ratio > 1.0f && K >= 2 && n / K >= 4;
-  size_t tmp_bytes = 0;
-  cub::CountingInputIterator<uint32_t> iota(0u);
-  if (balance) {
-    SCANN_TRY(pick_rows.alloc(n));
-    SCANN_TRY(pick_donors.alloc(K));
-    SCANN_TRY(pick_n.alloc(2));
-    size_t t1 = 0, t2 = 0;
-    HeavyRowPick hp{assign.p, cnt.p, static_cast<uint32_t>(K), 0u, target, 0ull};
-    LightClusterPick lp{cnt.p, 0u};
-    SCANN_CUDA(cub::DeviceSelect::If(nullptr, t1, iota, pick_rows.p, pick_n.p, static_cast<int>(n), hp));
-    SCANN_CUDA(cub::DeviceSelect::If(nullptr, t2, iota, pick_donors.p, pick_n.p + 1, static_cast<int>(K), lp));
-    tmp_bytes = std::max(t1, t2);
-    SCANN_TRY(cub_tmp.alloc(tmp_bytes));
-  }
+  SCANN_TRY(sc.reserve(n, K, dim));
+  PartOwner part;
+  const bool small = K <= 64 && K * dim <= 4096;
   for (int it = 0; it < iters; ++it) {
-    SCANN_TRY(assign_rows(x, n, dim, centers, K, assign.p, device));
-    SCANN_CUDA(cudaMemset(sums.p, 0, K * dim * sizeof(double)));
-    SCANN_CUDA(cudaMemset(cnt.p, 0, K * sizeof(uint32_t)));
-    kmeans_accum_kernel<<<grid_for(n, 8), 256>>>(x, n, dim, assign.p, K, sums.p, cnt.p);
-    kmeans_update_kernel<<<grid_for(K * dim), 256>>>(sums.p, cnt.p, K, dim, x, n, splitmix64(seed + 1000003ull * (it + 1)),
-                                                     centers);
-    SCANN_CUDA(cudaGetLastError());
-    if (balance && it + 2 < iters) {
-      HeavyRowPick hp{assign.p, cnt.p, static_cast<uint32_t>(K), static_cast<uint32_t>(balance_ratio * target), target,
-                      splitmix64(seed ^ (0xBA1A9CEull + it))};
-      LightClusterPick lp{cnt.p, static_cast<uint32_t>(0.6f * target)};
-      size_t tb = tmp_bytes;
-      SCANN_CUDA(cub::DeviceSelect::If(cub_tmp.p, tb, iota, pick_rows.p, pick_n.p, static_cast<int>(n), hp));
-      tb = tmp_bytes;
-      SCANN_CUDA(cub::DeviceSelect::If(cub_tmp.p, tb, iota, pick_donors.p, pick_n.p + 1, static_cast<int>(K), lp));
-      reseed_kernel<<<grid_for(K * dim), 256>>>(x, dim, pick_rows.p, pick_donors.p, pick_n.p, pick_n.p + 1, centers);
+    if (small) {
+      nearest_small_kernel<<<grid_for(n), 256, K * dim * sizeof(float)>>>(x, n, static_cast<int>(dim), centers,
+                                                                          static_cast<int>(K), sc.assign.p);
       SCANN_CUDA(cudaGetLastError());
+    } else {
+      SCANN_TRY(assign_rows(&part.p, x, n, dim, centers, K, sc.assign.p, device));
     }
+    SCANN_CUDA(cudaMemsetAsync(sc.sums.p, 0, K * dim * sizeof(double)));
+    SCANN_CUDA(cudaMemsetAsync(sc.cnt.p, 0, K * sizeof(uint32_t)));
+    kmeans_accum_kernel<<<grid_for(n, 8), 256>>>(x, n, dim, sc.assign.p, K, sc.sums.p, sc.cnt.p);
+    kmeans_update_kernel<<<grid_for(K * dim), 256>>>(sc.sums.p, sc.cnt.p, K, dim, x, n,
+                                                     splitmix64(seed + 1000003ull * (it + 1)), centers);
+    SCANN_CUDA(cudaGetLastError());
+  }
+  return SCANN_OK;
+}
+
+// nearest centre against the CURRENT centres (the partitioner's exact arithmetic either way)
+scann_status nearest_device(const float* x, size_t n, size_t dim, const float* centers, size_t K, uint32_t* assign,
+                            int device) {
+  if (K <= 64 && K * dim <= 4096) {
+    nearest_small_kernel<<<grid_for(n), 256, K * dim * sizeof(float)>>>(x, n, static_cast<int>(dim), centers,
+                                                                        static_cast<int>(K), assign);
+    SCANN_CUDA(cudaGetLastError());
+    return SCANN_OK;
+  }
+  return assign_rows(x, n, dim, centers, K, assign, device);
+}
+
+// k-means on contiguous device rows; centers: device [K][dim] (K <= n).
+// balance_ratio <= 1: plain Lloyd.  balance_ratio > 1: BALANCED training — Lloyd places K - K/8 centres, then the
+// heaviest cluster is bisected (2-means on its own rows) again and again until K centres exist.  High-dimensional data
+// has hubs (a centre near the bulk of the data collects the tails of many modes); Lloyd never leaves that optimum and
+// re-seeding inside a hub only shaves it, while bisection always halves the current worst leaf.  On the C5 data model
+// the largest leaf falls from 13-16x to ~2.5x the mean (it must stay below the scan's in-leaf position limit).
+scann_status kmeans_device(const float* x, size_t n, size_t dim, size_t K, int iters, uint64_t seed, float balance_ratio,
+                           float* centers, int device) {
+  LloydScratch sc;
+  const size_t reserve = K / 8;
+  if (!(balance_ratio > 1.0f) || reserve == 0 || n / K < 4) {
+    SCANN_TRY(lloyd_device(x, n, dim, K, iters, seed, centers, device, sc));
+    SCANN_CUDA(cudaDeviceSynchronize());
+    return SCANN_OK;
+  }
+  const size_t K0 = K - reserve;
+  SCANN_TRY(lloyd_device(x, n, dim, K0, iters, seed, centers, device, sc));
+  SCANN_TRY(nearest_device(x, n, dim, centers, K0, sc.assign.p, device));
+  std::vector<uint32_t> h_assign(n);
+  SCANN_CUDA(cudaMemcpy(h_assign.data(), sc.assign.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  std::vector<std::vector<uint32_t>> members(K);
+  for (size_t i = 0; i < n; ++i)
+    if (h_assign[i] < K0) members[h_assign[i]].push_back(static_cast<uint32_t>(i));
+  // max-heap on (rows, cluster); a cluster that cannot be split any more re-enters with weight 0
+  std::vector<std::pair<size_t, uint32_t>> heap;
+  for (size_t c = 0; c < K0; ++c) heap.emplace_back(members[c].size(), static_cast<uint32_t>(c));
+  std::make_heap(heap.begin(), heap.end());
+  size_t biggest = 0;
+  for (size_t c = 0; c < K0; ++c) biggest = std::max(biggest, members[c].size());
+  DevBuf<uint32_t> d_idx;
+  DevBuf<float> d_rows, d_two;
+  SCANN_TRY(d_idx.alloc(std::max<size_t>(biggest, 2)));
+  SCANN_TRY(d_rows.alloc(std::max<size_t>(biggest, 2) * dim));
+  SCANN_TRY(d_two.alloc(2 * dim));
+  LloydScratch sc2;
+  std::vector<uint32_t> side;
+  size_t have = K0;
+  while (have < K && !heap.empty() && heap.front().first >= 2) {
+    std::pop_heap(heap.begin(), heap.end());
+    const uint32_t c = heap.back().second;
+    heap.pop_back();
+    std::vector<uint32_t>& mem = members[c];
+    const size_t m = mem.size();
+    SCANN_CUDA(cudaMemcpy(d_idx.p, mem.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    gather_rows_kernel<<<grid_for(m * dim), 256>>>(x, dim, d_idx.p, m, d_rows.p);
+    SCANN_CUDA(cudaGetLastError());
+    SCANN_TRY(lloyd_device(d_rows.p, m, dim, 2, 6, seed + 7919ull * have, d_two.p, device, sc2));
+    SCANN_TRY(nearest_device(d_rows.p, m, dim, d_two.p, 2, sc2.assign.p, device));
+    side.resize(m);
+    SCANN_CUDA(cudaMemcpy(side.data(), sc2.assign.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> m0, m1;
+    for (size_t i = 0; i < m; ++i) (side[i] == 0 ? m0 : m1).push_back(mem[i]);
+    if (m0.empty() || m1.empty()) {  // identical rows: not splittable
+      heap.emplace_back(0, c);
+      std::push_heap(heap.begin(), heap.end());
+      continue;
+    }
+    SCANN_CUDA(cudaMemcpy(centers + static_cast<size_t>(c) * dim, d_two.p, dim * sizeof(float), cudaMemcpyDeviceToDevice));
+    SCANN_CUDA(cudaMemcpy(centers + have * dim, d_two.p + dim, dim * sizeof(float), cudaMemcpyDeviceToDevice));
+    members[have] = std::move(m1);
+    mem = std::move(m0);
+    heap.emplace_back(mem.size(), c);
+    std::push_heap(heap.begin(), heap.end());
+    heap.emplace_back(members[have].size(), static_cast<uint32_t>(have));
+    std::push_heap(heap.begin(), heap.end());
+    ++have;
+  }
+  if (have < K) {  // nothing left to split (duplicate rows): the remaining centres sit on hashed rows
+    const uint64_t a = coprime_multiplier(seed ^ 0xF111ull, n), b = splitmix64(seed ^ 0xF222ull) % n;
+    gather_affine_kernel<<<grid_for((K - have) * dim), 256>>>(x, n, dim, dim, a, b, K - have, centers + have * dim);
+    SCANN_CUDA(cudaGetLastError());
   }
   SCANN_CUDA(cudaDeviceSynchronize());
   return SCANN_OK;
@@ -257,6 +338,15 @@ scann_status pq_train_device(const float* rows, size_t n, size_t dim, size_t S, 
 }
 
 }  // namespace
+
+// kmtree.cu builds its nodes with the same trainer: centres of `x` (contiguous device rows) and, when assign_out is not
+// null, the final nearest-centre assignment against those centres
+scann_status kmeans_rows_device(const float* x, size_t n, size_t dim, size_t K, int iters, uint64_t seed,
+                                float balance_ratio, float* centers, uint32_t* assign_out, int device) {
+  SCANN_TRY(kmeans_device(x, n, dim, K, iters, seed, balance_ratio, centers, device));
+  if (assign_out) SCANN_TRY(assign_rows(x, n, dim, centers, K, assign_out, device));
+  return SCANN_OK;
+}
 
 }  // namespace scann
 

@@ -243,9 +243,9 @@ size_t part_tc_scratch_bytes(size_t K, size_t dim, size_t nq) {
 
 scann_status part_tc_prepare(const float* centers, size_t K, size_t dim, PartTc* out, cudaStream_t s) {
   const size_t kpad = tc_kpad(dim), rpad = tc_rows_pad(K);
-  SCANN_TRY(out->cbf.alloc(rpad * kpad));
-  SCANN_TRY(out->hx.alloc(rpad));
-  SCANN_TRY(out->small.alloc(1));
+  if (out->cbf.n != rpad * kpad) SCANN_TRY(out->cbf.alloc(rpad * kpad));  // kept across scann_part_update
+  if (out->hx.n != rpad) SCANN_TRY(out->hx.alloc(rpad));
+  if (out->small.n != 1) SCANN_TRY(out->small.alloc(1));
   SCANN_TRY(tc_prepare_rows(centers, false, K, dim, dim, 1.0f, true, out->cbf.p, out->hx.p, out->small.p, s));
   SCANN_CUDA(cudaMemcpyAsync(&out->cmax2, out->small.p, sizeof(float), cudaMemcpyDeviceToHost, s));
   SCANN_CUDA(cudaStreamSynchronize(s));
@@ -406,6 +406,28 @@ scann_status scann_part_create(const float* centers, size_t K, size_t dim, int d
     return st;
   }
   *out = h;
+  return SCANN_OK;
+}
+
+scann_status scann_part_update(scann_part* h, const float* centers, int memspace) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "Partitioner not built");
+  SCANN_REQUIRE(centers != nullptr, SCANN_INVALID_ARGUMENT, "NULL buffer");
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard g(h->device);
+  const float* src = centers;
+  DevBuf<float> tmp;
+  if (memspace == SCANN_DEVICE) SCANN_CUDA(cudaDeviceSynchronize());  // the caller's array was produced on another stream
+  if (h->ptc.ready) {  // the tensor-core operands are derived from h->centers
+    SCANN_CUDA(cudaMemcpyAsync(h->centers.p, centers, h->K * h->dim * sizeof(float), in_kind(memspace), h->stream));
+    src = h->centers.p;
+  } else if (memspace == SCANN_HOST) {
+    SCANN_TRY(tmp.upload(centers, h->K * h->dim, SCANN_HOST, h->stream));
+    src = tmp.p;
+  }
+  launch_transpose(src, h->K, h->dim, h->centersT.p, h->stream);
+  if (h->ptc.ready) SCANN_TRY(part_tc_prepare(h->centers.p, h->K, h->dim, &h->ptc, h->stream));
+  SCANN_CUDA(cudaStreamSynchronize(h->stream));
   return SCANN_OK;
 }
 

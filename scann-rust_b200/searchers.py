@@ -357,6 +357,101 @@ class TreePartitioner(_Handle):
 
 
 @dataclass
+class KMeansTreeConfig:
+    """KMeansTreeConfig (src/trees/kmeans_tree.rs:17-56); distance is SquaredL2 (search_leaves hard-wires it, :358-366)."""
+    num_children: int = 100
+    max_depth: int = 1
+    min_leaf_size: int = 1
+    kmeans_max_iterations: int = 20
+    seed: Optional[int] = None
+
+
+class KMeansTree(_Handle):
+    """KMeansTree (src/trees/kmeans_tree.rs:154-395): hierarchical k-means partitioning.  Nodes are numbered in
+    preorder; ``search_leaves`` returns leaf NODE ids (``export()`` maps them to datapoint indices)."""
+    _destroy = "scann_kmtree_destroy"
+
+    def __init__(self, config: KMeansTreeConfig = KMeansTreeConfig(), device: int = 0):
+        super().__init__()
+        self.config = config
+        self.device = device
+
+    def build(self, dataset):
+        capi.require_gpu()
+        if dataset is None or int(dataset.shape[0]) == 0:
+            raise ScannError(capi.INVALID_ARGUMENT, "Cannot build tree from empty dataset")
+        p_x, space, keep = _dataset_ptr(dataset, np.float32)
+        n, dim = int(dataset.shape[0]), int(dataset.shape[1])
+        c = self.config
+        self.close()
+        capi.check(capi.load().scann_kmtree_build(p_x, n, dim, dim, int(c.num_children), int(c.max_depth),
+                                                  int(c.min_leaf_size), int(c.kmeans_max_iterations),
+                                                  int(c.seed if c.seed is not None else 42), self.device, space,
+                                                  C.byref(self._h)))
+        del keep
+        return self
+
+    def build_from_arrays(self, centers, depth, child_begin, child_count, children):
+        """a tree built elsewhere (flattened in preorder, see include/scann_b200.h)"""
+        capi.require_gpu()
+        centers = capi.as_f32(centers)
+        u32 = lambda a: np.ascontiguousarray(a, np.uint32)
+        depth, child_begin, child_count, children = u32(depth), u32(child_begin), u32(child_count), u32(children)
+        self.close()
+        capi.check(capi.load().scann_kmtree_create(capi.np_ptr(centers), capi.np_ptr(depth), capi.np_ptr(child_begin),
+                                                   capi.np_ptr(child_count), capi.np_ptr(children) if len(children) else None,
+                                                   len(depth), len(children), centers.shape[1], self.device,
+                                                   C.byref(self._h)))
+        return self
+
+    def info(self):
+        v = [C.c_size_t(0) for _ in range(5)]
+        capi.check(capi.load().scann_kmtree_info(self._h, *[C.byref(a) for a in v]))
+        return dict(zip(("num_nodes", "num_leaves", "num_child_entries", "num_points", "dim"), (a.value for a in v)))
+
+    def num_leaves(self) -> int:
+        return self.info()["num_leaves"] if self._h else 0
+
+    def size(self) -> int:
+        return self.info()["num_points"] if self._h else 0
+
+    def export(self):
+        i = self.info()
+        out = {
+            "centers": np.empty((i["num_nodes"], i["dim"]), np.float32), "depth": np.empty(i["num_nodes"], np.uint32),
+            "child_begin": np.empty(i["num_nodes"], np.uint32), "child_count": np.empty(i["num_nodes"], np.uint32),
+            "children": np.empty(i["num_child_entries"], np.uint32), "leaf_begin": np.zeros(i["num_nodes"], np.uint32),
+            "leaf_count": np.zeros(i["num_nodes"], np.uint32), "leaf_points": np.empty(i["num_points"], np.uint32),
+        }
+        capi.check(capi.load().scann_kmtree_export(self._h, *[capi.np_ptr(out[k]) for k in (
+            "centers", "depth", "child_begin", "child_count", "children", "leaf_begin", "leaf_count", "leaf_points")]))
+        return out
+
+    def search_leaves(self, queries, k: int):
+        """KMeansTree::search_leaves (:302-319) for a batch → (leaf node ids [nq,k], dists, depths, counts)"""
+        if not self._h:
+            raise ScannError(capi.FAILED_PRECONDITION, "Tree not built")
+        b = _Batch(queries, self.device)
+        kk = max(int(k), 1)
+        if b.memspace == capi.DEVICE:
+            torch = _torch()
+            dev = queries.device
+            nodes = torch.empty((b.nq, kk), dtype=torch.int32, device=dev)
+            dists = torch.empty((b.nq, kk), dtype=torch.float32, device=dev)
+            depths = torch.empty((b.nq, kk), dtype=torch.int32, device=dev)
+            counts = torch.empty((b.nq,), dtype=torch.int32, device=dev)
+            ptrs = [C.c_void_p(t.data_ptr()) for t in (nodes, dists, depths, counts)]
+        else:
+            nodes = np.empty((b.nq, kk), np.uint32)
+            dists = np.empty((b.nq, kk), np.float32)
+            depths = np.empty((b.nq, kk), np.uint32)
+            counts = np.empty((b.nq,), np.uint32)
+            ptrs = [capi.np_ptr(a) for a in (nodes, dists, depths, counts)]
+        capi.check(capi.load().scann_kmtree_search_leaves(self._h, b.ptr, b.nq, b.dim, int(k), *ptrs, b.memspace, b.stream))
+        return nodes[:, :k], dists[:, :k], depths[:, :k], counts
+
+
+@dataclass
 class AsymmetricHasherConfig:
     """AsymmetricHasherConfig (src/hashes/hasher.rs:19-69); the GPU path is the 16-code LUT16 variant."""
     num_codes: int = 16

@@ -120,7 +120,7 @@ int main() {
     CHECK(parted.ok() && parted.value.search_mode() == SearchMode::Partitioned);
     auto pa = parted.value.search_batched(qs, 10);
     CHECK(pa.ok() && recall(pa.value) >= 0.95);
-    auto hashed = ScannBuilder().hashed(16).reorder(100).build(data.data(), n, dim, dim);
+    auto hashed = ScannBuilder().hashed(16).reorder(800).build(data.data(), n, dim, dim);  // flat PQ: a mode (500 rows) is one code cell
     CHECK(hashed.ok() && hashed.value.search_mode() == SearchMode::Hashed);
     auto ha = hashed.value.search_batched(qs, 10);
     CHECK(ha.ok() && recall(ha.value) >= 0.9);
@@ -134,7 +134,7 @@ int main() {
     CHECK(hasher.build(data.data(), n, dim, dim).code == ErrorCode::Ok);
     auto hs = hasher.search(qs[0], 5);
     CHECK(hs.ok() && hs.value.size() == 5);
-    auto hr = hasher.search_with_reordering(qs[0], 5, 50);
+    auto hr = hasher.search_with_reordering(qs[0], 5, 800);
     CHECK(hr.ok() && hr.value.size() == 5 && hr.value[0].first == truth.value[0][0].first);
     CHECK(std::fabs(hr.value[0].second - truth.value[0][0].second) <= 1e-5f * (1.0f + truth.value[0][0].second));
     auto hb = hasher.search_batched(qs, 5);

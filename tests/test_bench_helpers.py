@@ -61,3 +61,22 @@ def test_reference_arm_runs_without_the_product_library():
     assert line["impl"] == "reference" and line["metric"].startswith("queries/sec @ recall@10>=0.95")
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert "libscann_b200" not in r.stderr and "libscann_oracle" in r.stderr
+
+
+def test_ann_benchmark_recall_kat_and_flags():
+    """src/bin/ann_benchmark.rs:481-492 (recall_at_k_basic) and the CLI spellings (:22-33,63-73)"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ann_benchmark as ab
+
+    r = ab.average_recall_at_k([[1, 2, 3], [5, 7, 9]], [[1, 4, 3], [5, 6, 7]], 3)
+    assert abs(r - 2.0 / 3.0) < 1e-6
+    assert ab.average_recall_at_k([], [[1]], 3) == 0.0 and ab.average_recall_at_k([[1]], [[1]], 0) == 0.0
+    a = ab.parse(["--algorithm", "treeah", "--distance", "dot_product", "--k", "5", "--num-blocks", "16"])
+    assert (a.algorithm, a.distance, a.k, a.num_blocks, a.num_partitions, a.partitions_to_search) == \
+        ("tree_ah", "dot_product", 5, 16, 100, 10)
+    d = ab.parse([])
+    assert (d.algorithm, d.distance, d.synthetic_train, d.synthetic_test, d.dim, d.seed) == \
+        ("brute_force", "squared_l2", 10_000, 200, 64, 42)
+    train = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 2.0]], np.float32)
+    gt = ab.exact_ground_truth(train, np.array([[0.9, 0.1]], np.float32), 2)
+    assert gt[0].tolist() == [1, 0]
