@@ -672,4 +672,61 @@ class ScannBuilder {  // src/scann.rs:364-432
   ScannConfig cfg_;
 };
 
+// ------------------------------------------------------------------------------------------------
+// KMeansTree (src/trees/kmeans_tree.rs:154-395): hierarchical k-means partitioning; nodes are numbered in preorder.
+struct KMeansTreeConfig {  // :17-56
+  size_t num_children = 100;
+  size_t max_depth = 1;
+  size_t min_leaf_size = 1;
+  int kmeans_max_iterations = 20;
+  uint64_t seed = 42;
+};
+
+struct LeafHit {  // one element of search_leaves' Vec<(depth, distance, &node)> (:302-319)
+  uint32_t depth;
+  float distance;
+  uint32_t node;  // preorder node id of the leaf
+};
+
+class KMeansTree {
+ public:
+  explicit KMeansTree(KMeansTreeConfig cfg = {}) : cfg_(cfg) {}
+  KMeansTree(KMeansTree&& o) noexcept : cfg_(o.cfg_), h_(o.h_) { o.h_ = nullptr; }
+  KMeansTree(const KMeansTree&) = delete;
+  ~KMeansTree() { scann_kmtree_destroy(h_); }
+
+  // build(dataset) (:179-200); "Cannot build tree from empty dataset"
+  ScannError build(const float* data, size_t n, size_t dim, size_t stride, int device = 0) {
+    scann_kmtree_destroy(h_);
+    h_ = nullptr;
+    return make_error(scann_kmtree_build(data, n, dim, stride, cfg_.num_children, cfg_.max_depth, cfg_.min_leaf_size,
+                                         cfg_.kmeans_max_iterations, cfg_.seed, device, SCANN_HOST, &h_));
+  }
+  size_t num_leaves() const { return info(1); }  // :293-295
+  size_t size() const { return info(3); }        // :298-300
+  // search_leaves(query, k) (:302-319)
+  Result<std::vector<LeafHit>> search_leaves(const std::vector<float>& query, size_t k) const {
+    Result<std::vector<LeafHit>> r;
+    if (h_ == nullptr) return r;  // no root -> empty (:311-313)
+    std::vector<uint32_t> nodes(k ? k : 1), depths(k ? k : 1);
+    std::vector<float> dists(k ? k : 1);
+    uint32_t count = 0;
+    r.error = make_error(scann_kmtree_search_leaves(h_, query.data(), 1, query.size(), k, nodes.data(), dists.data(),
+                                                    depths.data(), &count, SCANN_HOST, nullptr));
+    if (r.ok())
+      for (uint32_t j = 0; j < count; ++j) r.value.push_back({depths[j], dists[j], nodes[j]});
+    return r;
+  }
+  scann_kmtree* handle() const { return h_; }
+
+ private:
+  size_t info(int which) const {
+    size_t v[5] = {0, 0, 0, 0, 0};
+    if (h_) scann_kmtree_info(h_, &v[0], &v[1], &v[2], &v[3], &v[4]);
+    return v[which];
+  }
+  KMeansTreeConfig cfg_;
+  scann_kmtree* h_ = nullptr;
+};
+
 }  // namespace scann

@@ -154,6 +154,26 @@ int main() {
     auto wbad = tx.search_batched_with_params(qs, params);
     CHECK(!wbad.ok() && wbad.error.code == ErrorCode::InvalidArgument);
   }
+  // ---- KMeansTree (src/trees/kmeans_tree.rs tests :425-441): build, size, sorted search_leaves ----
+  {
+    std::vector<float> pts;
+    const float cx[3] = {0.f, 10.f, 0.f}, cy[3] = {0.f, 10.f, 10.f};
+    for (int c = 0; c < 3; ++c)
+      for (int i = 0; i < 20; ++i) {
+        pts.push_back(cx[c] + i * 0.1f);
+        pts.push_back(cy[c] + i * 0.05f);
+      }
+    KMeansTreeConfig kc;
+    kc.num_children = 3;
+    KMeansTree tree(kc);
+    CHECK(tree.search_leaves({0.f, 0.f}, 2).ok() && tree.search_leaves({0.f, 0.f}, 2).value.empty());
+    CHECK(tree.build(pts.data(), 60, 2, 2).code == ErrorCode::Ok);
+    CHECK(tree.size() == 60 && tree.num_leaves() >= 1);
+    auto hits = tree.search_leaves({0.f, 0.f}, 2);
+    CHECK(hits.ok() && !hits.value.empty());
+    for (size_t i = 1; i < hits.value.size(); ++i) CHECK(hits.value[i].distance >= hits.value[i - 1].distance);
+    CHECK(tree.build(nullptr, 0, 2, 2).code == ErrorCode::InvalidArgument);
+  }
   std::puts("hpp mirror ok");
   return 0;
 }
