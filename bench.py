@@ -57,7 +57,7 @@ DEFAULTS = {
     "c1": dict(n=10_000, dim=128, nq=1_000, k=10),
     "c2": dict(n=1_000_000, dim=128, nq=10_000, k=10),
     "c3": dict(n=10_000_000, dim=96, partitions=2000, subspaces=48, leaves=64, reorder=100, k=10, nq=10_000,
-               latent=8192, spread=0.5, decay=1.0, balance=0.0),
+               latent=8192, spread=0.5, decay=1.0, balance=3.0),
     "c4": dict(n=100_000_000, dim=128, partitions=8192, subspaces=64, leaves=64, reorder=100, k=10, nq=10_000,
                latent=16384, spread=0.5, decay=1.0, sweep="32,64,128", train_rows=1_000_000, kmeans_iters=15,
                balance=3.0),
