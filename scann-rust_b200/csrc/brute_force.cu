@@ -501,6 +501,7 @@ struct BfCore {
       hcounts = ws.take<uint32_t>(chunk);
     }
     uint32_t* flag = reinterpret_cast<uint32_t*>(d_small.p + 1);
+    bool truncated = false;  // every chunk is finished before the truncation is reported: all outputs are written
     for (size_t q0 = 0; q0 < nq; q0 += chunk) {
       const size_t nqc = std::min(chunk, nq - q0);
       const float* qsrc = queries + q0 * dim;
@@ -543,10 +544,11 @@ struct BfCore {
         SCANN_CUDA(cudaMemcpyAsync(counts + q0, hcounts, nqc * 4, cudaMemcpyDeviceToHost, s));
       }
       SCANN_CUDA(cudaStreamSynchronize(s));
-      SCANN_REQUIRE(*h_flag == 0, SCANN_RESOURCE_EXHAUSTED,
-                    "more than max_results = %zu points lie within the radius for some query (results are truncated "
-                    "to the nearest ones)", max_results);
+      truncated = truncated || *h_flag != 0;
     }
+    SCANN_REQUIRE(!truncated, SCANN_RESOURCE_EXHAUSTED,
+                  "more than max_results = %zu points lie within the radius for some query (results are truncated "
+                  "to the nearest ones)", max_results);
     return SCANN_OK;
   }
 

@@ -285,7 +285,9 @@ scann_status launch_partition_tc(const PartTc& tc, const float* centers, size_t 
   sp.sms = sms;
   SCANN_TRY(launch_tc_scores(sp, s));
   const unsigned grid = static_cast<unsigned>((nq + kPtWarps - 1) / kPtWarps);
-  if (L <= 384) {
+  // survivors = L + the centres inside the 2*eps certification band; the band holds hundreds of centres when K is in
+  // the tens of thousands, and a list overflow means the slow exact pass over every centre (C5, L = 256: 45 ms per batch)
+  if (L <= 128 || (L <= 384 && K <= 16384)) {
     const size_t smem = part_tc_smem(512, dim);
     SCANN_CUDA(cudaFuncSetAttribute(part_tc_select_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(smem)));

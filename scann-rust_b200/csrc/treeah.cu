@@ -1081,6 +1081,7 @@ scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t n
     if (R == 0) {
       // (k as f32 * multiplier) as usize == 0: FastTopNeighbors(0) keeps nothing -> empty results
       SCANN_CUDA(cudaMemsetAsync(d_ids, 0xFF, nqc * k * 4, s));
+      SCANN_CUDA(cudaMemsetAsync(d_dists, 0x7F, nqc * k * 4, s));  // 0x7F7F7F7F = 3.39e38: padding, never uninitialised
       SCANN_CUDA(cudaMemsetAsync(d_counts, 0, nqc * 4, s));
       if (d_cc) SCANN_CUDA(cudaMemsetAsync(d_cc, 0, nqc * 4, s));
     } else {

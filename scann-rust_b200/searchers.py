@@ -209,13 +209,20 @@ class BruteForceSearcher(_Handle):
         ids, dists, counts = self.search_batched(np.asarray(query, np.float32)[None, :], k)
         return results_to_lists(ids, dists, counts)[0]
 
-    def search_radius_batched(self, queries, radius: float, max_results: int = 1024):
-        """search_radius (searcher.rs:142-167) for a batch → (ids [nq, max_results], dists, counts)."""
+    def search_radius_batched(self, queries, radius: float, max_results: int = 1024, allow_truncated: bool = False):
+        """search_radius (searcher.rs:142-167) for a batch → (ids [nq, max_results], dists, counts).  When more than
+        max_results rows lie inside the radius for some query the library still writes every query's nearest
+        max_results rows and reports RESOURCE_EXHAUSTED: raised here unless allow_truncated (then a warning)."""
         b = _Batch(queries, self.device)
         ids, dists, counts, pi, pd, pc = b.outputs(max_results)
         if b.nq:
-            capi.check(capi.load().scann_bf_search_radius(self._h, b.ptr, b.nq, b.dim, float(radius), max_results, pi, pd,
-                                                          pc, b.memspace, b.stream))
+            st = capi.load().scann_bf_search_radius(self._h, b.ptr, b.nq, b.dim, float(radius), max_results, pi, pd, pc,
+                                                    b.memspace, b.stream)
+            if st == capi.RESOURCE_EXHAUSTED and allow_truncated:
+                import warnings
+                warnings.warn("search_radius: results truncated to max_results for some query")
+            else:
+                capi.check(st)
         return ids, dists, counts
 
     def search_radius(self, query, radius: float, max_results: int = 1024):

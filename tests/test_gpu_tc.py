@@ -204,4 +204,7 @@ def test_bf_search_radius_reference_kat_and_truncation(gpu_lib):
     with pytest.raises(gpu_lib.ScannError) as e:
         bf.search_radius([0, 0, 0], 1.5, max_results=2)      # 4 rows qualify, only room for 2
     assert e.value.code == gpu_lib.capi.RESOURCE_EXHAUSTED
+    with pytest.warns(UserWarning):  # the truncated (nearest max_results) rows are still delivered
+        ti, td, tc = bf.search_radius_batched(np.array([[0, 0, 0]], np.float32), 1.5, max_results=2, allow_truncated=True)
+    assert tc[0] == 2 and (np.diff(td[0]) >= 0).all()
     assert bf.search_radius([9, 9, 9], 0.5) == []
