@@ -17,8 +17,11 @@
  *    SCANN_HOST calls, the legacy default stream for SCANN_DEVICE calls).
  *  - Result layout for all searchers: ids[nq*k] (u32, 0xFFFFFFFF padding), dists[nq*k] (f32, +inf
  *    padding), counts[nq] = number of valid results of each query (min(k, available)).
- *  - Handles are safe for concurrent `search` calls from several threads (calls on one handle
- *    serialise on an internal mutex around the shared workspace; tests/stress_tests.rs:256-297).
+ *  - Handles are safe for concurrent `search` calls from several threads (tests/stress_tests.rs:256-297): calls on one
+ *    handle serialise on an internal mutex while they enqueue, and their DEVICE work is ordered across streams by an
+ *    event each call records and the next one waits on — a SCANN_DEVICE call returns with its kernels only enqueued
+ *    and the handle's workspace is shared, so a following call on another stream starts after them.  For concurrency
+ *    between searches use one handle per stream (index arrays can be shared through SCANN_TREEAH_BORROW_RAW).
  *  - There is no CPU fallback: every entry point that computes needs a CUDA device and returns
  *    SCANN_UNAVAILABLE when none is usable.
  */
@@ -185,8 +188,9 @@ scann_status scann_treeah_set_reorder(scann_treeah* h, int enable);
  *       tau_in[q] cannot be among the global top-R of query q because R points at or below it exist — then merges
  *       and re-scores exactly as scann_treeah_search does.
  * The bounds are data-defined (not timing-defined), so results are deterministic and every shard's list is a
- * superset of the global top-R restricted to the shard.  Device pointers only; begin/end must be paired on one
- * thread (the handle stays locked in between); the batch must fit one chunk (nq*L*R*8 <= 1 GiB). */
+ * superset of the global top-R restricted to the shard.  Device pointers only.  Between begin and end the handle is
+ * BUSY, not locked: every other entry point answers SCANN_FAILED_PRECONDITION; a caller that cannot reach _end (e.g. its
+ * reduction failed) calls scann_treeah_search_abort.  The batch must fit one chunk (nq*L*R*8 <= 2 GiB). */
 /* `tokens` (device, nq*L u32, or NULL): the partition stage's output when the caller ran it — e.g. each shard
  * partitions nq/world queries with scann_treeah_partition and the shards all-gather the tokens, so the stage is
  * not repeated on every GPU.  The array must stay valid until scann_treeah_search_end returns.  L must be <= K. */
@@ -196,6 +200,7 @@ scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, si
                                        size_t R, size_t k, const uint32_t* tokens, float* tau_out, void* stream);
 scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint32_t* ids, float* dists,
                                      uint32_t* counts, void* stream);
+scann_status scann_treeah_search_abort(scann_treeah* h);
 /* introspection used by bench.py for the roofline arithmetic: algorithmic code bytes scanned by the
  * last scann_treeah_search call (Σ over (query, leaf) pairs of leaf_size * ceil(S/2)); host sync. */
 scann_status scann_treeah_last_scan_bytes(scann_treeah* h, uint64_t* bytes, uint64_t* pairs);

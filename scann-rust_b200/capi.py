@@ -35,7 +35,7 @@ SYMBOLS = [
     "scann_sq8_quantize", "scann_sq8_create", "scann_sq8_search", "scann_sq8_destroy",
     "scann_part_create", "scann_part_select", "scann_part_destroy", "scann_part_update",
     "scann_treeah_create", "scann_treeah_create_ex", "scann_treeah_search", "scann_treeah_destroy", "scann_treeah_last_scan_bytes",
-    "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end", "scann_treeah_partition",
+    "scann_treeah_set_profiling", "scann_treeah_get_profile", "scann_treeah_search_begin", "scann_treeah_search_end", "scann_treeah_search_abort", "scann_treeah_partition",
     "scann_treeah_set_filter", "scann_treeah_path_stats", "scann_treeah_tc_profile",
     "scann_lut16_build", "scann_lut16_scan", "scann_pq_encode", "scann_merge_topk", "scann_merge_topk_packed", "scann_tc_scores",
     "scann_ivf_create", "scann_ivf_search", "scann_ivf_destroy",
@@ -104,6 +104,7 @@ def load():
     L.scann_treeah_set_filter.argtypes = [vp, vp, sz, i32]
     L.scann_treeah_partition.argtypes = [vp, vp, sz, sz, sz, vp, vp]
     L.scann_treeah_search_end.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.scann_treeah_search_abort.argtypes = [vp]
     L.scann_treeah_path_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.scann_treeah_tc_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64),
                                           C.POINTER(C.c_uint64)]

@@ -275,6 +275,7 @@ struct BfCore {
   uint64_t stat_tc_chunks = 0, stat_legacy_chunks = 0;
   Workspace ws;
   std::mutex mu;
+  StreamOrder order;
   cudaStream_t stream = nullptr;
 
   scann_status init(const void* db, size_t n_, size_t dim_, size_t stride, int measure_, bool i8_, float scale_,
@@ -469,6 +470,7 @@ struct BfCore {
     DeviceGuard g(device);
     cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(user_stream)
                                                : (user_stream ? static_cast<cudaStream_t>(user_stream) : stream);
+    StreamOrderScope in_order(order, s);
     const bool host = memspace == SCANN_HOST;
     if (n == 0) {
       if (host) memset(counts, 0, nq * sizeof(uint32_t));
@@ -560,6 +562,7 @@ struct BfCore {
     DeviceGuard g(device);
     cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(user_stream)
                                                : (user_stream ? static_cast<cudaStream_t>(user_stream) : stream);
+    StreamOrderScope in_order(order, s);
     const bool host = memspace == SCANN_HOST;
     if (n == 0) {  // empty dataset -> Ok(vec![]) (searcher.rs:78-80) before any dimension check
       if (host) memset(counts, 0, nq * sizeof(uint32_t));

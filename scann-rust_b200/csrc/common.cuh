@@ -51,6 +51,29 @@ struct DeviceGuard {
 
 scann_status check_device(int device);
 
+// Orders the device work of successive calls on one handle ACROSS STREAMS.  A handle's workspace is shared by its calls
+// and a SCANN_DEVICE call returns with its kernels only enqueued, so the next call — possibly on another stream — must
+// not start before they have finished: every call waits on the event the previous one recorded.
+struct StreamOrder {
+  cudaEvent_t done = nullptr;
+  void enter(cudaStream_t s) {
+    if (done) cudaStreamWaitEvent(s, done, 0);
+  }
+  void leave(cudaStream_t s) {
+    if (!done && cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) done = nullptr;
+    if (done) cudaEventRecord(done, s);
+  }
+  ~StreamOrder() {
+    if (done) cudaEventDestroy(done);
+  }
+};
+struct StreamOrderScope {
+  StreamOrder& o;
+  cudaStream_t s;
+  StreamOrderScope(StreamOrder& o_, cudaStream_t s_) : o(o_), s(s_) { o.enter(s); }
+  ~StreamOrderScope() { o.leave(s); }
+};
+
 // grow-only device arena; one per handle, guarded by the handle's mutex
 struct Workspace {
   char* base = nullptr;

@@ -226,6 +226,7 @@ struct scann_ivf {
   scann::PartTc ptc;
   scann::Workspace ws;
   std::mutex mu;
+  scann::StreamOrder order;
   cudaStream_t stream = nullptr;
   int sms = 148;
 };
@@ -353,6 +354,7 @@ scann_status scann_ivf_search(scann_ivf* h, int mode, const float* queries, size
   DeviceGuard g(h->device);
   cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(stream)
                                              : (stream ? static_cast<cudaStream_t>(stream) : h->stream);
+  StreamOrderScope in_order(h->order, s);
   const bool host = memspace == SCANN_HOST;
   const size_t K = h->K;
   if (L > K) L = K;

@@ -209,6 +209,7 @@ struct scann_kmtree {
   std::vector<uint32_t> h_depth, h_child_begin, h_child_count, h_children, h_leaf_begin, h_leaf_count, h_leaf_points;
   scann::Workspace ws;
   std::mutex mu;
+  scann::StreamOrder order;
   cudaStream_t stream = nullptr;
 };
 
@@ -449,6 +450,7 @@ scann_status scann_kmtree_search_leaves(scann_kmtree* h, const float* queries, s
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(stream) : h->stream;
+  StreamOrderScope in_order(h->order, s);
   const bool host = memspace == SCANN_HOST;
   const size_t kk = std::max<size_t>(k, 1);
   const size_t per_q = static_cast<size_t>(h->levels) * h->max_children * 8;

@@ -365,6 +365,7 @@ struct scann_part {
   int sms = 148;
   scann::Workspace ws;
   std::mutex mu;
+  scann::StreamOrder order;
   cudaStream_t stream = nullptr;
 };
 
@@ -446,6 +447,7 @@ scann_status scann_part_select(scann_part* h, const float* queries, size_t nq, s
   DeviceGuard g(h->device);
   cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(stream)
                                              : (stream ? static_cast<cudaStream_t>(stream) : h->stream);
+  StreamOrderScope in_order(h->order, s);
   // bounded scratch: process the batch in chunks of queries
   size_t chunk = (size_t(2) << 30) / (h->K * sizeof(float));  // dense score scratch: 2 GiB keeps >= 8192 rows per pass at K = 65,536
   if (chunk < 1) chunk = 1;

@@ -461,6 +461,7 @@ struct scann_treeah {
   scann::PartTc ptc;                        // tensor-core centroid scoring operands (partition.cu)
   scann::Workspace ws;
   std::mutex mu;
+  scann::StreamOrder order;  // device work of successive calls, across streams
   cudaStream_t stream = nullptr;
   int sms = 148;
   // the chunk being searched, between its two phases (treeah_phase1 / treeah_phase2)
@@ -479,7 +480,7 @@ struct scann_treeah {
     int T = 1;  // ranks in class A of the worklist
     scann::ScanArgs a;
   } ck;
-  bool split_active = false;  // between scann_treeah_search_begin and _end (mu stays locked)
+  bool split_active = false;  // between scann_treeah_search_begin and _end / _abort: other entry points are refused
   // optional live profiling: (stage, start, end) CUDA-event spans; stages 0 partition, 1 worklist, 2 scan, 3 merge
   bool profiling = false;
   struct Span {
@@ -1049,6 +1050,7 @@ scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t n
   DeviceGuard g(h->device);
   cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(stream)
                                              : (stream ? static_cast<cudaStream_t>(stream) : h->stream);
+  StreamOrderScope in_order(h->order, s);
   if (L > h->K) L = h->K;  // partition() returns min(L, K) tokens (tree_partitioner.rs:214)
   const size_t Reff = R < 1 ? 1 : R;  // R == 0 (k*multiplier < 1) -> no candidates
   // chunk the batch so that the candidate buffer stays <= 1 GiB and the centre-distance scratch <= 512 MiB
@@ -1129,8 +1131,10 @@ scann_status scann_treeah_partition(scann_treeah* h, const float* queries, size_
   SCANN_REQUIRE(L >= 1 && L <= 1024, SCANN_INVALID_ARGUMENT, "partitions_to_search %zu outside 1..1024", L);
   SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "a split search is in flight on this handle");
   std::lock_guard<std::mutex> lock(h->mu);
+  SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "a split search is in flight on this handle");
   DeviceGuard g(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  StreamOrderScope in_order(h->order, s);
   const size_t K = h->K;
   const size_t Leff = std::min(L, K);
   SCANN_REQUIRE(Leff == L, SCANN_INVALID_ARGUMENT, "partitions_to_search %zu > %zu partitions", L, K);
@@ -1156,20 +1160,30 @@ scann_status scann_treeah_search_begin(scann_treeah* h, const float* queries, si
   if (L > h->K) L = h->K;
   SCANN_REQUIRE(nq * L * R * 8 <= (size_t(2) << 30) && (tokens != nullptr || nq * h->K * 4 <= (size_t(512) << 20)),
                 SCANN_INVALID_ARGUMENT, "batch of %zu queries is too large for the split search (split it)", nq);
-  h->mu.lock();
+  std::lock_guard<std::mutex> lock(h->mu);
+  SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "scann_treeah_search_begin called twice without _end");
   DeviceGuard g(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  h->order.enter(s);
   scann_status st = h->ws.reserve(treeah_chunk_bytes(h, nq, L, R, k, false, tokens != nullptr));
   if (st == SCANN_OK) {
     cudaMemsetAsync(h->stats.p, 0, 4 * sizeof(unsigned long long), s);
     h->ws.reset();
     st = treeah_phase1(h, queries, nq, L, R, k, true, tau_out, tokens, s);
   }
-  if (st != SCANN_OK) {
-    h->mu.unlock();
-    return st;
-  }
-  h->split_active = true;  // mu stays locked until _end
+  h->order.leave(s);
+  if (st != SCANN_OK) return st;
+  // The handle is marked busy, not locked: every other entry point answers FAILED_PRECONDITION until _end (or _abort),
+  // so nothing can be left locked by a caller that fails between the two calls.
+  h->split_active = true;
+  return SCANN_OK;
+}
+
+scann_status scann_treeah_search_abort(scann_treeah* h) {
+  using namespace scann;
+  SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->split_active = false;
   return SCANN_OK;
 }
 
@@ -1177,6 +1191,7 @@ scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint3
                                      uint32_t* counts, void* stream) {
   using namespace scann;
   SCANN_REQUIRE(h != nullptr, SCANN_FAILED_PRECONDITION, "searcher not built");
+  std::lock_guard<std::mutex> lock(h->mu);
   SCANN_REQUIRE(h->split_active, SCANN_FAILED_PRECONDITION, "scann_treeah_search_end without _begin");
   scann_status st = SCANN_OK;
   if (!(ids && dists && counts)) {
@@ -1184,10 +1199,11 @@ scann_status scann_treeah_search_end(scann_treeah* h, const float* tau_in, uint3
     st = SCANN_INVALID_ARGUMENT;
   } else {
     DeviceGuard g(h->device);
-    st = treeah_phase2(h, true, tau_in, ids, dists, counts, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    StreamOrderScope in_order(h->order, s);
+    st = treeah_phase2(h, true, tau_in, ids, dists, counts, nullptr, nullptr, nullptr, s);
   }
   h->split_active = false;
-  h->mu.unlock();
   return st;
 }
 

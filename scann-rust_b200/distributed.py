@@ -84,7 +84,12 @@ def two_phase_search(searcher, queries, k: int, group=None, partitions_to_search
     mark()
     tau = searcher.search_begin(queries, k, partitions_to_search, pre_reorder_k, tokens=tokens)
     mark()
-    dist.all_reduce(tau, op=dist.ReduceOp.MIN, group=group)
+    try:
+        dist.all_reduce(tau, op=dist.ReduceOp.MIN, group=group)
+    except Exception:
+        if hasattr(searcher, "search_abort"):
+            searcher.search_abort()  # the handle is busy between begin and end: give it back
+        raise
     mark()
     out = searcher.search_end(tau)
     mark()

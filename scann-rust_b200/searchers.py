@@ -653,9 +653,17 @@ class TreeXHybridSearcher(_Handle):
         b, k, _tokens = self._split
         ids, dists, counts, pi, pd, pc = b.outputs(k)
         pt = C.c_void_p(tau.data_ptr()) if tau is not None else None
-        capi.check(capi.load().scann_treeah_search_end(self._h, pt, pi, pd, pc, b.stream))
-        self._split = None
+        try:
+            capi.check(capi.load().scann_treeah_search_end(self._h, pt, pi, pd, pc, b.stream))
+        finally:
+            self._split = None
         return ids, dists, counts
+
+    def search_abort(self):
+        """Gives the handle back after a search_begin whose search_end will not be called (scann_treeah_search_abort)."""
+        if self._h and self._h.value:
+            capi.check(capi.load().scann_treeah_search_abort(self._h))
+        self._split = None
 
     def set_profiling(self, enable: bool):
         capi.check(capi.load().scann_treeah_set_profiling(self._h, int(enable)))

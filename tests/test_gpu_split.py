@@ -126,3 +126,56 @@ def test_two_phase_sharded_search_is_deterministic_superset(gpu_lib, oracle, wor
     assert (pd.cpu().numpy() <= fdn).all()
     rc, gt, _, _ = oracle.bf_search(x, qn, k, oracle.SQL2, nthreads=8)
     assert helpers.recall(mi, gt, k) >= helpers.recall(fi.cpu().numpy().view(np.uint32), gt, k) - 1e-9
+
+
+def test_split_search_abort_and_cross_thread_end(gpu_lib, oracle):
+    """Between begin and end the handle is busy, not locked: a plain search is refused, abort gives the handle back,
+    and end may run on another thread than begin (a held std::mutex would make that undefined behaviour)."""
+    import threading
+
+    x, idx = _index(oracle, n=5000, K=8, S=8)
+    s = _searcher(gpu_lib, idx, x, 4)
+    q = torch.tensor(x[:16]).cuda()
+    ref = s.search_batched(q, 5)
+    torch.cuda.synchronize()
+    s.search_begin(q, 5)
+    with pytest.raises(gpu_lib.ScannError) as e:
+        s.search_batched(q, 5)
+    assert e.value.code == gpu_lib.capi.FAILED_PRECONDITION
+    s.search_abort()
+    again = s.search_batched(q, 5)          # usable again
+    torch.cuda.synchronize()
+    assert (again[0] == ref[0]).all()
+    tau = s.search_begin(q, 5)
+    out = {}
+
+    def finish():
+        torch.cuda.set_device(0)
+        out["r"] = s.search_end(tau)
+        torch.cuda.synchronize()
+
+    t = threading.Thread(target=finish)
+    t.start()
+    t.join()
+    assert (out["r"][0] == ref[0]).all() and (out["r"][1] == ref[1]).all()
+
+
+def test_device_calls_on_two_streams_are_ordered(gpu_lib, oracle):
+    """SCANN_DEVICE calls return with their kernels enqueued; the handle's workspace is shared, so a call on another
+    stream must start after them (StreamOrder event).  Alternate two streams without any host synchronisation."""
+    x, idx = _index(oracle, n=20000, K=16, S=8)
+    s = _searcher(gpu_lib, idx, x, 6)
+    qa = torch.tensor(x[:512]).cuda()
+    qb = torch.tensor(x[512:1024]).cuda()
+    ra = s.search_batched(qa, 10)
+    rb = s.search_batched(qb, 10)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for it in range(6):
+        with torch.cuda.stream(s1 if it % 2 == 0 else s2):
+            outs.append(s.search_batched(qa if it % 2 == 0 else qb, 10))
+    torch.cuda.synchronize()
+    for it, o in enumerate(outs):
+        want = ra if it % 2 == 0 else rb
+        assert (o[0] == want[0]).all() and (o[1] == want[1]).all()
