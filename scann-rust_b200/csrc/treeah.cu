@@ -1047,6 +1047,7 @@ scann_status scann_treeah_search(scann_treeah* h, const float* queries, size_t n
   SCANN_REQUIRE((cand_ids == nullptr) == (cand_dists == nullptr), SCANN_INVALID_ARGUMENT,
                 "cand_ids and cand_dists go together");
   std::lock_guard<std::mutex> lock(h->mu);
+  SCANN_REQUIRE(!h->split_active, SCANN_FAILED_PRECONDITION, "a split search is in flight on this handle");
   DeviceGuard g(h->device);
   cudaStream_t s = memspace == SCANN_DEVICE ? static_cast<cudaStream_t>(stream)
                                              : (stream ? static_cast<cudaStream_t>(stream) : h->stream);
