@@ -92,6 +92,10 @@ def parse():
     p.add_argument("--emulate-shard", type=int, default=0,
                    help="single-GPU tuning aid: build and search only shard 0 of N (not a bench mode)")
     p.add_argument("--phase-times", action="store_true", help="multi-GPU: log the per-phase device times of the step")
+    p.add_argument("--prefetch", action="store_true",
+                   help="multi-GPU: prefetch the next batch's partition slice + token all-gather on a side stream "
+                        "(distributed.TokenPrefetcher; measured: no gain at N=2, the persistent scan kernels leave no "
+                        "SM for the side stream, the time moves into the result exchange)")
     p.add_argument("--split", action="store_true",
                    help="single-GPU tuning aid: use the two-phase search_begin/search_end path (no reduction)")
     p.add_argument("--sweep-leaves", default="", help="c3: comma list: print recall/QPS for each L (stderr) and exit")
@@ -958,9 +962,14 @@ def bench_c3(a, emit, torch, dist, pkg, dev, rank, world, local_rank):
     R = a.reorder
     xchg_events = []  # (start, end) CUDA events around the all-gather + merge of the timed steps
 
-    def step_device(qb, timed=False):
+    # --prefetch: the partition slice + token all-gather of the NEXT batch run on a side stream while the current batch is
+    # scanned (every step still does all of its own work: the tokens of step i+1 are computed during step i)
+    prefetcher = pkg.distributed.TokenPrefetcher(searcher, centers, a.leaves) if world > 1 and a.prefetch else None
+
+    def step_device(qb, timed=False, nxt=None):
         if world > 1:
-            ids, dists, cnt = pkg.distributed.two_phase_search(searcher, qb, a.k, pre_reorder_k=R)
+            ids, dists, cnt = pkg.distributed.two_phase_search(searcher, qb, a.k, pre_reorder_k=R, prefetcher=prefetcher,
+                                                               next_queries=nxt)
         elif a.split:
             ids, dists, cnt = searcher.search_end(searcher.search_begin(qb, a.k, pre_reorder_k=R))
         else:
@@ -1032,7 +1041,7 @@ def bench_c3(a, emit, torch, dist, pkg, dev, rank, world, local_rank):
 
     # ---------------- timed: device-resident ----------------
     for w in range(a.warmup):
-        step_device(queries[w % n_batches])
+        step_device(queries[w % n_batches], nxt=queries[(w + 1) % n_batches] if w + 1 < a.warmup else queries[0])
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -1044,7 +1053,7 @@ def bench_c3(a, emit, torch, dist, pkg, dev, rank, world, local_rank):
     barrier()
     e0.record()
     for s in range(a.steps):
-        step_device(queries[s % n_batches], timed=True)
+        step_device(queries[s % n_batches], timed=True, nxt=queries[(s + 1) % n_batches])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)

@@ -179,3 +179,37 @@ def test_device_calls_on_two_streams_are_ordered(gpu_lib, oracle):
     for it, o in enumerate(outs):
         want = ra if it % 2 == 0 else rb
         assert (o[0] == want[0]).all() and (o[1] == want[1]).all()
+
+
+def test_token_prefetcher_pipeline_gives_identical_results(gpu_lib, oracle, tmp_path):
+    """distributed.TokenPrefetcher: the partition slice + token all-gather of the next batch run on a side stream; the
+    results of a stream of batches must equal the un-pipelined two_phase_search (world of one NCCL rank)."""
+    import torch.distributed as dist
+
+    x, idx = _index(oracle, n=20000, K=16, S=8)
+    s = _searcher(gpu_lib, idx, x, 6)
+    batches = [torch.tensor(x[i * 256:(i + 1) * 256] + 0.01).cuda() for i in range(4)]
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        D = gpu_lib.distributed
+        plain = [D.two_phase_search(s, b, 10, pre_reorder_k=60) for b in batches]
+        torch.cuda.synchronize()
+        pf = D.TokenPrefetcher(s, idx["centers"], 6)
+        pf.prefetch(batches[0])
+        piped = []
+        for i, b in enumerate(batches):
+            piped.append(D.two_phase_search(s, b, 10, pre_reorder_k=60, prefetcher=pf,
+                                            next_queries=batches[i + 1] if i + 1 < len(batches) else None))
+        torch.cuda.synchronize()
+        for a, b in zip(plain, piped):
+            assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+        # a batch that was not prefetched falls back to the inline partition
+        other = D.two_phase_search(s, batches[2], 10, pre_reorder_k=60, prefetcher=pf)
+        torch.cuda.synchronize()
+        assert (other[0] == plain[2][0]).all()
+        pf.close()
+    finally:
+        if created:
+            dist.destroy_process_group()
