@@ -223,7 +223,7 @@ __device__ __forceinline__ int score_bound_from_tau(float tau, float mult, float
 __global__ void tcwl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, uint32_t K, uint32_t L, uint32_t T,
                                   const uint64_t* __restrict__ pt_off, uint32_t* __restrict__ leaf_cnt) {
   const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P || p % L < T) return;
+  if (p >= P || static_cast<uint32_t>(p) % L < T) return;  // 32-bit: see wl_virtual_leaf (treeah.cu)
   const uint32_t leaf = tokens[p];
   if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[leaf], 1u);
 }
@@ -301,7 +301,7 @@ __global__ void tcwl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t 
                                     const uint64_t* __restrict__ pt_off, const uint32_t* __restrict__ pair_start,
                                     uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted_pairs) {
   const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= P || p % L < T) return;
+  if (p >= P || static_cast<uint32_t>(p) % L < T) return;  // 32-bit: see wl_virtual_leaf (treeah.cu)
   const uint32_t leaf = tokens[p];
   if (leaf < K && pt_off[leaf + 1] > pt_off[leaf])
     sorted_pairs[pair_start[leaf] + atomicAdd(&cursor[leaf], 1u)] = static_cast<uint32_t>(p);
@@ -777,10 +777,11 @@ __global__ void tcs_flag_kernel(const uint32_t* __restrict__ tokens, size_t P, u
                                 uint32_t* __restrict__ fb_tokens) {
   const size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  const uint32_t q = static_cast<uint32_t>(p / L);
+  const uint32_t p32 = static_cast<uint32_t>(p);
+  const uint32_t q = p32 / L, rank = p32 - q * L;
   const bool f = qflag[q] != 0u || qcnt[q] > qcap;
-  fb_tokens[p] = (f && p % L >= T) ? tokens[p] : kNoKey;  // ranks < T were scanned before the tensor-core pass
-  if (f && p % L == 0) qflag[q] = 1u;
+  fb_tokens[p] = (f && rank >= T) ? tokens[p] : kNoKey;  // ranks < T were scanned before the tensor-core pass
+  if (f && rank == 0) qflag[q] = 1u;
 }
 
 // SCANN_TC_DEBUG=1: per-launch stage times and list statistics on stderr (synchronises; tuning only)
