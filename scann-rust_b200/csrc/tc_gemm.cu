@@ -314,6 +314,39 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(kTEmpty + as));
             }
+            if (a.filter) {
+              // Dot FILTER fast path: v = -acc, so "v <= thr" is "acc >= -thr" — the test runs on the raw accumulators
+              // (max tree, no negation: 32 instructions fewer per 32 scores in an epilogue-bound kernel); only a hit
+              // materialises v for its list entry
+              const float nthr = -thr;
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                float m = __uint_as_float(vr[8 * g8]);
+#pragma unroll
+                for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(vr[8 * g8 + j]));
+                const bool hit = m >= nthr;
+                if (__any_sync(0xFFFFFFFFu, hit)) {  // warp-uniform: the queue room check and flush are collective
+#pragma unroll
+                  for (int h4 = 0; h4 < 2; ++h4) {
+                    if (*wq_cnt > kWqCap - kWqStep) flush();
+                    if (hit) {
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) {
+                        const float acc = __uint_as_float(vr[8 * g8 + 4 * h4 + j]);
+                        if (acc >= nthr) {
+                          const uint32_t sl = atomicAdd(const_cast<uint32_t*>(wq_cnt), 1u);
+                          wq_rows[sl] = (static_cast<unsigned long long>(f32_key(-acc)) << 32) |
+                                        (row_tile + cc + 8 * g8 + 4 * h4 + j);
+                          wq_lanes[sl] = static_cast<uint8_t>(lane);
+                        }
+                      }
+                    }
+                    __syncwarp();
+                  }
+                }
+              }
+              continue;
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = -__uint_as_float(vr[j]);
           } else {
