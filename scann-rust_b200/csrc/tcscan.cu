@@ -853,25 +853,37 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   if (dbg)
     for (auto& e : ev) cudaEventCreate(&e);
   if (dbg) cudaEventRecord(ev[0], s);
-  SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 2 * K * 4, s));
   SCANN_CUDA(cudaMemsetAsync(qcnt, 0, p.nq * 4, s));
   SCANN_CUDA(cudaMemsetAsync(qflag, 0, p.nq * 4, s));
   const unsigned pb = static_cast<unsigned>((P + 255) / 256);
-  tcwl_count_kernel<<<pb, 256, 0, s>>>(p.tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(p.L),
-                                       static_cast<uint32_t>(p.T), p.pt_off, leaf_cnt);
-  tcwl_scan_kernel<<<1, 1024, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), p.leaf_perm, p.pt_off, pair_start, group_start,
+  // The count and scatter passes are atomics on 4-byte counters (8 per 32-byte sector: ~1300 serialised updates per
+  // sector at C3, 0.09 ms each).  The caller's worklist has usually grouped the same pairs already (class B of
+  // treeah.cu's build_worklist): then only the group / item tables are built here.
+  const bool reuse = p.wl_cnt != nullptr && p.wl_pair_start != nullptr && p.wl_sorted_pairs != nullptr;
+  const uint32_t* cnt_in = leaf_cnt;
+  const uint32_t* pairs_in = sorted_pairs;
+  if (reuse) {
+    cnt_in = p.wl_cnt;
+    pairs_in = p.wl_sorted_pairs;
+  } else {
+    SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 2 * K * 4, s));
+    tcwl_count_kernel<<<pb, 256, 0, s>>>(p.tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(p.L),
+                                         static_cast<uint32_t>(p.T), p.pt_off, leaf_cnt);
+  }
+  tcwl_scan_kernel<<<1, 1024, 0, s>>>(cnt_in, static_cast<uint32_t>(K), p.leaf_perm, p.pt_off, pair_start, group_start,
                                       item_start, counters, p.pair_points);
-  tcwl_scatter_kernel<<<pb, 256, 0, s>>>(p.tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(p.L),
-                                         static_cast<uint32_t>(p.T), p.pt_off, pair_start, cursor, sorted_pairs);
-  tcwl_items_kernel<<<static_cast<unsigned>((K + 127) / 128), 128, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), p.pt_off,
-                                                                          pair_start, group_start, item_start, groups,
-                                                                          items);
+  if (!reuse)
+    tcwl_scatter_kernel<<<pb, 256, 0, s>>>(p.tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(p.L),
+                                           static_cast<uint32_t>(p.T), p.pt_off, pair_start, cursor, sorted_pairs);
+  tcwl_items_kernel<<<static_cast<unsigned>((K + 127) / 128), 128, 0, s>>>(cnt_in, static_cast<uint32_t>(K), p.pt_off,
+                                                                          reuse ? p.wl_pair_start : pair_start,
+                                                                          group_start, item_start, groups, items);
   if (dbg) cudaEventRecord(ev[1], s);
   if (p.ev[0]) cudaEventRecord(p.ev[0], s);
   LutArgs la;
   la.groups = groups;
   la.counters = counters;
-  la.sorted_pairs = sorted_pairs;
+  la.sorted_pairs = pairs_in;
   la.queries = p.queries;
   la.centers = p.centers;
   la.codebook = p.codebook;
@@ -974,7 +986,7 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   out->qcnt = qcnt;
   out->qflag = qflag;
   out->fb_tokens = fb_tokens;
-  out->launches = 7;
+  out->launches = reuse ? 5 : 7;  // kernels of this function (memsets are not counted)
   return SCANN_OK;
 }
 

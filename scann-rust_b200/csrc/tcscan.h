@@ -26,6 +26,11 @@ struct TcScanParams {
   int sms;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // optional: recorded before the LUT kernel, before and after the scan
   unsigned long long* pair_points = nullptr;        // optional: += Σ over scanned (pair, leaf) of leaf size
+  // optional: the per-leaf lists of the pairs of rank >= T that the caller's own worklist has already built
+  // (treeah.cu build_worklist counts and scatters them as class B): saves this scan its count + scatter passes
+  const uint32_t* wl_cnt = nullptr;          // [K] pairs of rank >= T per leaf
+  const uint32_t* wl_pair_start = nullptr;   // [K] first entry of the leaf's list in wl_sorted_pairs
+  const uint32_t* wl_sorted_pairs = nullptr; // pair indices (q * L + rank), grouped by leaf
 };
 
 struct TcScanOut {

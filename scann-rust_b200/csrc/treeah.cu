@@ -784,6 +784,10 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
     tp.qcap = tc_qcap(R);
     tp.sms = h->sms;
     tp.pair_points = h->stats.p + 2;
+    // class B of the chunk's worklist (pairs of rank >= T, grouped by leaf) is exactly what the tensor-core scan groups
+    tp.wl_cnt = h->ck.leaf_cnt + K;
+    tp.wl_pair_start = h->ck.pair_start + K;
+    tp.wl_sorted_pairs = h->ck.sorted_pairs;
     if (h->profiling) {
       scann_treeah::TcSpan sp{{nullptr, nullptr, nullptr}};
       bool ok = true;
