@@ -70,6 +70,8 @@ __global__ void repack_blocked_kernel(const uint8_t* __restrict__ packed, const 
 // tau_q is in place before the bulk of the work starts — and on a sharded index the class-A bounds of all shards can
 // be min-reduced between the two phases (scann_treeah_search_begin / _end).  A "virtual leaf" v = leaf + K * class.
 // T = ranks in class A: 1 (the closest leaf) normally; the T closest leaves when the tensor-core scan takes the rest
+constexpr uint32_t kWlPad = 8;  // words between two atomic counters of the worklist passes (one per 32-byte sector)
+
 __device__ __forceinline__ uint32_t wl_virtual_leaf(uint32_t leaf, size_t p, uint32_t L, uint32_t K, uint32_t T) {
   // pairs of one chunk fit 32 bits (nq * L * R * 8 <= 2 GiB): a 64-bit modulo costs ~150 instructions per pair and made the
   // count / scatter kernels 0.09 ms each at 640k pairs
@@ -81,7 +83,14 @@ __global__ void wl_count_kernel(const uint32_t* __restrict__ tokens, size_t P, u
   size_t p = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= P) return;
   uint32_t leaf = tokens[p];
-  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[wl_virtual_leaf(leaf, p, L, K, T)], 1u);
+  // one counter per 32-byte sector (kWlPad words apart): the L2 serialises atomics on a sector, and 8 packed counters
+  // meant ~1300 serialised updates per sector at C3 (0.09 ms for 640k pairs)
+  if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) atomicAdd(&leaf_cnt[wl_virtual_leaf(leaf, p, L, K, T) * kWlPad], 1u);
+}
+
+__global__ void wl_unpad_kernel(const uint32_t* __restrict__ padded, uint32_t n, uint32_t* __restrict__ dense) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) dense[v] = padded[static_cast<size_t>(v) * kWlPad];
 }
 
 // Exclusive scans of pair counts and item counts over the 2K virtual leaves (three small kernels so that K = 65,536
@@ -234,7 +243,7 @@ __global__ void wl_scatter_kernel(const uint32_t* __restrict__ tokens, size_t P,
   uint32_t leaf = tokens[p];
   if (leaf < K && pt_off[leaf + 1] > pt_off[leaf]) {
     const uint32_t v = wl_virtual_leaf(leaf, p, L, K, T);
-    uint32_t slot = atomicAdd(&cursor[v], 1u);
+    uint32_t slot = atomicAdd(&cursor[static_cast<size_t>(v) * kWlPad], 1u);
     sorted_pairs[pair_start[v] + slot] = static_cast<uint32_t>(p);
   }
 }
@@ -579,14 +588,16 @@ static scann_status treeah_worklist(scann_treeah* h, const uint32_t* tokens, siz
   const int G = h->ck.G;
   const uint32_t T = static_cast<uint32_t>(h->ck.T);
   const bool with_stats = first;
-  uint32_t* leaf_cnt = h->ck.leaf_cnt;
-  uint32_t* cursor = leaf_cnt + 2 * K;
-  SCANN_CUDA(cudaMemsetAsync(leaf_cnt, 0, 4 * K * sizeof(uint32_t), s));
+  uint32_t* leaf_cnt = h->ck.leaf_cnt;                 // [2K] dense counts, then two padded arrays of 2K counters
+  uint32_t* pad_cnt = leaf_cnt + 2 * K;                // [2K * kWlPad] counters of the count pass
+  uint32_t* cursor = pad_cnt + 2 * K * kWlPad;         // [2K * kWlPad] cursors of the scatter pass
+  SCANN_CUDA(cudaMemsetAsync(pad_cnt, 0, 4 * K * kWlPad * sizeof(uint32_t), s));
   // the rebuilt worklist (flagged queries after a tensor-core scan) keeps the per-pair lists of the class-A ranks
   if (first) SCANN_CUDA(cudaMemsetAsync(h->ck.cand_cnt, 0, P * sizeof(uint32_t), s));
   unsigned pb = static_cast<unsigned>((P + 255) / 256);
   wl_count_kernel<<<pb, 256, 0, s>>>(tokens, P, static_cast<uint32_t>(K), static_cast<uint32_t>(L), T, h->pt_off.p,
-                                     leaf_cnt);
+                                     pad_cnt);
+  wl_unpad_kernel<<<static_cast<unsigned>((2 * K + 255) / 256), 256, 0, s>>>(pad_cnt, static_cast<uint32_t>(2 * K), leaf_cnt);
   const uint32_t nwb = static_cast<uint32_t>((2 * K + kWlBlock - 1) / kWlBlock), bpp32 = static_cast<uint32_t>((h->S + 1) / 2);
   wl_reduce_kernel<<<nwb, kWlBlock, 0, s>>>(leaf_cnt, static_cast<uint32_t>(K), G, h->leaf_perm.p, h->pt_off.p, bpp32,
                                             h->ck.wl_blk_pair, h->ck.wl_blk_item, h->ck.wl_blk_bytes);
@@ -643,7 +654,7 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
                                    nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0))));
   uint32_t* tokens = h->ws.take<uint32_t>(P);
   if (tokens_in) tokens = const_cast<uint32_t*>(tokens_in);  // the caller partitioned (and keeps the array alive)
-  uint32_t* leaf_cnt = h->ws.take<uint32_t>(4 * K);  // counts + cursors of the 2K virtual leaves
+  uint32_t* leaf_cnt = h->ws.take<uint32_t>(2 * K + 4 * K * kWlPad);  // counts of the 2K virtual leaves + padded counters / cursors
   uint32_t* pair_start = h->ws.take<uint32_t>(2 * K + 1);
   uint32_t* item_start = h->ws.take<uint32_t>(2 * K + 1);
   uint32_t* counters = h->ws.take<uint32_t>(4);
@@ -724,7 +735,7 @@ static scann_status treeah_phase1(scann_treeah* h, const float* dq, size_t nq, s
   h->ck.cand = cand;
   h->ck.cand_cnt = cand_cnt;
   h->ck.qthr = qthr;
-  h->prof_launches += (tokens_in ? 0 : (h->ptc.ready ? 3 : 2)) + 6;  // partition (2 or 3 kernels) + 6 worklist kernels
+  h->prof_launches += (tokens_in ? 0 : (h->ptc.ready ? 3 : 2)) + 7;  // partition (2 or 3 kernels) + 7 worklist kernels
   if (two_phase) {
     // 3a. probe of the class-A items: the first probe_blocks() blocks of every query's closest leaf prove a bound in
     // bounded time (a full scan of the largest leaves would serialise on a few CTAs); phase 2 scans them in full
@@ -799,7 +810,7 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
     }
     SCANN_TRY(launch_tc_scan(tp, h->ws, &tco, s));
     SCANN_TRY(treeah_worklist(h, tco.fb_tokens, nq, L, false, s));
-    h->prof_launches += tco.launches + 6;
+    h->prof_launches += tco.launches + 7;
   }
   a.end_idx = 0;
   a.max_blocks = 0;
@@ -861,7 +872,7 @@ static size_t treeah_chunk_bytes(const scann_treeah* h, size_t nq, size_t L, siz
   auto add = [&](size_t bytes) { b += Workspace::padded(bytes); };
   if (!have_tokens) add(std::max(nq * K * 4, h->ptc.ready ? part_tc_scratch_bytes(K, h->dim, nq) : size_t(0)));
   add(P * 4);
-  add(4 * K * 4);
+  add((2 * K + 4 * K * kWlPad) * 4);
   add((2 * K + 1) * 4);
   add((2 * K + 1) * 4);
   add(16);
