@@ -355,22 +355,21 @@ __device__ __forceinline__ uint32_t lut16_quantize_nonneg(float v, float mn, flo
   return min(i, 255u);
 }
 
+// The row loop is bound by the latency of its dependent global loads (group -> pair -> query / centre rows: ~2 us per row
+// against ~0.9 us of arithmetic), i.e. by the number of resident warps.  The codewords therefore live in shared memory
+// (a lane reads its 4 codes x DS floats with one or two conflict-free LDS.128 per step) instead of 64 registers, which
+// takes the kernel from 128 to <= 64 registers and from 16 to 32 warps per SM.
 template <int DS>
-__global__ void __launch_bounds__(256) tc_lut_kernel(const LutArgs a) {
+__global__ void __launch_bounds__(256, DS > 0 ? 4 : 2) tc_lut_kernel(const LutArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* qres = reinterpret_cast<float*>(sm) + warp * a.dim;
   const int nstep = a.S / 8;  // 128 table bytes per step (S is a multiple of 16)
   constexpr int kDs = DS > 0 ? DS : 1;
-  float cbr[8][4][kDs];
+  float* cbs = reinterpret_cast<float*>(sm) + 8 * a.dim;  // [S * 16 * DS] codewords (DS > 0), 16-byte aligned (dim % 16 == 0)
   if (DS > 0) {
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-#pragma unroll
-        for (int j = 0; j < kDs; ++j)
-          cbr[t][b][j] = t < nstep ? __ldg(a.codebook + (128 * t + 4 * lane + b) * DS + j) : 0.0f;
+    for (int i = threadIdx.x; i < a.S * 16 * DS; i += blockDim.x) cbs[i] = __ldg(a.codebook + i);
+    __syncthreads();
   }
   const uint32_t ngroups = a.counters[1];
   const uint32_t total = ngroups * kTcsGroup;
@@ -399,13 +398,25 @@ __global__ void __launch_bounds__(256) tc_lut_kernel(const LutArgs a) {
       for (int t = 0; t < 8; ++t) {
         if (t < nstep) {
           const int s = 8 * t + (lane >> 2);  // subspace of this lane's four entries
+          float cw[4 * kDs];  // this lane's 4 codes x DS floats of step t
+          if (DS > 0) {
+            const float4* c4 = reinterpret_cast<const float4*>(cbs + (128 * t + 4 * lane) * DS);
+#pragma unroll
+            for (int v = 0; v < kDs; ++v) {
+              const float4 x = c4[v];
+              cw[4 * v + 0] = x.x;
+              cw[4 * v + 1] = x.y;
+              cw[4 * v + 2] = x.z;
+              cw[4 * v + 3] = x.w;
+            }
+          }
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             float sum = 0.0f;
             if (DS > 0) {
 #pragma unroll
               for (int jj = 0; jj < kDs; ++jj) {
-                const float d = __fsub_rn(qres[s * DS + jj], cbr[t][b][jj]);
+                const float d = __fsub_rn(qres[s * DS + jj], cw[b * DS + jj]);
                 sum = __fadd_rn(sum, __fmul_rn(d, d));
               }
             } else {
@@ -897,8 +908,8 @@ scann_status launch_tc_scan(const TcScanParams& p, Workspace& ws, TcScanOut* out
   la.L = static_cast<int>(p.L);
   la.use_residuals = p.use_residuals;
   la.row_bytes = row_bytes;
-  const size_t lsm = 8 * p.dim * sizeof(float);
-  const unsigned lgrid = static_cast<unsigned>(p.sms * 8);
+  const size_t lsm = 8 * p.dim * sizeof(float) + (la.ds <= 2 ? S * 16 * la.ds * sizeof(float) : 0);
+  const unsigned lgrid = static_cast<unsigned>(p.sms * (la.ds <= 2 ? 4 : 2));  // = the resident CTAs (persistent row loop)
   if (la.ds == 1) tc_lut_kernel<1><<<lgrid, 256, lsm, s>>>(la);
   else if (la.ds == 2) tc_lut_kernel<2><<<lgrid, 256, lsm, s>>>(la);
   else tc_lut_kernel<0><<<lgrid, 256, lsm, s>>>(la);
