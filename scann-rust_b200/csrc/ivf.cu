@@ -216,6 +216,13 @@ __global__ void __launch_bounds__(256) ivf_topk_kernel(const IvfArgs a) {
 
 }  // namespace scann
 
+// create-time validation: every member id must index the per-datapoint arrays (raw rows / codes).  The reference skips
+// such entries through dataset.get(idx); a malformed index is refused here instead of read out of bounds by the kernels.
+__global__ void ids_in_range_kernel(const uint32_t* __restrict__ ids, size_t n, uint32_t limit, uint32_t* __restrict__ bad) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n && ids[i] >= limit) atomicAdd(bad, 1u);
+}
+
 struct scann_ivf {
   int device = 0;
   size_t K = 0, dim = 0, n = 0, num_raw = 0, stride = 0, S = 0, C = 0, ds = 0;
@@ -317,6 +324,23 @@ scann_status scann_ivf_create(const float* centers, size_t K, size_t dim, const 
     if (codebook) {
       if ((st = h->codebook.upload(codebook, S * C * h->ds, memspace, s)) != SCANN_OK) break;
       if ((st = h->codes.upload(codes_by_id, num_raw * S, memspace, s)) != SCANN_OK) break;
+    }
+    if ((raw || codebook) && n > 0) {
+      scann::DevBuf<uint32_t> bad;
+      if ((st = bad.alloc(1)) != SCANN_OK) break;
+      cudaMemsetAsync(bad.p, 0, 4, s);
+      ids_in_range_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(h->ids.p, n, static_cast<uint32_t>(
+          std::min<size_t>(num_raw, 0xFFFFFFFFull)), bad.p);
+      uint32_t nbad = 0;
+      if (cudaMemcpyAsync(&nbad, bad.p, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        st = cuda_fail(cudaGetLastError(), "ivf_create id check", __FILE__, __LINE__);
+        break;
+      }
+      if (nbad != 0) {
+        set_error("%u member ids are >= the %zu datapoints of the dataset", nbad, num_raw);
+        st = SCANN_INVALID_ARGUMENT;
+        break;
+      }
     }
     if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
       st = cuda_fail(cudaGetLastError(), "ivf_create sync", __FILE__, __LINE__);

@@ -105,3 +105,15 @@ def test_leafscan_errors_and_facade(gpu_lib, oracle):
     assert sc.search_mode == gpu_lib.SearchMode.Partitioned
     ids, dists, counts = sc.search_batched(x[:32])
     assert ids.shape == (32, 5) and (np.asarray(ids)[:, 0] == np.arange(32)).all() and (np.asarray(dists)[:, 0] == 0).all()
+
+
+def test_ivf_create_refuses_member_ids_outside_the_dataset(gpu_lib, oracle):
+    """index arrays are validated at create — a member id >= the number of datapoints would be read out of
+    bounds by the scan kernels (the reference skips such entries through dataset.get)."""
+    x, centers, order, off = _ivf_index(oracle, 2000, 16, 8, 5)
+    bad = order.copy()
+    bad[7] = 2000  # one id past the end
+    with pytest.raises(gpu_lib.ScannError) as e:
+        gpu_lib.LeafScanSearcher(centers, bad, off, x)
+    assert e.value.code == gpu_lib.capi.INVALID_ARGUMENT and "member ids" in e.value.message
+    gpu_lib.LeafScanSearcher(centers, order, off, x).close()  # the well-formed index is accepted
