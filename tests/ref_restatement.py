@@ -1,0 +1,116 @@
+"""TEST INFRASTRUCTURE.  A SECOND, independent restatement of the approximate stage of Tree-AH in plain Python / numpy
+scalars, written from the Rust source (not from oracle/scann_oracle.cpp), used to cross-check the C++ oracle on small
+cases: if two independent restatements agree bit for bit — distances, ids AND tie order — a transcription mistake in either
+would have to be made twice.  (Neither is output of the reference itself: the crate cannot be built in this image.)
+
+Follows, line for line:
+  TreePartitioner::partition          src/partitioning/tree_partitioner.rs:175-229  (sequential f32 sum of d*d, stable sort)
+  residual                            src/tree_x_hybrid/mod.rs:307-315              (q - centroid per dimension)
+  Lut16LookupTables::from_query       src/hashes/lut16.rs:151-173                   (squared_l2 per code, sequential)
+  Lut16SimdTables::from_float_tables  src/hashes/lut16_simd.rs:39-90                (global min/max, 255/range, round, as u8)
+  lut16_distances_batch_portable      src/simd/dispatch.rs:259-295                  (low nibble first, u32 sum, as f32)
+  dequantisation                      src/hashes/lut16_simd.rs:134-140              (sum * multiplier + bias * S)
+  FastTopNeighbors::push / results    src/brute_force/top_k.rs:333-383              (first slot holding the max is replaced)
+  search_with_filter merge            src/tree_x_hybrid/mod.rs:282-291              (flatten, stable sort, truncate)
+"""
+import numpy as np
+
+F = np.float32
+
+
+def sqdist_seq(a, b):
+    s = F(0.0)
+    for x, y in zip(a, b):
+        d = F(F(x) - F(y))
+        s = F(s + F(d * d))
+    return s
+
+
+def partition(centers, q, L):
+    d = [sqdist_seq(q, c) for c in centers]
+    order = sorted(range(len(centers)), key=lambda i: (d[i], i))  # sort_by_key(OrderedFloat) is stable: ties keep index order
+    return order[:min(L, len(order))]
+
+
+def rust_round(x):
+    """f32::round: half away from zero"""
+    x = F(x)
+    return F(np.floor(x + F(0.5))) if x >= 0 else F(np.ceil(x - F(0.5)))
+
+
+def as_u8(x):
+    """Rust `as u8`: saturating, NaN -> 0"""
+    if x != x:
+        return 0
+    return int(min(max(float(x), 0.0), 255.0))
+
+
+def lut16_tables(codebook, resid):
+    """codebook [S][16][ds] -> (u8 tables [S][16], bias, multiplier)"""
+    S, C, ds = codebook.shape
+    ft = np.empty((S, C), np.float32)
+    for s in range(S):
+        for c in range(C):
+            ft[s, c] = sqdist_seq(resid[s * ds:(s + 1) * ds], codebook[s, c])
+    gmin, gmax = F(np.finfo(np.float32).max), F(np.finfo(np.float32).min)
+    for v in ft.flat:
+        gmin = min(gmin, F(v))
+        gmax = max(gmax, F(v))
+    rng = F(gmax - gmin)
+    if rng < F(1e-10):
+        mult, scale = F(1.0), F(1.0)
+    else:
+        scale = F(F(255.0) / rng)
+        mult = F(F(1.0) / scale)
+    q8 = np.empty((S, C), np.uint8)
+    for s in range(S):
+        for c in range(C):
+            q8[s, c] = as_u8(rust_round(F(F(ft[s, c] - gmin) * scale)))
+    return q8, gmin, mult
+
+
+class FastTopNeighbors:
+    def __init__(self, capacity):
+        self.cap = capacity
+        self.idx, self.dist = [], []
+
+    def push(self, index, distance):
+        if len(self.idx) < self.cap:
+            self.idx.append(index)
+            self.dist.append(distance)
+        elif self.cap > 0:
+            mi, md = 0, self.dist[0]
+            for i in range(1, len(self.dist)):
+                if self.dist[i] > md:
+                    md, mi = self.dist[i], i
+            if distance < md:
+                self.idx[mi], self.dist[mi] = index, distance
+
+    def results(self):
+        return sorted(zip(self.idx, self.dist), key=lambda t: t[1])  # stable
+
+
+def approx_candidates(centers, codebook, part_offsets, ids, packed, q, L, R, use_residuals=True):
+    """-> [(datapoint index, approximate distance)] in the order search_with_filter hands to reorder_results"""
+    S = codebook.shape[0]
+    bpp = (S + 1) // 2
+    allr = []
+    for leaf in partition(centers, q, L):
+        resid = np.array([F(F(a) - F(b)) for a, b in zip(q, centers[leaf])], np.float32) if use_residuals else q
+        q8, bias, mult = lut16_tables(codebook, resid)
+        bias_total = F(bias * F(S))
+        top = FastTopNeighbors(R)
+        for row in range(int(part_offsets[leaf]), int(part_offsets[leaf + 1])):
+            total, sub = 0, 0
+            for b in range(bpp):
+                byte = int(packed[row, b])
+                if sub < S:
+                    total += int(q8[sub, byte & 0x0F])
+                    sub += 1
+                if sub < S:
+                    total += int(q8[sub, (byte >> 4) & 0x0F])
+                    sub += 1
+            top.push(int(ids[row]), F(F(F(total) * mult) + bias_total))
+        allr.extend(top.results())
+    allr.sort(key=lambda t: t[1])  # stable
+    return allr[:R]
