@@ -114,3 +114,79 @@ def approx_candidates(centers, codebook, part_offsets, ids, packed, q, L, R, use
         allr.extend(top.results())
     allr.sort(key=lambda t: t[1])  # stable
     return allr[:R]
+
+
+class RustBinaryHeap:
+    """std::collections::BinaryHeap<(OrderedFloat<f32>, u32)> (max-heap), the algorithms of library/alloc binary_heap:
+    push = sift_up(0, old_len); pop = swap the last element into the root, sift_down_to_bottom(0), then sift_up."""
+
+    def __init__(self):
+        self.data = []
+
+    def __len__(self):
+        return len(self.data)
+
+    def peek(self):
+        return self.data[0] if self.data else None
+
+    def _sift_up(self, start, pos):
+        d = self.data
+        elt = d[pos]
+        while pos > start:
+            parent = (pos - 1) // 2
+            if elt <= d[parent]:
+                break
+            d[pos] = d[parent]
+            pos = parent
+        d[pos] = elt
+        return pos
+
+    def push(self, item):
+        self.data.append(item)
+        self._sift_up(0, len(self.data) - 1)
+
+    def pop(self):
+        d = self.data
+        if not d:
+            return None
+        item = d.pop()
+        if d:
+            item, d[0] = d[0], item
+            end, start, pos = len(d), 0, 0
+            elt = d[pos]
+            child = 2 * pos + 1
+            while child <= max(end - 2, 0) and child + 1 < end:
+                if d[child] <= d[child + 1]:
+                    child += 1
+                d[pos] = d[child]
+                pos = child
+                child = 2 * pos + 1
+            if child == end - 1:
+                d[pos] = d[child]
+                pos = child
+            d[pos] = elt
+            self._sift_up(start, pos)
+        return item
+
+
+class TopK:
+    """src/brute_force/top_k.rs:19-112: heap of (distance, index); results() = heap.iter() order, stable-sorted by distance"""
+
+    def __init__(self, k):
+        self.k = k
+        self.heap = RustBinaryHeap()
+
+    def push(self, index, distance):
+        distance = float(np.float32(distance))
+        if len(self.heap) < self.k:
+            self.heap.push((distance, index))
+            return True
+        top = self.heap.peek()
+        if top is not None and distance < top[0]:
+            self.heap.pop()
+            self.heap.push((distance, index))
+            return True
+        return False
+
+    def results(self):
+        return sorted(((i, d) for d, i in self.heap.data), key=lambda t: t[1])

@@ -42,3 +42,29 @@ def test_fast_top_neighbors_restatement_matches_reference_unit_tests():
     z = rr.FastTopNeighbors(0)
     z.push(1, np.float32(1.0))
     assert z.results() == []
+
+
+@pytest.mark.parametrize("k,n,levels,seed", [(1, 50, 3, 0), (5, 200, 4, 1), (10, 500, 6, 2), (32, 400, 5, 3), (100, 300, 7, 4)])
+def test_oracle_topk_heap_order_equals_python_binary_heap(oracle, k, n, levels, seed):
+    """TopK (BinaryHeap of (OrderedFloat, index)): accepted flags, kept set and the ORDER results() returns — which inside
+    ties is the heap's internal array order — against a Python emulation of std's BinaryHeap sift algorithms."""
+    rng = np.random.default_rng(seed)
+    dists = rng.integers(0, levels, n).astype(np.float32)  # few distinct values: ties everywhere
+    ids = rng.permutation(n).astype(np.uint32)
+    oi, od, acc = oracle.topk_run(k, ids, dists)
+    t = rr.TopK(k)
+    pacc = [t.push(int(i), d) for i, d in zip(ids, dists)]
+    res = t.results()
+    assert pacc == acc.tolist()
+    assert [i for i, _ in res] == oi.tolist()
+    assert [np.float32(d) for _, d in res] == od.tolist()
+
+
+def test_python_binary_heap_is_a_heap():
+    rng = np.random.default_rng(9)
+    h = rr.RustBinaryHeap()
+    vals = [(float(v), int(i)) for i, v in enumerate(rng.integers(0, 20, 300))]
+    for v in vals:
+        h.push(v)
+    out = [h.pop() for _ in range(len(vals))]
+    assert out == sorted(vals, reverse=True)
