@@ -190,3 +190,38 @@ class TopK:
 
     def results(self):
         return sorted(((i, d) for d, i in self.heap.data), key=lambda t: t[1])
+
+
+def sq8_quantize(db, num_std_devs=3.0, bits=8):
+    """QuantizationStats::from_dataset (src/quantization/mod.rs:77-110: sequential f64 sums, sample variance) +
+    ScalarQuantizer::calibrate (scalar.rs:103-130, the non-symmetric std-dev branch) + quantize_value (:161-165)
+    -> (codes i8 [n, dim], (min_value, max_value, scale, inv_scale))"""
+    mn, mx = F(np.finfo(np.float32).max), F(np.finfo(np.float32).min)
+    s = s2 = 0.0
+    cnt = 0
+    for row in db:
+        for v in row:
+            v = F(v)
+            mn, mx = min(mn, v), max(mx, v)
+            s += float(v)
+            s2 += float(v) * float(v)
+            cnt += 1
+    mean = F(s / cnt) if cnt > 0 else F(0.0)
+    var = F((s2 - s * s / cnt) / (cnt - 1)) if cnt > 1 else F(0.0)
+    std = F(np.sqrt(var))
+    levels = (1 << bits) - 1
+    rng0 = F(F(num_std_devs) * std)
+    lo, hi = max(F(mean - rng0), mn), min(F(mean + rng0), mx)
+    rng = F(hi - lo)
+    if rng > F(1e-10):
+        scale, inv = F(rng / F(levels)), F(F(levels) / rng)
+    else:
+        scale, inv = F(1.0), F(1.0)
+    codes = np.empty(db.shape, np.int8)
+    for i, row in enumerate(db):
+        for j, v in enumerate(row):
+            c = min(max(F(v), lo), hi)
+            qi = int(rust_round(F(F(c - lo) * inv)))
+            qi = min(max(qi, 0), levels)
+            codes[i, j] = np.array(qi, np.int64).astype(np.uint8).view(np.int8)  # `as i8` wraps 128..255 to -128..-1
+    return codes, (lo, hi, scale, inv)

@@ -68,3 +68,15 @@ def test_python_binary_heap_is_a_heap():
         h.push(v)
     out = [h.pop() for _ in range(len(vals))]
     assert out == sorted(vals, reverse=True)
+
+
+@pytest.mark.parametrize("seed,scale", [(0, 1.0), (1, 37.5), (2, 1e-3)])
+def test_oracle_sq8_quantiser_equals_python_restatement(oracle, seed, scale):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal((300, 7)) * scale).astype(np.float32)
+    x[5, 3] = np.float32(40.0 * scale)  # an outlier beyond 3 sigma: clipped
+    codes, cal = oracle.sq8_quantize(x)
+    pc, (lo, hi, sc, inv) = rr.sq8_quantize(x)
+    assert (np.array([lo, hi, sc, inv], np.float32).view(np.uint32) == cal.view(np.uint32)).all()
+    assert (codes == pc).all()
+    assert codes.min() < 0  # values above 127 wrap to negative i8, as in the reference
