@@ -320,15 +320,16 @@ struct MergeArgs {
   uint32_t qcap;
 };
 
-constexpr int kMergeChunk = 2048;
+constexpr int kMergeChunk = 2048;       // streaming chunk of the merge when a query can have L * R candidates
+constexpr int kMergeChunkSmall = 512;   // after a tensor-core scan a query has a few hundred: smaller CTAs, 16 per SM
 constexpr int kMergeThreads = 128;
 
-template <int NT>
+template <int NT, int CHUNK>
 __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   const int p2 = next_pow2(a.R < 1 ? 1 : a.R);
   uint64_t* buf = reinterpret_cast<uint64_t*>(sm);              // [R + chunk]
-  uint64_t* out = buf + (a.R + kMergeChunk);                    // [p2]
+  uint64_t* out = buf + (a.R + CHUNK);                          // [p2]
   uint32_t* hist = reinterpret_cast<uint32_t*>(out + p2);       // [264]
   uint32_t* prefix = hist + 264;                                // [L + 1]
   uint32_t* cid = prefix + (a.L + 1);                           // [p2] datapoint ids
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
     uint2 c = cq[static_cast<size_t>(lo) * a.R + (i - prefix[lo])];
     return (static_cast<uint64_t>(f32_key(__uint_as_float(c.x))) << 32) | (static_cast<uint64_t>(lo) << 22) | c.y;
   };
-  const int m = block_topr_sorted<NT, kMergeChunk>(gen, total + nlist, a.R, buf, out, hist);
+  const int m = block_topr_sorted<NT, CHUNK>(gen, total + nlist, a.R, buf, out, hist);
 
   // the R approximate candidates, in (approx distance, leaf rank, position) order
   for (int j = tid; j < p2; j += NT) {
@@ -407,6 +408,7 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
   if (a.raw != nullptr) {
     // exact distance of every candidate row, 8 lanes per row (src/tree_x_hybrid/mod.rs:342-364)
     const int grp = tid >> 3, sub = tid & 7;
+#pragma unroll 2  // two passes' row loads in flight: the pass is a chain of dependent global loads
     for (int j0 = 0; j0 < m; j0 += NT / 8) {
       int j = j0 + grp;
       bool valid = j < m;
@@ -441,9 +443,9 @@ __global__ void __launch_bounds__(NT) merge_reorder_kernel(const MergeArgs a) {
   if (tid == 0) a.out_counts[q] = static_cast<uint32_t>(kk);
 }
 
-static size_t merge_smem_bytes(int R, int L, int dim) {
+static size_t merge_smem_bytes(int R, int L, int dim, int chunk) {
   int p2 = next_pow2(R < 1 ? 1 : R);
-  return (static_cast<size_t>(R) + kMergeChunk + p2) * 8 + 264 * 4 + (static_cast<size_t>(L) + 1) * 4 +
+  return (static_cast<size_t>(R) + chunk + p2) * 8 + 264 * 4 + (static_cast<size_t>(L) + 1) * 4 +
          static_cast<size_t>(p2) * 8 + static_cast<size_t>(dim) * 4 + 16;
 }
 
@@ -845,11 +847,21 @@ static scann_status treeah_phase2(scann_treeah* h, bool two_phase, const float* 
   m.cand_ids = d_cand_ids;
   m.cand_dists = d_cand_dists;
   m.cand_counts = d_cand_counts;
-  size_t msm = merge_smem_bytes(static_cast<int>(R), static_cast<int>(L), static_cast<int>(h->dim));
-  // candidates per query after pruning are few: 128 threads per query keep more queries in flight per SM
-  SCANN_CUDA(cudaFuncSetAttribute(merge_reorder_kernel<kMergeThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(msm)));
-  merge_reorder_kernel<kMergeThreads><<<static_cast<unsigned>(nq), kMergeThreads, msm, s>>>(m);
+  // candidates per query after pruning are few: 128 threads per query keep more queries in flight per SM; after a
+  // tensor-core scan the smaller streaming chunk makes the CTA 8 KB instead of 20 KB (the kernel is latency-bound: 16
+  // instead of 11 resident queries per SM)
+  const bool small = h->ck.use_tc;
+  size_t msm = merge_smem_bytes(static_cast<int>(R), static_cast<int>(L), static_cast<int>(h->dim),
+                                small ? kMergeChunkSmall : kMergeChunk);
+  if (small) {
+    SCANN_CUDA(cudaFuncSetAttribute(merge_reorder_kernel<kMergeThreads, kMergeChunkSmall>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(msm)));
+    merge_reorder_kernel<kMergeThreads, kMergeChunkSmall><<<static_cast<unsigned>(nq), kMergeThreads, msm, s>>>(m);
+  } else {
+    SCANN_CUDA(cudaFuncSetAttribute(merge_reorder_kernel<kMergeThreads, kMergeChunk>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(msm)));
+    merge_reorder_kernel<kMergeThreads, kMergeChunk><<<static_cast<unsigned>(nq), kMergeThreads, msm, s>>>(m);
+  }
   SCANN_CUDA(cudaGetLastError());
   h->span_end(s);
   h->prof_launches += two_phase && tau_in ? 3 : 2;  // (tau_in) + lut16_scan + merge_reorder
