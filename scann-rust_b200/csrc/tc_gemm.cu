@@ -109,6 +109,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t elect_one() {  // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
 
 // K-major operand tile in the canonical 128-byte-swizzle layout (rows of 128 B, 8-row groups 1024 B apart):
 // start address >> 4, LBO (ignored for swizzled K-major) = 1, SBO = 1024 >> 4, descriptor version 1 (sm_100),
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0, aphase = 0;
       for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
         const uint32_t qt = u % a.q_tiles, nu = u / a.q_tiles;
@@ -218,7 +223,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // elect.sync instead of "lane == 0": the compiler then knows that a single thread runs the loop and keeps the
+    // descriptors on the uniform datapath — the 16 UTCHMMA of a tile back to back.  With "lane == 0" every tcgen05.mma
+    // was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (167 of them in the object).
+    if (elect_one()) {
       uint32_t stage = 0, phase = 0, aphase = 0, as = 0, asphase = 0;
       for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
         const uint32_t nu = u / a.q_tiles;
