@@ -45,8 +45,7 @@ constexpr int kTcTmemCols = 512;
 // one global atomic per entry, all lanes at once — a survivor costs a shared-memory atomic instead of a serialised
 // round trip to L2 (at ~1 survivor per 1024 scores nearly every 32x32 chunk has one).
 constexpr int kWqCap = 192;                          // entries per warp queue
-constexpr int kWqStep = 128;                         // most entries one filter step can add (32 lanes x 4 columns)
-constexpr int kWqBytes = kWqCap * 8 + kWqCap + 16;   // (score key, row) u64, lanes u8, count u32 (+ pad)
+constexpr int kWqBytes = kWqCap * 8 + kWqCap + 16;   // (score key, row) u64, lanes u8 (+ pad)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -109,6 +108,19 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// shared-memory queue operations by 32-bit shared address (a pointer that has been through a non-inlined call is generic
+// to the compiler, and generic atomics / stores are what it then emits)
+__device__ __forceinline__ uint32_t atoms_inc(uint32_t saddr) {
+  uint32_t r;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t elect_one() {  // one lane of the (converged) warp
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -143,6 +155,30 @@ struct TcArgs {
   int no_hx;                // FILTER with hx == 0 for every real row (Dot): v = -acc, the hx loads and subtractions are
                             // skipped (padding rows then score 0 and may enter a list: the re-score ignores ids >= n)
 };
+
+// FILTER survivors.  A hit is queued by its own lane (one shared-memory atomic for the slot) as (raw w bits, row); the
+// warp looks at its queue once per tile and writes it out when it is half full.  Both routines are single copies,
+// called: inlined at every use they were a fifth of the epilogue's code, and the epilogue was stalling on instruction
+// fetch (ncu: stall_no_inst on the filter lines of a 45 KB loop body).
+__device__ __forceinline__ unsigned long long tc_list_entry(uint32_t w_bits, uint32_t row) {
+  return (static_cast<unsigned long long>(f32_key(-__uint_as_float(w_bits))) << 32) | row;  // v = -w
+}
+__device__ __noinline__ void tc_flush(uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ cand,
+                                      uint32_t cap, uint32_t qwarp, const uint2* wq_rows, const uint8_t* wq_lanes,
+                                      uint32_t nw) {
+  for (uint32_t i = threadIdx.x & 31u; i < nw; i += 32) {
+    const uint32_t qq = qwarp + wq_lanes[i];
+    const uint2 e = wq_rows[i];
+    const uint32_t slot = atomicAdd(cand_cnt + qq, 1u);
+    if (slot < cap) cand[static_cast<size_t>(qq) * cap + slot] = tc_list_entry(e.y, e.x);
+  }
+}
+// the queue is full (more than half a queue of hits in one tile): straight to the query's list
+__device__ __noinline__ void tc_emit_direct(uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ cand,
+                                            uint32_t cap, uint32_t q, uint32_t w_bits, uint32_t row) {
+  const uint32_t slot = atomicAdd(cand_cnt + q, 1u);
+  if (slot < cap) cand[static_cast<size_t>(q) * cap + slot] = tc_list_entry(w_bits, row);
+}
 
 template <int MT, int KA, int STAGES>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -273,24 +309,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     constexpr int ncols = MT == 2 ? kTcBN / 2 : kTcBN / 4;
     const int c0 = (MT == 2 ? (grp & 1) : grp) * ncols;
     constexpr int nchunks = ncols / 32;
-    unsigned long long* const wq_rows = reinterpret_cast<unsigned long long*>(wq_base + e * kWqBytes);
+    uint2* const wq_rows = reinterpret_cast<uint2*>(wq_base + e * kWqBytes);  // (row, raw w bits)
     uint8_t* const wq_lanes = reinterpret_cast<uint8_t*>(wq_rows + kWqCap);
-    volatile uint32_t* const wq_cnt = reinterpret_cast<uint32_t*>(wq_lanes + kWqCap);
+    uint32_t* const wq_cnt = reinterpret_cast<uint32_t*>(wq_lanes + kWqCap);
+    const uint32_t wq_rows_s = smem_u32(wq_rows), wq_lanes_s = smem_u32(wq_lanes), wq_cnt_s = smem_u32(wq_cnt);
     if (lane == 0) *wq_cnt = 0;
     __syncwarp();
-    uint32_t qwarp = 0;  // first query of this warp in the current unit
-    auto flush = [&]() {
-      __syncwarp();
-      const uint32_t nw = *wq_cnt;
-      for (uint32_t i = lane; i < nw; i += 32) {
-        const uint32_t qq = qwarp + wq_lanes[i];
-        const uint32_t slot = atomicAdd(a.cand_cnt + qq, 1u);
-        if (slot < a.cap) a.cand[static_cast<size_t>(qq) * a.cap + slot] = wq_rows[i];
-      }
-      __syncwarp();
-      if (lane == 0) *wq_cnt = 0;
-      __syncwarp();
-    };
     uint32_t as = 0, asphase = 0;
     for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const uint32_t qt = u % a.q_tiles, nu = u / a.q_tiles;
@@ -298,11 +322,20 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint32_t t1 = min(t0 + a.tiles_per_unit, a.n_tiles);
       const uint32_t q = (qt * MT + mt) * kTcBM + quad * 32 + lane;
       const bool qvalid = q < a.nq;
-      qwarp = q - lane;
-      float thr = __int_as_float(0xFF800000);  // -inf: nothing passes
-      if (a.filter && qvalid) thr = a.thr[q];
+      const uint32_t qwarp = q - lane;  // first query of this warp in the unit
+      float nthr = __int_as_float(0x7F800000);  // +inf: nothing passes
+      if (a.filter && qvalid) nthr = -a.thr[q];
+      // queue whatever the warp holds (all lanes; called at points where the warp is converged)
+      auto flush = [&]() {
+        __syncwarp();
+        const uint32_t nw = min(*const_cast<volatile uint32_t*>(wq_cnt), static_cast<uint32_t>(kWqCap));
+        if (nw) tc_flush(a.cand_cnt, a.cand, a.cap, qwarp, wq_rows, wq_lanes, nw);
+        __syncwarp();
+        if (lane == 0) *wq_cnt = 0;
+        __syncwarp();
+      };
       for (uint32_t t = t0; t < t1; ++t) {
-        if (t + 1 < t1 && lane < ncols / 32)  // pull the next tile's hx lines into L1 while this tile is filtered
+        if (!a.no_hx && t + 1 < t1 && lane < ncols / 32)  // pull the next tile's hx lines into L1 while this tile is filtered
           asm volatile("prefetch.global.L1 [%0];" ::"l"(a.hx + a.row0 + (t + 1) * a.tile_stride * kTcBN + c0 + lane * 32));
         mbar_wait(bar(kTFull + as), asphase);
         tc_fence_after();
@@ -314,49 +347,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           const int cc = ch * 32;
           uint32_t vr[32];
           tc_ld32(taddr + cc, vr);
-          float v[32];
+          // w = acc - hx = -v for every score of the chunk (IEEE subtraction is symmetric: -(acc - hx) is bit for bit
+          // hx - acc), so one copy of the filter code serves Dot (hx == 0: w is the raw accumulator) and the L2 family
+          float w[32];
           if (a.no_hx) {
             tc_wait_ld();
-            if (ch + 1 == nchunks) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(kTEmpty + as));
-            }
-            if (a.filter) {
-              // Dot FILTER fast path: v = -acc, so "v <= thr" is "acc >= -thr" — the test runs on the raw accumulators
-              // (max tree, no negation: 32 instructions fewer per 32 scores in an epilogue-bound kernel); only a hit
-              // materialises v for its list entry
-              const float nthr = -thr;
 #pragma unroll
-              for (int g8 = 0; g8 < 4; ++g8) {
-                float m = __uint_as_float(vr[8 * g8]);
-#pragma unroll
-                for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(vr[8 * g8 + j]));
-                const bool hit = m >= nthr;
-                if (__any_sync(0xFFFFFFFFu, hit)) {  // warp-uniform: the queue room check and flush are collective
-#pragma unroll
-                  for (int h4 = 0; h4 < 2; ++h4) {
-                    if (*wq_cnt > kWqCap - kWqStep) flush();
-                    if (hit) {
-#pragma unroll
-                      for (int j = 0; j < 4; ++j) {
-                        const float acc = __uint_as_float(vr[8 * g8 + 4 * h4 + j]);
-                        if (acc >= nthr) {
-                          const uint32_t sl = atomicAdd(const_cast<uint32_t*>(wq_cnt), 1u);
-                          wq_rows[sl] = (static_cast<unsigned long long>(f32_key(-acc)) << 32) |
-                                        (row_tile + cc + 8 * g8 + 4 * h4 + j);
-                          wq_lanes[sl] = static_cast<uint8_t>(lane);
-                        }
-                      }
-                    }
-                    __syncwarp();
-                  }
-                }
-              }
-              continue;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = -__uint_as_float(vr[j]);
+            for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(vr[j]);
           } else {
             const float4* h4 = reinterpret_cast<const float4*>(a.hx + row_tile + cc);
             float h[32];
@@ -369,48 +366,50 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               h[4 * j + 3] = x.w;
             }
             tc_wait_ld();
-            if (ch + 1 == nchunks) {
-              // the whole accumulator is in registers: hand it back to the MMA warp before the last chunk's work
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(kTEmpty + as));
-            }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __fsub_rn(h[j], __uint_as_float(vr[j]));
+            for (int j = 0; j < 32; ++j) w[j] = __fsub_rn(__uint_as_float(vr[j]), h[j]);
+          }
+          if (ch + 1 == nchunks) {
+            // the whole accumulator is in registers: hand it back to the MMA warp before the last chunk's work
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kTEmpty + as));
           }
           if (!a.filter) {
             if (qvalid) {
               float4* o = reinterpret_cast<float4*>(a.dense + static_cast<size_t>(q) * a.ld + col_tile + cc);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              for (int j = 0; j < 8; ++j) o[j] = make_float4(-w[4 * j], -w[4 * j + 1], -w[4 * j + 2], -w[4 * j + 3]);
             }
-          } else {
+            continue;
+          }
+          // FILTER: v <= thr is w >= -thr.  A max tree per 8 columns; only the lanes with a hit (about one group in
+          // three has one, at C2) leave the straight path, and nothing in it is a warp-wide step.
 #pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              float m = v[8 * g8];
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float m = w[8 * g8];
 #pragma unroll
-              for (int j = 1; j < 8; ++j) m = fminf(m, v[8 * g8 + j]);
-              const bool hit = m <= thr;
-              if (__any_sync(0xFFFFFFFFu, hit)) {  // warp-uniform: the queue room check and flush are collective
+            for (int j = 1; j < 8; ++j) m = fmaxf(m, w[8 * g8 + j]);
+            if (m >= nthr) {
 #pragma unroll
-                for (int h4 = 0; h4 < 2; ++h4) {
-                  if (*wq_cnt > kWqCap - kWqStep) flush();
-                  if (hit) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      if (v[8 * g8 + 4 * h4 + j] <= thr) {
-                        const uint32_t sl = atomicAdd(const_cast<uint32_t*>(wq_cnt), 1u);
-                        wq_rows[sl] = (static_cast<unsigned long long>(f32_key(v[8 * g8 + 4 * h4 + j])) << 32) |
-                                      (row_tile + cc + 8 * g8 + 4 * h4 + j);
-                        wq_lanes[sl] = static_cast<uint8_t>(lane);
-                      }
-                    }
+              for (int j = 0; j < 8; ++j) {
+                if (w[8 * g8 + j] >= nthr) {
+                  const uint32_t row = row_tile + cc + 8 * g8 + j;
+                  const uint32_t sl = atoms_inc(wq_cnt_s);
+                  if (sl < static_cast<uint32_t>(kWqCap)) {
+                    sts_v2(wq_rows_s + 8u * sl, row, __float_as_uint(w[8 * g8 + j]));
+                    sts_u8(wq_lanes_s + sl, static_cast<uint32_t>(lane));
+                  } else {
+                    tc_emit_direct(a.cand_cnt, a.cand, a.cap, q, __float_as_uint(w[8 * g8 + j]), row);
                   }
-                  __syncwarp();
                 }
               }
             }
           }
+        }
+        if (a.filter) {
+          __syncwarp();
+          if (*const_cast<volatile uint32_t*>(wq_cnt) > kWqCap / 2) flush();  // warp-uniform
         }
         if (++as == 2) {
           as = 0;
