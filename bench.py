@@ -383,8 +383,9 @@ def bench_bf(a, emit, torch, pkg, dev, local_rank):
            "agreement_with_independent_exact_topk": agree,
            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": a.nq * a.dim * 4,
                    "d2h_bytes_per_step": a.nq * (a.k * 8 + 4)},
-           "gpu_launches": int(a.steps * ((a.nq + 4095) // 4096) * 6),  # per 4096-query chunk: prep, sample GEMM, bound,
-           # filter GEMM, overflow flag, exact re-score
+           # per 4096-query chunk: prep, sample GEMM, bound, filter GEMM, overflow flag, exact re-score; from 32768 rows on
+           # the filter runs as prefix pass + tightened bound + pass over the rest
+           "gpu_launches": int(a.steps * ((a.nq + 4095) // 4096) * (8 if a.n >= 32768 else 6)),
            "path_chunks": {"tcgen05": tc, "cuda_core": legacy},
            "roofline": {"bound": "tensor", "kernel": "tc_score_kernel (whole step: sample + filter + exact re-score)",
                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,

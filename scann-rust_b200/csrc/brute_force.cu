@@ -231,6 +231,30 @@ __global__ void __launch_bounds__(256) bf_bound_kernel(const float* __restrict__
   if (lane == 0) thr[q] = (t == t) ? t : inf;
 }
 
+// Step c', one warp per query, after the FILTER pass over a PREFIX of the rows: the prefix survivors are real rows with
+// known scores, so (an upper bound of) the kk-th smallest score among them bounds the kk-th smallest score over all rows
+// just like the sample did — and much more tightly (a 1/8 prefix holds ~kk/8-th-quantile rows where the 16384-row sample
+// holds the kk/0.016-th).  thr[q] only ever tightens; a list that is short of kk entries or overflowed keeps its bound.
+__global__ void __launch_bounds__(256) bf_tighten_kernel(const unsigned long long* __restrict__ lists,
+                                                         const uint32_t* __restrict__ cnt, uint32_t cap, int kk,
+                                                         const float* __restrict__ qn, float xmax2, size_t nq,
+                                                         int rows_i8, float* __restrict__ thr) {
+  __shared__ uint32_t s_hist[8][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t q = static_cast<size_t>(blockIdx.x) * 8 + warp;
+  if (q >= nq) return;
+  const uint32_t c = cnt[q];
+  if (c < static_cast<uint32_t>(kk) || c > cap) return;
+  const unsigned long long* l = lists + q * cap;
+  const float vU = warp_kth_upper_bound_of(
+      [&](int i) { return key_f32(static_cast<uint32_t>(l[i] >> 32)); }, static_cast<int>(c),
+      static_cast<uint32_t>(kk), s_hist[warp], lane);
+  const float eps = tc_rank_eps(sqrtf(qn[q]), sqrtf(xmax2), rows_i8 != 0);
+  float t = vU + 2.0f * eps;
+  t = t + fabsf(t) * 1e-6f;
+  if (lane == 0 && t == t && t < thr[q]) thr[q] = t;
+}
+
 // radius search: thr[q] in score units so that every row whose exact distance can be <= radius passes the filter
 //   SqL2: d <= r  <=>  (d - |q|^2)/2 <= (r - |q|^2)/2;  L2: d <= r^2;  Dot: -q.x <= r
 __global__ void bf_radius_thr_kernel(const float* __restrict__ qn, float xmax2, float radius, int measure, size_t nq,
@@ -255,6 +279,8 @@ __global__ void bf_overflow_kernel(const uint32_t* __restrict__ cnt, size_t nq, 
 constexpr size_t kTcQTile = 4096;      // queries per tensor-core chunk
 constexpr size_t kTcSampleTiles = 128; // 128-row tiles in the threshold sample (16384 rows)
 constexpr size_t kTcCap = 4096;        // candidate list capacity per query
+constexpr size_t kTcTwoPassTiles = 256;  // two FILTER passes from 32768 rows on
+constexpr size_t kTcTwoPassMaxK = 512;    // ... and while the prefix lists can be expected to hold kk entries
 
 struct BfCore {
   int device = 0;
@@ -448,7 +474,20 @@ struct BfCore {
     p.thr = thr;
     p.cand = lists;
     p.cand_cnt = cnt;
-    SCANN_TRY(launch_tc_scores(p, s));  // c. all rows, survivors into the lists
+    // c. all rows, survivors into the lists — in two passes when the data is large: the first eighth of the rows under
+    // the sample's bound, then the rest under the bound its survivors give (4x fewer survivors per query at C2, and the
+    // FILTER epilogue's time is what its survivors cost)
+    const size_t pre_tiles = (tiles >= kTcTwoPassTiles && kk <= kTcTwoPassMaxK) ? tiles / 8 : 0;
+    if (pre_tiles > 0) {
+      p.nrows = pre_tiles * 128;
+      SCANN_TRY(launch_tc_scores(p, s));
+      bf_tighten_kernel<<<static_cast<unsigned>((nqc + 7) / 8), 256, 0, s>>>(
+          lists, cnt, static_cast<uint32_t>(kTcCap), static_cast<int>(kk), qn, xmax2, nqc, i8 ? 1 : 0, thr);
+      SCANN_CUDA(cudaGetLastError());
+      p.row0 = pre_tiles * 128;
+      p.nrows = rpad - pre_tiles * 128;
+    }
+    SCANN_TRY(launch_tc_scores(p, s));
     bf_overflow_kernel<<<static_cast<unsigned>((nqc + 255) / 256), 256, 0, s>>>(cnt, nqc, kTcCap, flag);
     SCANN_CUDA(cudaMemcpyAsync(h_flag, flag, 4, cudaMemcpyDeviceToHost, s));
     // d. exact re-score (harmless if a list overflowed: the outputs are rewritten by the legacy chunk)

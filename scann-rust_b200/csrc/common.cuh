@@ -397,12 +397,12 @@ __device__ int block_topr_sorted_grouped(Gen gen, int n, int R, uint64_t* buf, u
 // value ends at the returned edge (>= that value; the slack covers the rounding of the bucket arithmetic).  Entries
 // that are NaN or +inf land in the last bucket; the result is +inf when the need-th smallest lies there.  Three passes
 // over the row (L1/L2 resident), one of them with shared-memory atomics.  hist: 256 u32 private to the warp.
-__device__ __forceinline__ float warp_kth_upper_bound(const float* __restrict__ row, int n, uint32_t need,
-                                                      uint32_t* hist, int lane) {
+template <class Get>  // get(i) = the i-th value, i in [0, n)
+__device__ __forceinline__ float warp_kth_upper_bound_of(Get get, int n, uint32_t need, uint32_t* hist, int lane) {
   const float inf = __int_as_float(0x7F800000);
   float mn = inf, mx = -inf;
   for (int i = lane; i < n; i += 32) {
-    const float v = row[i];
+    const float v = get(i);
     mn = fminf(mn, v);
     if (v < inf) mx = fmaxf(mx, v);
   }
@@ -418,7 +418,7 @@ __device__ __forceinline__ float warp_kth_upper_bound(const float* __restrict__ 
   for (int j = 0; j < 8; ++j) hist[lane + 32 * j] = 0;
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
-    const float v = row[i];
+    const float v = get(i);
     int b = 255;
     if (v < inf) b = min(254, max(0, static_cast<int>((v - mn) * scale)));
     atomicAdd(&hist[b], 1u);
@@ -457,6 +457,10 @@ __device__ __forceinline__ float warp_kth_upper_bound(const float* __restrict__ 
   __syncwarp();
   if (bL >= 255) return inf;
   return mn + static_cast<float>(bL + 1) * width * 1.00001f + (fabsf(mn) + fabsf(mx)) * 1e-6f;
+}
+__device__ __forceinline__ float warp_kth_upper_bound(const float* __restrict__ row, int n, uint32_t need,
+                                                      uint32_t* hist, int lane) {
+  return warp_kth_upper_bound_of([&](int i) { return row[i]; }, n, need, hist, lane);
 }
 
 #endif  // __CUDACC__
