@@ -422,7 +422,16 @@ struct BfCore {
 
   // ---- tensor-core chunk: steps a-d of the file header.  *overflow = 1 when some list overflowed (outputs are then
   // not written and the caller runs legacy_chunk).  Synchronises the stream (the overflow flag is read on the host).
-  size_t tc_sample_tiles() const { return std::min<size_t>(kTcSampleTiles, tc_rows_pad(n) / 128); }
+  // the threshold sample is every stride-th 128-row tile over the WHOLE row range (a stride rounded down left the last
+  // rows of the array unsampled: sorted data then has its best rows outside the sample and the lists overflow)
+  size_t tc_sample_stride() const {
+    const size_t tiles = tc_rows_pad(n) / 128;
+    return std::max<size_t>(1, (tiles + kTcSampleTiles - 1) / kTcSampleTiles);
+  }
+  size_t tc_sample_tiles() const {
+    const size_t tiles = tc_rows_pad(n) / 128, stride = tc_sample_stride();
+    return (tiles + stride - 1) / stride;  // <= kTcSampleTiles; tile (tc_sample_tiles() - 1) * stride is the last one hit
+  }
   size_t tc_need(size_t nqc, size_t kk) const {
     const size_t qpad = tc_queries_pad(nqc, dim);
     return Workspace::padded(qpad * tc_kpad(dim) * 2) + Workspace::padded(qpad * 4) +
@@ -450,7 +459,7 @@ struct BfCore {
     p.hx = hx.p;
     p.row0 = 0;
     p.nrows = scols;
-    p.tile_stride = tiles / stiles;  // >= 1; the sample is every tile_stride-th 128-row tile
+    p.tile_stride = tc_sample_stride();  // >= 1; the sample is every tile_stride-th 128-row tile
     p.filter = false;
     p.dense = dense;
     p.ld = scols;

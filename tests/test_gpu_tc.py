@@ -101,6 +101,62 @@ def test_bf_clustered_rows_sorted_by_cluster(gpu_lib, oracle):
     assert bf.path_stats()[0] >= 1
 
 
+@pytest.mark.parametrize("measure", ["SquaredL2", "DotProduct"])
+@pytest.mark.parametrize("order,k", [("best_last", 10), ("best_first", 10), ("best_last", 100), ("dups_across", 10),
+                                     ("far_prefix", 10)])
+def test_bf_two_pass_filter_row_orders(gpu_lib, oracle, measure, order, k):
+    # From 32768 rows on the FILTER runs in two passes: the first eighth of the rows under the sample's bound, the rest
+    # under the bound derived from the prefix survivors (brute_force.cu, bf_tighten_kernel).  Row orders that make the
+    # prefix unrepresentative must not cost exactness: all good rows at the end (the prefix bound is loose), all at the
+    # start (the tightened bound is as tight as it gets), exact duplicates of the best row on both sides of the cut,
+    # and a prefix so far from the queries that its lists may hold fewer than k rows.
+    n, dim, nq = 60_000, 64, 96
+    x = helpers.gaussian(n, dim, 21)
+    u = helpers.gaussian(1, dim, 22)[0]
+    u /= np.linalg.norm(u)
+    q = (np.float32(3.0) * u[None, :] + np.float32(0.3) * helpers.gaussian(nq, dim, 23)).astype(np.float32)
+    proj = x @ u
+    if order == "best_last":
+        db = x[np.argsort(proj, kind="stable")]
+    elif order == "best_first":
+        db = x[np.argsort(-proj, kind="stable")]
+    elif order == "dups_across":
+        db = x.copy()
+        db[:50] = np.float32(3.0) * u
+        db[-50:] = np.float32(3.0) * u
+    else:  # far_prefix: the first eighth is a tight far-away cluster
+        db = x.copy()
+        db[: n // 8] = np.float32(-40.0) * u[None, :] + np.float32(0.01) * helpers.gaussian(n // 8, dim, 24)
+    db = np.ascontiguousarray(db, np.float32)
+    m = gpu_lib.DistanceMeasure[measure]
+    om = {"SquaredL2": oracle.SQL2, "DotProduct": oracle.DOT}[measure]
+    bf = gpu_lib.BruteForceSearcher(db, m)
+    ids, dists, counts = bf.search_batched(q, k)
+    assert bf.path_stats() == (1, 0), "the tcgen05 path did not answer this batch"
+    rc, oids, odists, ocounts = oracle.bf_search(db, q, k, om, nthreads=8)
+    assert (counts == ocounts).all()
+    assert (dists.view(np.uint32) == odists.view(np.uint32)).all()
+    compared, mism = helpers.ids_equal_away_from_ties(ids, dists, oids, odists, counts, rel_gap=0.0)
+    assert mism == 0
+
+
+def test_sq8_two_pass_filter_best_rows_last(gpu_lib, oracle):
+    n, dim, nq, k = 50_000, 128, 64, 10
+    x = helpers.gaussian(n, dim, 31)
+    u = helpers.gaussian(1, dim, 32)[0]
+    u /= np.linalg.norm(u)
+    q = (np.float32(3.0) * u[None, :] + np.float32(0.3) * helpers.gaussian(nq, dim, 33)).astype(np.float32)
+    db = np.ascontiguousarray(x[np.argsort(x @ u, kind="stable")], np.float32)
+    ocodes, ocal = oracle.sq8_quantize(db)
+    s = gpu_lib.ScalarQuantizedBruteForceSearcher.from_quantized(ocodes, float(ocal[2]), gpu_lib.DistanceMeasure.DotProduct)
+    ids, dists, counts = s.search_batched(q, k)
+    assert s.path_stats() == (1, 0)
+    rc, oids, odists, ocounts = oracle.sq8_search(ocodes, float(ocal[2]), q, k, oracle.DOT, nthreads=8)
+    assert (dists.view(np.uint32) == odists.view(np.uint32)).all()
+    compared, mism = helpers.ids_equal_away_from_ties(ids, dists, oids, odists, counts, rel_gap=0.0)
+    assert mism == 0
+
+
 def test_bf_list_overflow_falls_back(gpu_lib, oracle):
     # 9000 identical rows: every row passes any threshold -> the lists (cap 4096) overflow -> CUDA-core path
     db = np.tile(helpers.gaussian(1, 32, 1), (9000, 1)).astype(np.float32)
