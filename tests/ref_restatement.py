@@ -225,3 +225,105 @@ def sq8_quantize(db, num_std_devs=3.0, bits=8):
             qi = min(max(qi, 0), levels)
             codes[i, j] = np.array(qi, np.int64).astype(np.uint8).view(np.int8)  # `as i8` wraps 128..255 to -128..-1
     return codes, (lo, hi, scale, inv)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The AVX2 + FMA distance kernels, lane for lane, with the fused multiply-add evaluated EXACTLY (rational arithmetic, one
+# rounding to f32) — written from the Rust source:
+#   horizontal_sum_f32_avx2                       src/simd/x86.rs:31-44   ((v0+v4) + (v1+v5)) + ((v2+v6) + (v3+v7))
+#   dot_product_avx2 / squared_l2_avx2            src/simd/x86.rs:72-96, 139-165
+#   one_to_many_{dot_product,squared_l2}_avx2     src/simd/x86.rs:195-346 (3 / 4 rows in flight: same arithmetic per row)
+#   one_to_many_int8_float_{dot_product,squared_l2}_avx2   src/distance_measures/one_to_many_asymmetric.rs:77-144, 207-261
+#   horizontal_sum_avx (hadd, hadd)               src/distance_measures/one_to_many_asymmetric.rs:383-399 (same tree)
+from fractions import Fraction  # noqa: E402
+
+
+def f32_from_fraction(fr):
+    """Round an exact rational to the nearest f32, ties to even (normal and subnormal range; overflow -> inf)."""
+    if fr == 0:
+        return F(0.0)
+    neg = fr < 0
+    a = -fr if neg else fr
+    e = a.numerator.bit_length() - a.denominator.bit_length()
+    if Fraction(2) ** e > a:
+        e -= 1
+    if Fraction(2) ** (e + 1) <= a:
+        e += 1
+    qexp = max(e, -126) - 23  # exponent of the last mantissa bit
+    scaled = a / (Fraction(2) ** qexp)
+    n = scaled.numerator // scaled.denominator
+    rem = scaled - n
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (n & 1)):
+        n += 1
+    if n * Fraction(2) ** qexp >= Fraction(2) ** 128:
+        v = float("inf")
+    else:
+        v = float(Fraction(n) * Fraction(2) ** qexp)  # <= 25 significant bits: exact in f64
+    return F(-v if neg else v)
+
+
+def fma32(a, b, c):
+    """_mm256_fmadd_ps per lane: a * b + c with ONE rounding"""
+    a, b, c = F(a), F(b), F(c)
+    if not (np.isfinite(a) and np.isfinite(b) and np.isfinite(c)):
+        return F(a * b + c)
+    return f32_from_fraction(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+
+def hsum8(v):
+    s = [F(v[i] + v[i + 4]) for i in range(4)]      # extractf128 + add_ps
+    return F(F(s[0] + s[1]) + F(s[2] + s[3]))       # movehdup/add, movehl/add_ss  (= hadd, hadd)
+
+
+def _row_f32(q, x, measure):
+    dim = len(q)
+    chunks = dim // 8
+    acc = [F(0.0)] * 8
+    for c in range(chunks):
+        for l in range(8):
+            j = 8 * c + l
+            if measure == "dot":
+                acc[l] = fma32(q[j], x[j], acc[l])
+            else:
+                d = F(F(q[j]) - F(x[j]))
+                acc[l] = fma32(d, d, acc[l])
+    r = hsum8(acc)
+    for j in range(8 * chunks, dim):  # scalar tail: multiply, then add (Rust does not contract)
+        if measure == "dot":
+            r = F(r + F(F(q[j]) * F(x[j])))
+        else:
+            d = F(F(q[j]) - F(x[j]))
+            r = F(r + F(d * d))
+    return F(-r) if measure == "dot" else r
+
+
+def one_to_many_f32(q, db, measure):
+    return np.array([_row_f32(q, x, measure) for x in db], np.float32)
+
+
+def one_to_many_i8(q, db_i8, inv_mul, measure):
+    out = []
+    inv = F(inv_mul)
+    for x in db_i8:
+        dim = len(q)
+        chunks = dim // 8
+        acc = [F(0.0)] * 8
+        for c in range(chunks):
+            for l in range(8):
+                j = 8 * c + l
+                xs = F(F(int(x[j])) * inv)  # cvtepi8 -> cvtepi32_ps -> mul_ps: sign-extended, no offset
+                if measure == "dot":
+                    acc[l] = fma32(q[j], xs, acc[l])
+                else:
+                    d = F(F(q[j]) - xs)
+                    acc[l] = fma32(d, d, acc[l])
+        r = hsum8(acc)
+        for j in range(8 * chunks, dim):
+            xs = F(F(int(x[j])) * inv)
+            if measure == "dot":
+                r = F(r + F(F(q[j]) * xs))
+            else:
+                d = F(F(q[j]) - xs)
+                r = F(r + F(d * d))
+        out.append(F(-r) if measure == "dot" else r)
+    return np.array(out, np.float32)

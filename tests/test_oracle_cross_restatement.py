@@ -80,3 +80,60 @@ def test_oracle_sq8_quantiser_equals_python_restatement(oracle, seed, scale):
     assert (np.array([lo, hi, sc, inv], np.float32).view(np.uint32) == cal.view(np.uint32)).all()
     assert (codes == pc).all()
     assert codes.min() < 0  # values above 127 wrap to negative i8, as in the reference
+
+
+# ----------------------------------------------------------------------------- the AVX2 + FMA distance kernels
+def test_exact_fma_helper_rounds_like_ieee():
+    # against float64 evaluation where that is exact enough to decide, and hand-made halfway cases
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        a, b, c = (np.float32(v) for v in rng.standard_normal(3) * 10.0 ** rng.integers(-3, 4))
+        exact = rr.Fraction(float(a)) * rr.Fraction(float(b)) + rr.Fraction(float(c))
+        got = rr.fma32(a, b, c)
+        lo, hi = np.nextafter(got, np.float32(-np.inf)), np.nextafter(got, np.float32(np.inf))
+        err = abs(rr.Fraction(float(got)) - exact)
+        assert err <= abs(rr.Fraction(float(lo)) - exact) and err <= abs(rr.Fraction(float(hi)) - exact)
+    one, ulp = np.float32(1.0), np.float32(2.0 ** -23)
+    # 1 + ulp/2 is a tie: to even (1.0); 1 + 3 ulp/2 is a tie: to even (1 + 2 ulp)
+    assert rr.fma32(np.float32(0.5), ulp, one) == one
+    assert rr.fma32(np.float32(1.5), ulp, one) == np.float32(1.0 + 2.0 ** -22)
+    # a product that the unfused sequence rounds differently: (1 + 2^-12)^2 - 1 = 2^-11 + 2^-24 (the square's 2^-24 is a
+    # tie at 1.0's precision and is rounded away before the subtraction)
+    x = np.float32(1.0 + 2.0 ** -12)
+    fused, unfused = rr.fma32(x, x, np.float32(-1.0)), np.float32(np.float32(x * x) - np.float32(1.0))
+    assert unfused == np.float32(2.0 ** -11) and fused == np.float32(2.0 ** -11 + 2.0 ** -24)
+    assert rr.f32_from_fraction(rr.Fraction(1, 2 ** 149)) == np.float32(1e-45)  # smallest subnormal
+
+
+@pytest.mark.parametrize("dim", [1, 7, 8, 9, 16, 33, 96, 100])
+@pytest.mark.parametrize("measure", ["dot", "sql2"])
+def test_oracle_one_to_many_equals_exact_fma_restatement(oracle, dim, measure):
+    # 11 rows: the 3-row (Dot) and 4-row (SqL2) batches AND their remainder rows; magnitudes spread over six decades so
+    # that a different summation order or an unfused multiply-add would change low bits
+    rng = np.random.default_rng(100 + dim)
+    q = (rng.standard_normal(dim) * 10.0 ** rng.integers(-3, 3, dim)).astype(np.float32)
+    db = (rng.standard_normal((11, dim)) * 10.0 ** rng.integers(-3, 3, (11, dim))).astype(np.float32)
+    om = oracle.DOT if measure == "dot" else oracle.SQL2
+    got = oracle.one_to_many(q, db, om)
+    want = rr.one_to_many_f32(q, db, measure)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    # and the order matters on this data: a plain left-to-right f32 sum differs somewhere
+    if dim >= 16:
+        naive = np.array([np.float32(sum((np.float32(a) * np.float32(b) if measure == "dot" else
+                                          np.float32(np.float32(a - b) * np.float32(a - b))) for a, b in zip(q, x)))
+                          for x in db], np.float32)
+        naive = -naive if measure == "dot" else naive
+        assert (naive.view(np.uint32) != want.view(np.uint32)).any()
+
+
+@pytest.mark.parametrize("dim", [5, 8, 24, 43, 128])
+@pytest.mark.parametrize("measure", ["dot", "sql2"])
+def test_oracle_int8_one_to_many_equals_exact_fma_restatement(oracle, dim, measure):
+    rng = np.random.default_rng(200 + dim)
+    q = (rng.standard_normal(dim) * 3).astype(np.float32)
+    db = rng.integers(-128, 128, (9, dim), dtype=np.int8)
+    inv = np.float32(0.0234375 * 1.37)
+    om = oracle.DOT if measure == "dot" else oracle.SQL2
+    got = oracle.one_to_many_i8(q, db, float(inv), om)
+    want = rr.one_to_many_i8(q, db, inv, measure)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
