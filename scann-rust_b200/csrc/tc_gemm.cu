@@ -44,8 +44,9 @@ constexpr int kTcTmemCols = 512;
 // FILTER staging: every epilogue warp queues its survivors (row, lane) in shared memory and flushes the queue with
 // one global atomic per entry, all lanes at once — a survivor costs a shared-memory atomic instead of a serialised
 // round trip to L2 (at ~1 survivor per 1024 scores nearly every 32x32 chunk has one).
-constexpr int kWqCap = 192;                          // entries per warp queue
-constexpr int kWqBytes = kWqCap * 8 + kWqCap + 16;   // (score key, row) u64, lanes u8 (+ pad)
+constexpr int kWqLane = 8;                           // queue slots of ONE lane (= one query) of an epilogue warp
+constexpr int kWqFlushAt = 6;                        // the warp writes its queues out when some lane holds this many
+constexpr int kWqBytes = kWqLane * 32 * 8 + 16;      // [slot][lane] (row, raw w bits) (+ pad)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -108,18 +109,10 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// shared-memory queue operations by 32-bit shared address (a pointer that has been through a non-inlined call is generic
-// to the compiler, and generic atomics / stores are what it then emits)
-__device__ __forceinline__ uint32_t atoms_inc(uint32_t saddr) {
-  uint32_t r;
-  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(saddr) : "memory");
-  return r;
-}
+// shared-memory queue store by 32-bit shared address (a pointer that has been through a non-inlined call is generic to
+// the compiler, and generic stores are what it then emits)
 __device__ __forceinline__ void sts_v2(uint32_t saddr, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t elect_one() {  // one lane of the (converged) warp
   uint32_t pred;
@@ -156,24 +149,24 @@ struct TcArgs {
                             // skipped (padding rows then score 0 and may enter a list: the re-score ignores ids >= n)
 };
 
-// FILTER survivors.  A hit is queued by its own lane (one shared-memory atomic for the slot) as (raw w bits, row); the
-// warp looks at its queue once per tile and writes it out when it is half full.  Both routines are single copies,
-// called: inlined at every use they were a fifth of the epilogue's code, and the epilogue was stalling on instruction
-// fetch (ncu: stall_no_inst on the filter lines of a 45 KB loop body).
+// FILTER survivors.  A lane of an epilogue warp is one query, and it queues its hits in slots of its OWN (slot-major
+// shared memory, no atomics, nothing warp-wide: a hit costs a compare, an address and a store).  Once per tile the warp
+// votes; when some lane holds kWqFlushAt entries every lane reserves its list slots with ONE atomic and writes its
+// entries out.  Both routines are single copies, called: inlined at every use they were a fifth of the epilogue's code.
 __device__ __forceinline__ unsigned long long tc_list_entry(uint32_t w_bits, uint32_t row) {
   return (static_cast<unsigned long long>(f32_key(-__uint_as_float(w_bits))) << 32) | row;  // v = -w
 }
 __device__ __noinline__ void tc_flush(uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ cand,
-                                      uint32_t cap, uint32_t qwarp, const uint2* wq_rows, const uint8_t* wq_lanes,
-                                      uint32_t nw) {
-  for (uint32_t i = threadIdx.x & 31u; i < nw; i += 32) {
-    const uint32_t qq = qwarp + wq_lanes[i];
-    const uint2 e = wq_rows[i];
-    const uint32_t slot = atomicAdd(cand_cnt + qq, 1u);
-    if (slot < cap) cand[static_cast<size_t>(qq) * cap + slot] = tc_list_entry(e.y, e.x);
+                                      uint32_t cap, uint32_t q, uint32_t wq_lane_s, uint32_t n) {
+  if (n == 0) return;
+  const uint32_t base = atomicAdd(cand_cnt + q, n);
+  for (uint32_t i = 0; i < n && base + i < cap; ++i) {
+    uint32_t row, bits;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(row), "=r"(bits) : "r"(wq_lane_s + 256u * i) : "memory");
+    cand[static_cast<size_t>(q) * cap + base + i] = tc_list_entry(bits, row);
   }
 }
-// the queue is full (more than half a queue of hits in one tile): straight to the query's list
+// a lane's slots are full (more than kWqLane - kWqFlushAt hits of one query in one tile): straight to the query's list
 __device__ __noinline__ void tc_emit_direct(uint32_t* __restrict__ cand_cnt, unsigned long long* __restrict__ cand,
                                             uint32_t cap, uint32_t q, uint32_t w_bits, uint32_t row) {
   const uint32_t slot = atomicAdd(cand_cnt + q, 1u);
@@ -309,12 +302,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     constexpr int ncols = MT == 2 ? kTcBN / 2 : kTcBN / 4;
     const int c0 = (MT == 2 ? (grp & 1) : grp) * ncols;
     constexpr int nchunks = ncols / 32;
-    uint2* const wq_rows = reinterpret_cast<uint2*>(wq_base + e * kWqBytes);  // (row, raw w bits)
-    uint8_t* const wq_lanes = reinterpret_cast<uint8_t*>(wq_rows + kWqCap);
-    uint32_t* const wq_cnt = reinterpret_cast<uint32_t*>(wq_lanes + kWqCap);
-    const uint32_t wq_rows_s = smem_u32(wq_rows), wq_lanes_s = smem_u32(wq_lanes), wq_cnt_s = smem_u32(wq_cnt);
-    if (lane == 0) *wq_cnt = 0;
-    __syncwarp();
+    const uint32_t wq_lane_s = smem_u32(wq_base + e * kWqBytes) + 8u * static_cast<uint32_t>(lane);  // slot i: + 256 i
+    uint32_t wq_n = 0;  // entries this lane holds
     uint32_t as = 0, asphase = 0;
     for (uint32_t u = blockIdx.x; u < total_units; u += gridDim.x) {
       const uint32_t qt = u % a.q_tiles, nu = u / a.q_tiles;
@@ -322,18 +311,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const uint32_t t1 = min(t0 + a.tiles_per_unit, a.n_tiles);
       const uint32_t q = (qt * MT + mt) * kTcBM + quad * 32 + lane;
       const bool qvalid = q < a.nq;
-      const uint32_t qwarp = q - lane;  // first query of this warp in the unit
       float nthr = __int_as_float(0x7F800000);  // +inf: nothing passes
       if (a.filter && qvalid) nthr = -a.thr[q];
-      // queue whatever the warp holds (all lanes; called at points where the warp is converged)
-      auto flush = [&]() {
-        __syncwarp();
-        const uint32_t nw = min(*const_cast<volatile uint32_t*>(wq_cnt), static_cast<uint32_t>(kWqCap));
-        if (nw) tc_flush(a.cand_cnt, a.cand, a.cap, qwarp, wq_rows, wq_lanes, nw);
-        __syncwarp();
-        if (lane == 0) *wq_cnt = 0;
-        __syncwarp();
-      };
       for (uint32_t t = t0; t < t1; ++t) {
         if (!a.no_hx && t + 1 < t1 && lane < ncols / 32)  // pull the next tile's hx lines into L1 while this tile is filtered
           asm volatile("prefetch.global.L1 [%0];" ::"l"(a.hx + a.row0 + (t + 1) * a.tile_stride * kTcBN + c0 + lane * 32));
@@ -395,10 +374,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               for (int j = 0; j < 8; ++j) {
                 if (w[8 * g8 + j] >= nthr) {
                   const uint32_t row = row_tile + cc + 8 * g8 + j;
-                  const uint32_t sl = atoms_inc(wq_cnt_s);
-                  if (sl < static_cast<uint32_t>(kWqCap)) {
-                    sts_v2(wq_rows_s + 8u * sl, row, __float_as_uint(w[8 * g8 + j]));
-                    sts_u8(wq_lanes_s + sl, static_cast<uint32_t>(lane));
+                  if (wq_n < static_cast<uint32_t>(kWqLane)) {
+                    sts_v2(wq_lane_s + 256u * wq_n, row, __float_as_uint(w[8 * g8 + j]));
+                    ++wq_n;
                   } else {
                     tc_emit_direct(a.cand_cnt, a.cand, a.cap, q, __float_as_uint(w[8 * g8 + j]), row);
                   }
@@ -407,16 +385,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
           }
         }
-        if (a.filter) {
-          __syncwarp();
-          if (*const_cast<volatile uint32_t*>(wq_cnt) > kWqCap / 2) flush();  // warp-uniform
+        if (a.filter && __any_sync(0xFFFFFFFFu, wq_n >= static_cast<uint32_t>(kWqFlushAt))) {
+          tc_flush(a.cand_cnt, a.cand, a.cap, q, wq_lane_s, wq_n);
+          wq_n = 0;
         }
         if (++as == 2) {
           as = 0;
           asphase ^= 1;
         }
       }
-      if (a.filter) flush();  // the queue's lane -> query mapping changes with the unit
+      if (a.filter) {  // the lane -> query mapping changes with the unit
+        tc_flush(a.cand_cnt, a.cand, a.cap, q, wq_lane_s, wq_n);
+        wq_n = 0;
+      }
     }
   }
 
