@@ -19,12 +19,17 @@
 //   b. thr[q] = v_k + 2*eps_q, eps_q = a rigorous bound on |v - exact| (bf16 operand rounding: 2^-7 |q| max|x| for f32 rows, 2^-8 for int8 rows,
 //      plus f32 accumulation slack).  Any row with v > thr is beaten by the k sample rows whatever the
 //      rounding did, so it cannot be among the exact top-k.
-//   c. FILTER pass over all rows appends the rows with v <= thr to per-query lists (a few hundred to ~1-2k).
+//   c. FILTER pass over all rows appends the rows with v <= thr to per-query lists.  From 32768 rows on it runs in two
+//      passes: the first eighth of the rows under the sample's bound, then bf_tighten_kernel replaces the bound by
+//      (kk-th smallest score among the prefix survivors) + 2*eps — the same argument with real rows in place of sample
+//      rows — and the other seven eighths run under it (2.8k -> a few hundred survivors per query at C2).
 //   d. rescore_lists_kernel: second certification inside the list (only the rows within 2*eps of the list's k-th
-//      smallest score can be in the top-k: k + a few tens of the ~900), exact distances of those in the reference's
-//      AVX2 order, (distance, id) order.
+//      smallest score can be in the top-k: k + a few tens), exact distances of those in the reference's AVX2 order,
+//      (distance, id) order.
 // Results are therefore the exact top-k by the reference's own f32 distances, not "top-k up to GEMM rounding".
-// A list overflow (cap 4096: huge k, or massively duplicated rows) sends that query chunk through steps 1-3.
+// A list overflow (cap 4096: huge k, or massively duplicated rows) sends that query chunk through steps 1-3.  Steps 1-3
+// carry k + 32 candidates ranked by an f32 GEMM score without an error-bound argument: exact unless more than 32 rows
+// lie within that GEMM's rounding error of the k-th distance.
 #include <string.h>
 
 #include <algorithm>
