@@ -327,3 +327,19 @@ def one_to_many_i8(q, db_i8, inv_mul, measure):
                 r = F(r + F(d * d))
         out.append(F(-r) if measure == "dot" else r)
     return np.array(out, np.float32)
+
+
+def reorder_results(raw, q, cand_ids, k, measure):
+    """TreeXHybridSearcher::reorder_results (src/tree_x_hybrid/mod.rs:342-364): exact distance of every candidate by the
+    single-pair kernel (DistanceMeasure::distance -> squared_l2_avx2 / -dot_product_avx2, src/distance_measures/mod.rs:70-81,
+    one_to_one.rs:156-214,464-469 — the same lane arithmetic as the one-to-many kernels), candidates whose id has no row
+    are skipped (dataset.get), stable sort by distance only, truncate."""
+    ex = []
+    for i in cand_ids:
+        if int(i) < len(raw):
+            d = _row_f32(q, raw[int(i)], "dot" if measure == "dot" else "sql2")
+            if measure == "l2":
+                d = F(np.sqrt(d))
+            ex.append((int(i), d))
+    ex.sort(key=lambda t: t[1])  # sort_by(partial_cmp): stable, ties keep the candidate (= approximate) order
+    return ex[:k]

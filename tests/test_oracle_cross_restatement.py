@@ -137,3 +137,32 @@ def test_oracle_int8_one_to_many_equals_exact_fma_restatement(oracle, dim, measu
     got = oracle.one_to_many_i8(q, db, float(inv), om)
     want = rr.one_to_many_i8(q, db, inv, measure)
     assert (got.view(np.uint32) == want.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("measure", ["sql2", "dot"])
+@pytest.mark.parametrize("n,dim,K,S,L,R,k,seed", [(1200, 16, 6, 8, 3, 30, 10, 11), (700, 24, 5, 12, 5, 12, 12, 12)])
+def test_oracle_tree_ah_end_to_end_equals_python_restatement(oracle, measure, n, dim, K, S, L, R, k, seed):
+    # the whole TreeXHybridSearcher::search of the restatement (partition -> residual LUT16 scan -> per-leaf
+    # FastTopNeighbors -> stable merge -> exact reorder with the AVX2 + FMA single-pair kernel -> stable sort -> top-k)
+    # against the oracle's final (id, distance) lists, bit for bit and in order; the grid makes exact distance ties real
+    x, _ = helpers.clustered(n, dim, 8, 0.4, seed, normalize=False)
+    x = (np.round(x * 2) / 2).astype(np.float32)
+    idx = helpers.build_index(oracle, x, K, S, seed=seed, iters=4)
+    q = (x[::max(1, n // 8)][:8] + np.float32(0.25)).astype(np.float32)
+    om = oracle.SQL2 if measure == "sql2" else oracle.DOT
+    rc, oids, odists, ocounts = oracle.treex_search(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"],
+                                                    idx["packed"], x, q, L, R, k, lut16=True, reorder_measure=om)
+    assert rc == 0
+    ties = 0
+    for i in range(len(q)):
+        cand = rr.approx_candidates(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"], q[i],
+                                    L, R)
+        want = rr.reorder_results(x, q[i], [j for j, _ in cand], k, measure)
+        c = int(ocounts[i])
+        assert c == len(want)
+        wd = np.array([d for _, d in want], np.float32)
+        wi = np.array([j for j, _ in want], np.uint32)
+        assert (odists[i, :c].view(np.uint32) == wd.view(np.uint32)).all(), "exact distances differ"
+        assert (oids[i, :c] == wi).all(), "ids / tie order differ"
+        ties += int((np.diff(wd) == 0).sum())
+    assert ties > 0 or measure == "dot", "the SqL2 case was meant to contain exact distance ties"
