@@ -343,3 +343,27 @@ def reorder_results(raw, q, cand_ids, k, measure):
             ex.append((int(i), d))
     ex.sort(key=lambda t: t[1])  # sort_by(partial_cmp): stable, ties keep the candidate (= approximate) order
     return ex[:k]
+
+
+def bf_search(db, q, k, measure):
+    """BruteForceSearcher::search_impl (src/brute_force/searcher.rs:96-139): all distances by the one-to-many kernel (sqrt
+    pass for L2), N pushes through TopK in index order, drain_sorted; k clamped to N (:91)."""
+    d = one_to_many_f32(q, db, "dot" if measure == "dot" else "sql2")
+    if measure == "l2":
+        d = np.sqrt(d).astype(np.float32)
+    t = TopK(min(k, len(db)))
+    for i, v in enumerate(d):
+        t.push(i, v)
+    return t.results()
+
+
+def sq8_search(codes, scale, q, k, measure):
+    """ScalarQuantizedBruteForceSearcher::search_impl (src/brute_force/scalar_quantized.rs:187-246): the int8 one-to-many
+    kernels with inv_multiplier = quantizer.scale(), stride = dim, then TopK as above."""
+    d = one_to_many_i8(q, codes, scale, "dot" if measure == "dot" else "sql2")
+    if measure == "l2":
+        d = np.sqrt(d).astype(np.float32)
+    t = TopK(min(k, len(codes)))
+    for i, v in enumerate(d):
+        t.push(i, v)
+    return t.results()

@@ -166,3 +166,45 @@ def test_oracle_tree_ah_end_to_end_equals_python_restatement(oracle, measure, n,
         assert (oids[i, :c] == wi).all(), "ids / tie order differ"
         ties += int((np.diff(wd) == 0).sum())
     assert ties > 0 or measure == "dot", "the SqL2 case was meant to contain exact distance ties"
+
+
+@pytest.mark.parametrize("measure", ["sql2", "l2", "dot"])
+@pytest.mark.parametrize("n,dim,k", [(300, 12, 10), (150, 20, 40), (7, 5, 10)])
+def test_oracle_brute_force_end_to_end_equals_python_restatement(oracle, measure, n, dim, k):
+    # BruteForceSearcher::search: one-to-many kernel -> N heap pushes -> drain_sorted.  Grid data: many exactly equal
+    # distances, so the ids the heap keeps at the cut-off and the ORDER inside ties are exercised; k > n is clamped
+    rng = np.random.default_rng(n + dim)
+    db = rng.integers(-2, 3, (n, dim)).astype(np.float32)
+    q = rng.integers(-2, 3, (6, dim)).astype(np.float32)
+    om = {"sql2": oracle.SQL2, "l2": oracle.L2, "dot": oracle.DOT}[measure]
+    rc, oids, odists, ocounts = oracle.bf_search(db, q, k, om, nthreads=2)
+    assert rc == 0
+    ties = 0
+    for i in range(len(q)):
+        want = rr.bf_search(db, q[i], k, measure)
+        c = int(ocounts[i])
+        assert c == len(want) == min(k, n)
+        wd = np.array([d for _, d in want], np.float32)
+        assert (odists[i, :c].view(np.uint32) == wd.view(np.uint32)).all()
+        assert oids[i, :c].tolist() == [j for j, _ in want], "ids / tie order differ"
+        ties += int((np.diff(wd) == 0).sum())
+    assert ties > 0
+
+
+@pytest.mark.parametrize("measure", ["sql2", "dot"])
+def test_oracle_sq8_search_end_to_end_equals_python_restatement(oracle, measure):
+    # quantiser (sequential f64 statistics, 3-sigma clipping, wrap to i8) -> sign-extending int8 kernels -> TopK
+    rng = np.random.default_rng(77)
+    db = (rng.integers(-6, 7, (200, 16)) * 0.25).astype(np.float32)
+    q = (rng.integers(-6, 7, (5, 16)) * 0.25).astype(np.float32)
+    codes, (lo, hi, sc, inv) = rr.sq8_quantize(db)
+    ocodes, ocal = oracle.sq8_quantize(db)
+    assert (codes == ocodes).all() and np.float32(sc).view(np.uint32) == ocal[2].view(np.uint32)
+    om = oracle.SQL2 if measure == "sql2" else oracle.DOT
+    rc, oids, odists, ocounts = oracle.sq8_search(ocodes, float(ocal[2]), q, 10, om, nthreads=2)
+    assert rc == 0
+    for i in range(len(q)):
+        want = rr.sq8_search(codes, sc, q[i], 10, measure)
+        wd = np.array([d for _, d in want], np.float32)
+        assert (odists[i].view(np.uint32) == wd.view(np.uint32)).all()
+        assert oids[i].tolist() == [j for j, _ in want], "ids / tie order differ"
