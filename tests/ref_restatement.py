@@ -367,3 +367,119 @@ def sq8_search(codes, scale, q, k, measure):
     for i, v in enumerate(d):
         t.push(i, v)
     return t.results()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Product-quantisation pieces and the flat AsymmetricHasher, from the Rust source:
+#   SubspaceCodebook::encode / compute_distances   src/hashes/codebook.rs:82-115   (strict '<': lowest code on ties)
+#   Codebook::encode                               src/hashes/codebook.rs:205-216
+#   PackedCodes4Bit::from_codes                    src/hashes/lut16.rs:43-61       (low nibble = even subspace)
+#   LookupTable::from_query / compute_distance     src/hashes/lut.rs:47-82         (sequential f32 sum)
+#   AsymmetricHasher::search / search_with_reordering   src/hashes/hasher.rs:162-229 (exact SqL2 hard-coded for the re-rank)
+def pq_encode(codebook, x):
+    S, C, ds = codebook.shape
+    codes = []
+    for s in range(S):
+        sub = x[s * ds:(s + 1) * ds]
+        best, best_d = 0, F(np.inf)
+        for c in range(C):
+            d = sqdist_seq(sub, codebook[s, c])
+            if d < best_d:
+                best_d, best = d, c
+        codes.append(best)
+    return codes
+
+
+def pack4(point_codes):
+    out = []
+    for i in range(0, len(point_codes), 2):
+        lo = point_codes[i] & 0x0F
+        hi = ((point_codes[i + 1] & 0x0F) << 4) if i + 1 < len(point_codes) else 0
+        out.append(lo | hi)
+    return out
+
+
+def lut_f32(codebook, q):
+    S, C, ds = codebook.shape
+    return [[sqdist_seq(q[s * ds:(s + 1) * ds], codebook[s, c]) for c in range(C)] for s in range(S)]
+
+
+def lut_f32_distance(lut, codes):
+    s = F(0.0)
+    for sub, code in enumerate(codes):
+        s = F(s + lut[sub][int(code)])
+    return s
+
+
+def ah_search(codebook, codes, q, k):
+    lut = lut_f32(codebook, q)
+    top = FastTopNeighbors(k)
+    for i, c in enumerate(codes):
+        top.push(i, lut_f32_distance(lut, c))
+    return top.results()
+
+
+def ah_search_with_reordering(codebook, codes, raw, q, k, pre_reorder_k):
+    cand = ah_search(codebook, codes, q, pre_reorder_k)
+    return reorder_results(raw, q, [i for i, _ in cand], k, "sql2")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The Scann facade's tree modes, from src/scann.rs:215-294 and src/utils/reordering.rs:23-54
+def _measure_distance(q, x, measure):
+    d = _row_f32(q, x, "dot" if measure == "dot" else "sql2")
+    return F(np.sqrt(d)) if measure == "l2" else d
+
+
+def scann_search_partitioned(centers, part_offsets, part_ids, raw, q, L, k, measure):
+    """search_partitioned: members of the L closest partitions in token order, exact distance each by the single-pair
+    kernel, stable sort by distance, truncate"""
+    res = []
+    for leaf in partition(centers, q, L):
+        for idx in part_ids[int(part_offsets[leaf]):int(part_offsets[leaf + 1])]:
+            if int(idx) < len(raw):
+                res.append((int(idx), _measure_distance(q, raw[int(idx)], measure)))
+    res.sort(key=lambda t: t[1])
+    return res[:k]
+
+
+def scann_search_tree_ah(centers, part_offsets, part_ids, codebook, codes_by_id, q, L, k):
+    """search_tree_ah ("variant B"): ONE f32 LUT of the un-residualised query, every member of the L closest partitions
+    scored by LookupTable::compute_distance, stable sort, truncate"""
+    lut = lut_f32(codebook, q)
+    res = []
+    for leaf in partition(centers, q, L):
+        for idx in part_ids[int(part_offsets[leaf]):int(part_offsets[leaf + 1])]:
+            res.append((int(idx), lut_f32_distance(lut, codes_by_id[int(idx)])))
+    res.sort(key=lambda t: t[1])
+    return res[:k]
+
+
+def reordering_helper(raw, q, results, k, measure):
+    """ReorderingHelper::reorder: exact distance of the given results, stable sort, first k"""
+    ex = [(i, _measure_distance(q, raw[i], measure)) for i, _ in results if i < len(raw)]
+    ex.sort(key=lambda t: t[1])
+    return ex[:k]
+
+
+def kmtree_search_leaves(centers, depth, child_begin, child_count, children, q, k):
+    """KMeansTree::search_leaves (src/trees/kmeans_tree.rs:302-355) on a tree flattened in preorder: depth-first, children
+    in stable ascending order of their sequential squared distance, a leaf is always pushed, every level stops descending
+    once 2k leaves are collected, stable sort by distance, first k.  -> [(node, distance, depth)]"""
+    results = []
+
+    def rec(node):
+        d = sqdist_seq(q, centers[node])
+        if int(child_count[node]) == 0:
+            results.append((int(node), d, int(depth[node])))
+            return
+        kids = [int(children[int(child_begin[node]) + i]) for i in range(int(child_count[node]))]
+        order = sorted(((i, sqdist_seq(q, centers[c])) for i, c in enumerate(kids)), key=lambda t: t[1])
+        for i, _ in order:
+            rec(kids[i])
+            if len(results) >= 2 * k:
+                break
+
+    rec(0)
+    results.sort(key=lambda t: t[1])
+    return results[:k]

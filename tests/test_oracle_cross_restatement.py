@@ -208,3 +208,119 @@ def test_oracle_sq8_search_end_to_end_equals_python_restatement(oracle, measure)
         wd = np.array([d for _, d in want], np.float32)
         assert (odists[i].view(np.uint32) == wd.view(np.uint32)).all()
         assert oids[i].tolist() == [j for j, _ in want], "ids / tie order differ"
+
+
+# ----------------------------------------------------------------------------- PQ pieces and the flat AsymmetricHasher
+@pytest.mark.parametrize("S,C,ds", [(8, 16, 2), (5, 16, 3), (4, 256, 4)])
+def test_oracle_pq_encode_pack_lut_equal_python_restatement(oracle, S, C, ds):
+    rng = np.random.default_rng(S * 100 + C)
+    cb = (rng.integers(-3, 4, (S, C, ds)) * 0.5).astype(np.float32)  # coarse grid: equidistant codewords exist
+    cb[:, 3] = cb[:, 1]                                               # and exact duplicates: the LOWER code must win
+    x = (rng.integers(-3, 4, (60, S * ds)) * 0.5).astype(np.float32)
+    ocodes = oracle.pq_encode(cb, x)
+    want = np.array([rr.pq_encode(cb, r) for r in x], np.uint8)
+    assert (ocodes == want).all()
+    assert not (want == 3).any()
+    if C == 16:
+        assert (oracle.pack4(ocodes) == np.array([rr.pack4(list(r)) for r in want], np.uint8)).all()
+    q = (rng.standard_normal(S * ds) * 1.7).astype(np.float32)
+    olut = oracle.lut_f32(cb, q)
+    wlut = np.array(rr.lut_f32(cb, q), np.float32)
+    assert (olut.view(np.uint32) == wlut.view(np.uint32)).all()
+    od = oracle.lut_f32_scan(olut, ocodes)
+    wd = np.array([rr.lut_f32_distance(rr.lut_f32(cb, q), r) for r in want], np.float32)
+    assert (od.view(np.uint32) == wd.view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("k,pre_k", [(10, 0), (5, 25), (40, 40)])
+def test_oracle_asymmetric_hasher_equals_python_restatement(oracle, k, pre_k):
+    # flat AH: f32 LUT -> scan of all N -> FastTopNeighbors(k) [-> exact SqL2 re-rank of pre_reorder_k candidates]
+    rng = np.random.default_rng(k + pre_k)
+    S, C, ds, n = 6, 16, 2, 250
+    cb = (rng.integers(-3, 4, (S, C, ds)) * 0.5).astype(np.float32)
+    x = (rng.integers(-3, 4, (n, S * ds)) * 0.5).astype(np.float32)
+    codes = oracle.pq_encode(cb, x)
+    q = (rng.integers(-3, 4, (5, S * ds)) * 0.5).astype(np.float32)
+    rc, oids, odists, ocounts = oracle.ah_search(cb, codes, q, k, lut16=False, raw=x if pre_k else None, pre_k=pre_k,
+                                                 nthreads=2)
+    assert rc == 0
+    for i in range(len(q)):
+        want = (rr.ah_search_with_reordering(cb, codes, x, q[i], k, pre_k) if pre_k else rr.ah_search(cb, codes, q[i], k))
+        c = int(ocounts[i])
+        assert c == len(want)
+        wd = np.array([d for _, d in want], np.float32)
+        assert (odists[i, :c].view(np.uint32) == wd.view(np.uint32)).all()
+        assert oids[i, :c].tolist() == [j for j, _ in want], "ids / tie order differ"
+
+
+# ----------------------------------------------------------------------------- the Scann facade's tree modes
+def _facade_case(oracle, seed, n=400, dim=12, K=7, S=6):
+    rng = np.random.default_rng(seed)
+    x = (rng.integers(-4, 5, (n, dim)) * 0.5).astype(np.float32)
+    centers = x[rng.permutation(n)[:K]].copy()
+    tok = np.array([rr.partition(centers, r, 1)[0] for r in x])
+    order = np.argsort(tok, kind="stable").astype(np.uint32)
+    off = np.zeros(K + 1, np.uint64)
+    off[1:] = np.cumsum(np.bincount(tok, minlength=K))
+    cb = (rng.integers(-3, 4, (S, 16, dim // S)) * 0.5).astype(np.float32)
+    q = (rng.integers(-4, 5, (6, dim)) * 0.5).astype(np.float32)
+    return x, centers, off, order, cb, q
+
+
+@pytest.mark.parametrize("measure", ["sql2", "l2", "dot"])
+def test_oracle_scann_search_partitioned_equals_python_restatement(oracle, measure):
+    x, centers, off, order, cb, q = _facade_case(oracle, 5)
+    om = {"sql2": oracle.SQL2, "l2": oracle.L2, "dot": oracle.DOT}[measure]
+    L, k = 3, 15
+    rc, oids, odists, ocounts = oracle.scann_partitioned(centers, off, order, x, q, L, k, om, nthreads=2)
+    assert rc == 0
+    for i in range(len(q)):
+        want = rr.scann_search_partitioned(centers, off, order, x, q[i], L, k, measure)
+        c = int(ocounts[i])
+        assert c == len(want)
+        wd = np.array([d for _, d in want], np.float32)
+        assert (odists[i, :c].view(np.uint32) == wd.view(np.uint32)).all()
+        assert oids[i, :c].tolist() == [j for j, _ in want], "ids / tie order differ"
+
+
+@pytest.mark.parametrize("reorder", [None, "sql2", "dot"])
+def test_oracle_scann_search_tree_ah_equals_python_restatement(oracle, reorder):
+    x, centers, off, order, cb, q = _facade_case(oracle, 6)
+    codes = oracle.pq_encode(cb, x)
+    L, k = 3, 12
+    om = -1 if reorder is None else {"sql2": oracle.SQL2, "dot": oracle.DOT}[reorder]
+    rc, oids, odists, ocounts = oracle.scann_tree_ah(centers, off, order, cb, codes, x if reorder else None, q, L, k,
+                                                     reorder_measure=om, nthreads=2)
+    assert rc == 0
+    for i in range(len(q)):
+        want = rr.scann_search_tree_ah(centers, off, order, cb, codes, q[i], L, k)
+        if reorder:
+            want = rr.reordering_helper(x, q[i], want, k, reorder)
+        c = int(ocounts[i])
+        assert c == len(want)
+        wd = np.array([d for _, d in want], np.float32)
+        assert (odists[i, :c].view(np.uint32) == wd.view(np.uint32)).all()
+        assert oids[i, :c].tolist() == [j for j, _ in want], "ids / tie order differ"
+
+
+# ----------------------------------------------------------------------------- KMeansTree::search_leaves
+@pytest.mark.parametrize("seed,dim,fanout,depth_max,k", [(1, 3, 4, 4, 1), (2, 2, 5, 3, 3), (7, 3, 4, 5, 8), (4, 1, 6, 3, 2), (9, 2, 3, 6, 20)])
+def test_oracle_kmtree_search_leaves_equals_python_restatement(oracle, seed, dim, fanout, depth_max, k):
+    import test_kmtree
+    rng = np.random.default_rng(seed)
+    centers, depth, cb, cc, ch = test_kmtree.random_tree(rng, dim, fanout, depth_max)
+    centers = np.round(centers).astype(np.float32)  # integer grid: equal child distances, so the stable orders matter
+    q = np.round(rng.standard_normal((12, dim))).astype(np.float32)
+    nodes, dists, depths, counts = oracle.kmtree_search_leaves(centers, depth, cb, cc, ch, q, k)
+    ties = 0
+    for i in range(len(q)):
+        want = rr.kmtree_search_leaves(centers, depth, cb, cc, ch, q[i], k)
+        c = int(counts[i])
+        assert c == len(want)
+        assert nodes[i, :c].tolist() == [n for n, _, _ in want]
+        wd = np.array([d for _, d, _ in want], np.float32)
+        assert (dists[i, :c].view(np.uint32) == wd.view(np.uint32)).all()
+        assert depths[i, :c].tolist() == [d for _, _, d in want]
+        alld = [float(rr.sqdist_seq(q[i], c)) for c in centers]
+        ties += len(alld) - len(set(alld))
+    assert ties > 0, "the grid was meant to give equal centre distances (stable child order / final sort exercised)"
