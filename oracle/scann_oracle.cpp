@@ -12,7 +12,11 @@
 // End-to-end outputs of the reference itself could not be generated here: beyond those KATs the
 // parity is "pinned by KATs only".  Tie order inside exact-distance ties (BinaryHeap drain order,
 // FastTopNeighbors eviction slot) is restated from Rust std semantics but is not pinned by any
-// reference test.
+// reference test.  What holds this file beyond the KATs: a second, independent restatement of every hot-path row in
+// Python, written from the Rust source (tests/ref_restatement.py; exact fused multiply-add, BinaryHeap sift algorithms,
+// FastTopNeighbors slot replacement, stable sorts) — tests/test_oracle_cross_restatement.py requires this library to
+// equal it bit for bit, ids, distances and tie ORDER, on tie-saturated inputs.  Two restatements agreeing is still not
+// reference output.
 //
 // Build: g++ -O2 -std=c++17 -mavx2 -mfma -ffp-contract=off -fPIC -shared (see oracle/Makefile).
 // -ffp-contract=off is REQUIRED: scalar Rust never fuses a*b+c; FMA appears only where the

@@ -1,7 +1,10 @@
-"""TEST INFRASTRUCTURE.  A SECOND, independent restatement of the approximate stage of Tree-AH in plain Python / numpy
-scalars, written from the Rust source (not from oracle/scann_oracle.cpp), used to cross-check the C++ oracle on small
-cases: if two independent restatements agree bit for bit — distances, ids AND tie order — a transcription mistake in either
-would have to be made twice.  (Neither is output of the reference itself: the crate cannot be built in this image.)
+"""TEST INFRASTRUCTURE.  A SECOND, independent restatement of the reference's hot path in plain Python / numpy scalars,
+written from the Rust source (not from oracle/scann_oracle.cpp), used to cross-check the C++ oracle on small cases: if two
+independent restatements agree bit for bit — distances, ids AND tie order — a transcription mistake in either would have
+to be made twice.  (Neither is output of the reference itself: the crate cannot be built in this image.)  First the
+approximate stage of Tree-AH; further down the AVX2 + FMA distance kernels with an exact fused multiply-add, the exact
+reorder, the brute-force searchers, the PQ pieces, the flat AsymmetricHasher, the facade's tree modes and KMeansTree —
+each block names the Rust lines it follows.
 
 Follows, line for line:
   TreePartitioner::partition          src/partitioning/tree_partitioner.rs:175-229  (sequential f32 sum of d*d, stable sort)
