@@ -93,8 +93,9 @@ class FastTopNeighbors:
         return sorted(zip(self.idx, self.dist), key=lambda t: t[1])  # stable
 
 
-def approx_candidates(centers, codebook, part_offsets, ids, packed, q, L, R, use_residuals=True):
-    """-> [(datapoint index, approximate distance)] in the order search_with_filter hands to reorder_results"""
+def approx_candidates(centers, codebook, part_offsets, ids, packed, q, L, R, use_residuals=True, allow=None):
+    """-> [(datapoint index, approximate distance)] in the order search_with_filter hands to reorder_results.
+    allow: optional RestrictFilter as a set of allowed datapoint ids (checked before the push, tree_x_hybrid/mod.rs:325-331)"""
     S = codebook.shape[0]
     bpp = (S + 1) // 2
     allr = []
@@ -104,6 +105,8 @@ def approx_candidates(centers, codebook, part_offsets, ids, packed, q, L, R, use
         bias_total = F(bias * F(S))
         top = FastTopNeighbors(R)
         for row in range(int(part_offsets[leaf]), int(part_offsets[leaf + 1])):
+            if allow is not None and int(ids[row]) not in allow:
+                continue
             total, sub = 0, 0
             for b in range(bpp):
                 byte = int(packed[row, b])
@@ -486,3 +489,13 @@ def kmtree_search_leaves(centers, depth, child_begin, child_count, children, q, 
     rec(0)
     results.sort(key=lambda t: t[1])
     return results[:k]
+
+
+def bf_search_radius(db, q, radius, measure):
+    """BruteForceSearcher::search_radius (src/brute_force/searcher.rs:142-167): every row with d <= radius, stable sort"""
+    d = one_to_many_f32(q, db, "dot" if measure == "dot" else "sql2")
+    if measure == "l2":
+        d = np.sqrt(d).astype(np.float32)
+    res = [(i, v) for i, v in enumerate(d) if v <= F(radius)]
+    res.sort(key=lambda t: t[1])
+    return res

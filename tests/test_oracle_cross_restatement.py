@@ -324,3 +324,43 @@ def test_oracle_kmtree_search_leaves_equals_python_restatement(oracle, seed, dim
         alld = [float(rr.sqdist_seq(q[i], c)) for c in centers]
         ties += len(alld) - len(set(alld))
     assert ties > 0, "the grid was meant to give equal centre distances (stable child order / final sort exercised)"
+
+
+# ----------------------------------------------------------------------------- restrict filter, radius search
+@pytest.mark.parametrize("keep", [0.05, 0.5, 0.97])
+def test_oracle_search_with_filter_equals_python_restatement(oracle, keep):
+    n, dim, K, S, L, R, k, seed = 900, 16, 5, 8, 4, 20, 8, 21
+    x, _ = helpers.clustered(n, dim, 8, 0.4, seed, normalize=False)
+    x = (np.round(x * 2) / 2).astype(np.float32)
+    idx = helpers.build_index(oracle, x, K, S, seed=seed, iters=4)
+    q = (x[::max(1, n // 6)][:6] + np.float32(0.25)).astype(np.float32)
+    mask = np.random.default_rng(int(keep * 100)).random(n) < keep
+    bits = np.packbits(mask, bitorder="little")
+    rc, oids, odists, ocounts, ocand, ocd, ocn = oracle.treex_search(
+        idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"], x, q, L, R, k, lut16=True,
+        want_candidates=True, allow=bits)
+    assert rc == 0
+    allowed = set(np.nonzero(mask)[0].tolist())
+    for i in range(len(q)):
+        cand = rr.approx_candidates(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"], q[i],
+                                    L, R, allow=allowed)
+        c = int(ocn[i])
+        assert c == len(cand) and ocand[i, :c].tolist() == [j for j, _ in cand]
+        assert all(j in allowed for j in ocand[i, :c].tolist())
+        want = rr.reorder_results(x, q[i], [j for j, _ in cand], k, "sql2")
+        m = int(ocounts[i])
+        assert oids[i, :m].tolist() == [j for j, _ in want]
+        assert (odists[i, :m].view(np.uint32) == np.array([d for _, d in want], np.float32).view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("measure,radius", [("sql2", 16.0), ("l2", 4.0), ("dot", -2.0), ("sql2", -1.0)])
+def test_oracle_search_radius_equals_python_restatement(oracle, measure, radius):
+    rng = np.random.default_rng(31)
+    db = rng.integers(-2, 3, (250, 9)).astype(np.float32)
+    q = rng.integers(-2, 3, 9).astype(np.float32)
+    om = {"sql2": oracle.SQL2, "l2": oracle.L2, "dot": oracle.DOT}[measure]
+    oi, od = oracle.bf_search_radius(db, q, radius, om)
+    want = rr.bf_search_radius(db, q, radius, measure)
+    assert oi.tolist() == [j for j, _ in want]
+    assert (od.view(np.uint32) == np.array([d for _, d in want], np.float32).view(np.uint32)).all()
+    assert (len(want) > 10) == (radius > 0 or measure == "dot")  # the cases really select something (or nothing)
