@@ -5,7 +5,8 @@ Provenance: the reference (sunbains/scann-rust) is a Rust crate that cannot be b
 golden-vector files, so these vectors are outputs of the CPU ORACLE (oracle/scann_oracle.cpp — the restatement that is
 pinned against the reference's own known-answer tests, tests/test_oracle_kat.py) on small seeded inputs.  They freeze
 that behaviour: tests/test_golden.py checks that the oracle still reproduces them (CPU) and that the CUDA path matches
-them (GPU), independently of the live oracle-vs-GPU comparisons in the other test files.
+them (GPU), independently of the live oracle-vs-GPU comparisons in the other test files; the second, independent restatement
+(tests/ref_restatement.py) must reproduce them as well, without the oracle in the loop.
 
 Run from the repo root:  python tests/golden/make_golden.py
 """
