@@ -364,3 +364,45 @@ def test_oracle_search_radius_equals_python_restatement(oracle, measure, radius)
     assert oi.tolist() == [j for j, _ in want]
     assert (od.view(np.uint32) == np.array([d for _, d in want], np.float32).view(np.uint32)).all()
     assert (len(want) > 10) == (radius > 0 or measure == "dot")  # the cases really select something (or nothing)
+
+
+# ----------------------------------------------------------------------------- randomised sweep
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_equals_python_restatement_random_sweep(oracle, seed):
+    """Random small configurations (sizes, dims with and without an 8-lane tail, k around and above n, grid coarseness):
+    brute force (three measures) and Tree-AH end to end, ids + distances + tie order."""
+    rng = np.random.default_rng(1000 + seed)
+    n, dim = int(rng.integers(3, 120)), int(rng.choice([3, 8, 11, 16, 20]))
+    k = int(rng.integers(1, n + 5))
+    step = float(rng.choice([0.25, 0.5, 1.0]))
+    db = (rng.integers(-3, 4, (n, dim)) * step).astype(np.float32)
+    q = (rng.integers(-3, 4, (3, dim)) * step).astype(np.float32)
+    for measure, om in (("sql2", oracle.SQL2), ("l2", oracle.L2), ("dot", oracle.DOT)):
+        rc, oids, odists, ocounts = oracle.bf_search(db, q, k, om, nthreads=1)
+        for i in range(len(q)):
+            want = rr.bf_search(db, q[i], k, measure)
+            c = int(ocounts[i])
+            assert c == len(want)
+            assert oids[i, :c].tolist() == [j for j, _ in want]
+            assert (odists[i, :c].view(np.uint32) == np.array([d for _, d in want], np.float32).view(np.uint32)).all()
+    # Tree-AH on a separate index: S divides dim, K partitions by nearest of K random rows
+    S = int(rng.choice([2, 4]))
+    dim2 = S * int(rng.integers(1, 4))
+    n2 = int(rng.integers(40, 300))
+    x = (rng.integers(-3, 4, (n2, dim2)) * step).astype(np.float32)
+    K = int(rng.integers(2, 6))
+    idx = helpers.build_index(oracle, x, K, S, seed=seed, iters=3)
+    L, R, kk = int(rng.integers(1, K + 1)), int(rng.integers(1, 40)), int(rng.integers(1, 15))
+    qq = (rng.integers(-3, 4, (3, dim2)) * step).astype(np.float32)
+    for measure, om in (("sql2", oracle.SQL2), ("dot", oracle.DOT)):
+        rc, oids, odists, ocounts = oracle.treex_search(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"],
+                                                        idx["packed"], x, qq, L, R, kk, lut16=True, reorder_measure=om)
+        assert rc == 0
+        for i in range(len(qq)):
+            cand = rr.approx_candidates(idx["centers"], idx["codebook"], idx["part_offsets"], idx["ids"], idx["packed"],
+                                        qq[i], L, R)
+            want = rr.reorder_results(x, qq[i], [j for j, _ in cand], kk, measure)
+            c = int(ocounts[i])
+            assert c == len(want)
+            assert oids[i, :c].tolist() == [j for j, _ in want]
+            assert (odists[i, :c].view(np.uint32) == np.array([d for _, d in want], np.float32).view(np.uint32)).all()
